@@ -1,0 +1,285 @@
+"""Benchmark of the GCC-NMF separation hot path on B200 (contract: see the task statement).
+
+Workload (`config.workload`): BASELINE.json configs[1] -- offline enhancement of synthetic 30 s
+stereo @ 16 kHz, 1024-FFT, hop 256, K=1024 atoms, 64 TDOAs, 100 KL-NMF iterations: 1872 stereo
+STFT frames per 30 s clip.  A "step" is one pass of the whole pipeline (STFT -> GCC-PHAT angular
+spectrogram -> KL-NMF -> all-TDOA GCC-NMF argmax mask -> masked reconstruction -> iSTFT) over one clip.
+
+  value  frames/s with the clip already resident in HBM (CUDA events around each step)
+  e2e    frames/s through the public host-buffer call (`GCCNMFPipeline.enhance_host`): pinned host
+         samples -> H2D -> pipeline -> D2H of the separated signals, all inside the timed region
+  N > 1  one long recording of N x 30 s, frame-sharded over the ranks, ONE dictionary learnt jointly
+         (an all-reduce of the (F x K + K) W-update numerator per KL-NMF iteration); weak scaling.
+
+`--impl reference` times the reference's own CPU algorithm (the numpy oracle port: the reference is
+pure Python and /root/reference does not exist on the GPU box) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(sampleRate=16000, windowSize=1024, hopSize=256, dictionarySize=1024, numTDOAs=64,
+           numIterations=100, microphoneSeparationInMetres=0.1, duration_s=30.0)
+METRIC = 'STFT frames/sec (1024-FFT, K=1024) full GCC-NMF pipeline'
+UNIT = 'frames/s'
+
+
+def workload_config(n_gpus):
+    return {'workload': 'BASELINE.json configs[1]: offline enhancement, synthetic 30 s stereo @16 kHz per GPU, '
+                        '1024-FFT hop=256, K=1024, 64 TDOAs, 100 KL-NMF iterations (1872 frames per clip)',
+            'frames_per_step': 1872 * n_gpus, 'sharding': 'frames' if n_gpus > 1 else 'none',
+            'l2': 'L2 flushed (256 MiB write) between timed steps, flush excluded from the step events',
+            'nmf_init': 'seeded numpy draw (gccNMFFunctions.py:70-73) made once per shape at plan time, copied on device per step'}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        # under-load samples: the upper half of the observed SM clocks
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {'sm_mhz': float(np.median(load)) if load else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(sample_seconds=3.0, repeats=1):
+    """The oracle port of the reference numpy path (offlineSpeechEnhancement.ipynb cells 12-41 order)
+    timed on this box's host cores on a bounded sample of the same workload."""
+    from oracle import gccnmf_oracle as orc
+    from gcc_nmf_b200.synth import synthetic_stereo
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [(i.get('internal_api'), i.get('num_threads')) for i in threadpool_info()]
+    except Exception:
+        blas = []
+    x = synthetic_stereo(CFG['duration_s'])[:, :int(sample_seconds * CFG['sampleRate'])]
+    frames = 1 + (x.shape[1] - CFG['windowSize']) // CFG['hopSize']
+    best, stages = None, None
+    for _ in range(repeats):
+        tm = {}
+        t0 = time.perf_counter()
+        orc.runEnhancement(x, CFG['sampleRate'], CFG['windowSize'], CFG['hopSize'], CFG['numTDOAs'],
+                           CFG['microphoneSeparationInMetres'], CFG['dictionarySize'], CFG['numIterations'], timings=tm)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, stages = dt, tm
+    return {'value': frames / best, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': '%.1f s of the same synthetic clip (%d frames), same N/hop/K/D/iterations; %.2f s of CPU work; '
+                      'numpy %s, BLAS threads %s' % (sample_seconds, frames, best, np.__version__, blas),
+            'seconds': best, 'frames': frames, 'stage_seconds': {k: round(v, 3) for k, v in stages.items()}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sample_s = 3.0
+    vals = []
+    for i in range(args.warmup + args.steps):
+        b = cpu_baseline(sample_s)
+        if i >= args.warmup:
+            vals.append(b)
+    v = float(np.mean([b['value'] for b in vals]))
+    sec = float(np.mean([b['seconds'] for b in vals]))
+    b = vals[-1]
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(1),
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': b['cores'], 'kind': 'port', 'sample': b['sample'],
+                         'stage_seconds': b['stage_seconds']},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', d.get('bf16_tflops')), d.get('hbm_gbs'), 'measured (MEASURED_PEAKS.json, sustained bf16)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from gcc_nmf_b200.synth import synthetic_stereo
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torch.distributed.run --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    frames_per_clip = 1 + (int(CFG['duration_s'] * CFG['sampleRate']) - CFG['windowSize']) // CFG['hopSize']
+    if world == 1:
+        from gcc_nmf_b200.pipeline import GCCNMFPipeline
+        pipe = GCCNMFPipeline(CFG['sampleRate'], CFG['windowSize'], CFG['hopSize'], CFG['numTDOAs'],
+                              CFG['microphoneSeparationInMetres'], CFG['dictionarySize'], CFG['numIterations'], device=local)
+        x_host = torch.from_numpy(synthetic_stereo(CFG['duration_s'])).pin_memory()
+        step_dev = lambda xd, st=False: pipe.enhance(xd, collect_stage_times=st)   # noqa: E731
+        step_host = lambda out: pipe.enhance_host(x_host, out)                      # noqa: E731
+        total_frames = frames_per_clip
+    else:
+        from gcc_nmf_b200.distributed import ShardedGCCNMFPipeline
+        pipe = ShardedGCCNMFPipeline(CFG['sampleRate'], CFG['windowSize'], CFG['hopSize'], CFG['numTDOAs'],
+                                     CFG['microphoneSeparationInMetres'], CFG['dictionarySize'], CFG['numIterations'],
+                                     device=local, clip_seconds=CFG['duration_s'])
+        x_host = torch.from_numpy(pipe.local_samples()).pin_memory()
+        step_dev = lambda xd, st=False: pipe.enhance(xd, collect_stage_times=st)   # noqa: E731
+        step_host = lambda out: pipe.enhance_host(x_host, out)                      # noqa: E731
+        total_frames = pipe.total_frames
+    h = pipe.h
+    x_dev = x_host.to(h.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=h.device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        r = step_dev(x_dev)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = h.launches
+    step_ms, stage_ms = [], {}
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = step_dev(x_dev, True)
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        for k, v in pipe.stage_times_ms().items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / args.steps
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = h.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=h.device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = total_frames * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer API
+    out_host = None
+    for _ in range(max(args.warmup, 3)):
+        out_host = step_host(out_host)
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out_host = step_host(out_host)
+        e1.record()
+        e1.synchronize()
+        e2e_ms.append(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    barrier()
+    e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=h.device)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_value = total_frames * args.steps / (float(e2e_total.item()) * 1e-3)
+
+    if rank == 0:
+        F, K, I = CFG['windowSize'] // 2 + 1, CFG['dictionarySize'], CFG['numIterations']
+        T_local = frames_per_clip
+        nmf_ms = stage_ms.get('nmf', float('nan'))
+        flops_per_iter = 16.0 * F * K * T_local            # 4 GEMMs x 2 F K (2T) per iteration
+        achieved = flops_per_iter * I / (nmf_ms * 1e-3) / 1e12
+        peak_tf, peak_hbm, peak_src = load_peaks()
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world),
+            'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
+            'wall_s_timed_region': wall, 'gpu_launches': int(launches), 'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(x_host.numel() * 4),
+                    'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': float(e2e_total.item()) / args.steps},
+            'roofline': {'kernel': 'KL-NMF iteration (W.H with fused V/(W.H), W^T.R, R.H^T GEMMs + updates), per rank',
+                         'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                         'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                         'algorithmic_flops_per_launch_group': flops_per_iter, 'ms_per_iteration': nmf_ms / I,
+                         'note': 'algorithmic flops 16 F K T per iteration / CUDA-event time of the NMF stage inside the step'},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline(3.0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,275 @@
+"""ctypes binding of libgccnmf_b200.so (the C ABI declared in include/gccnmf_b200.h).
+
+PyTorch is used only as the device container (allocation, streams); every numeric op on the hot
+path is one of the library's sm_100a kernels.  There is NO CPU fallback: importing this module
+without the built library, or creating a handle without a CUDA device, raises.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libgccnmf_b200.so')
+
+
+class GCCNMFError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+class ParameterError(Exception):
+    """Mirror of gccNMF/librosaSTFT.py:292-294 (mal-formed inputs)."""
+
+
+GCCNMF_OK = 0
+GCCNMF_ERR_INVALID_ARGUMENT = -1
+GCCNMF_ERR_CUDA = -2
+GCCNMF_ERR_WORKSPACE = -3
+GCCNMF_ERR_UNSUPPORTED = -4
+GCCNMF_ERR_NO_DEVICE = -5
+
+_H = c_void_p   # gccnmf_handle*
+_P = c_void_p   # device pointer
+_S = c_void_p   # cudaStream_t
+
+# name -> (restype, argtypes); must list every symbol of include/gccnmf_b200.h (tests check this)
+SIGNATURES = {
+    'gccnmf_abi_version': (c_int, []),
+    'gccnmf_create': (c_int, [ctypes.POINTER(c_void_p), c_int]),
+    'gccnmf_destroy': (c_int, [_H]),
+    'gccnmf_last_error': (c_char_p, [_H]),
+    'gccnmf_status_string': (c_char_p, [c_int]),
+    'gccnmf_launch_count': (c_int64, [_H]),
+    'gccnmf_stft_num_frames': (c_int, [c_int64, c_int, c_int]),
+    'gccnmf_stft': (c_int, [_H, _P, c_int64, c_int, c_int64, _P, c_int, c_int, c_int, _P, _P, _S]),
+    'gccnmf_istft_length': (c_int64, [c_int, c_int, c_int, c_int]),
+    'gccnmf_istft_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'gccnmf_istft_ola': (c_int, [_H, _P, c_int, c_int, c_int, c_int, _P, c_float, c_int, c_int, _P, _P, c_size_t, _S]),
+    'gccnmf_klnmf_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'gccnmf_klnmf': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_int, c_float, c_float, c_int, _P, c_size_t, _S]),
+    'gccnmf_klnmf_update_H': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, _P, c_size_t, _S]),
+    'gccnmf_klnmf_partial_W': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
+    'gccnmf_klnmf_apply_W': (c_int, [_H, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
+    'gccnmf_phat_angspec_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'gccnmf_phat_angspec': (c_int, [_H, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _S]),
+    'gccnmf_tdoa_gccnmf': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _S]),
+    'gccnmf_coeff_mask': (c_int, [_H, _P, c_int, c_int, c_int, _P, _P, _S]),
+    'gccnmf_argmax_mask': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, _S]),
+    'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library and declare every signature.  Raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('%s is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(or python gcc-nmf_b200/build.py).  There is no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'device-resident contiguous tensor required'
+    return t.data_ptr()
+
+
+class Handle(object):
+    """Owns one gccnmf_handle bound to a CUDA device; all methods enqueue on torch's current stream."""
+
+    def __init__(self, device=0):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise GCCNMFError('no CUDA device visible: gcc-nmf_b200 has no CPU fallback')
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)   # make sure the primary context exists before the library binds to it
+        h = c_void_p()
+        st = self.lib.gccnmf_create(ctypes.byref(h), self.device.index)
+        if st != GCCNMF_OK:
+            raise GCCNMFError('gccnmf_create failed (%s): %s' % (self.lib.gccnmf_status_string(st).decode(),
+                                                                 self.lib.gccnmf_last_error(None).decode()))
+        self.h = h
+        self._workspaces = {}
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.gccnmf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def launches(self):
+        return int(self.lib.gccnmf_launch_count(self.h))
+
+    def check(self, status):
+        if status == GCCNMF_OK:
+            return
+        msg = self.lib.gccnmf_last_error(self.h).decode()
+        if status == GCCNMF_ERR_INVALID_ARGUMENT:
+            raise ParameterError(msg)
+        raise GCCNMFError('%s: %s' % (self.lib.gccnmf_status_string(status).decode(), msg))
+
+    def workspace(self, key, nbytes):
+        """Caller-owned scratch, cached per purpose and grown on demand."""
+        ws = self._workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.device)
+            self._workspaces[key] = ws
+        return ws
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, array, dtype=None):
+        t = self.torch.as_tensor(array)
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.contiguous().to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ ops (device tensors in / out)
+    def stft(self, samples, window, n_fft, hop, conjugate=True, want_V=False):
+        """samples (C, n) f32 cuda, window (n_fft) f64 cuda -> X (C, F, T) c64 [, V (F, C*T) f32]."""
+        torch = self.torch
+        C, n = samples.shape
+        T = self.lib.gccnmf_stft_num_frames(n, n_fft, hop)
+        if T < 1:
+            if hop < 1:
+                raise ParameterError('Invalid hop_length: %d' % hop)
+            raise ParameterError('Buffer is too short (n=%d) for frame_length=%d' % (n, n_fft))
+        F = n_fft // 2 + 1
+        X = self.empty((C, F, T), torch.complex64)
+        V = self.empty((F, C * T), torch.float32) if want_V else None
+        self.check(self.lib.gccnmf_stft(self.h, _ptr(samples), samples.stride(0), C, n, _ptr(window), n_fft, hop,
+                                        1 if conjugate else 0, _ptr(X), _ptr(V), self.stream))
+        return (X, V) if want_V else X
+
+    def istft_ola(self, spec, window, n_fft, hop, gain=1.0, center=True, conjugate=True):
+        """spec (B, F, T) c64 cuda -> y (B, length) f32."""
+        torch = self.torch
+        B, F, T = spec.shape
+        length = self.lib.gccnmf_istft_length(n_fft, hop, T, 1 if center else 0)
+        y = self.empty((B, max(int(length), 0)), torch.float32)
+        nbytes = self.lib.gccnmf_istft_workspace_bytes(B, n_fft, T)
+        ws = self.workspace('istft', nbytes)
+        self.check(self.lib.gccnmf_istft_ola(self.h, _ptr(spec), B, n_fft, hop, T, _ptr(window), float(gain),
+                                             1 if center else 0, 1 if conjugate else 0, _ptr(y), _ptr(ws), ws.numel(),
+                                             self.stream))
+        return y
+
+    def klnmf(self, V, W, H, iterations, sparsity_alpha=0.0, epsilon=1e-16, update_W=True):
+        """In place on W (F, K), H (K, T2) f32 cuda."""
+        F, T2 = V.shape
+        K = W.shape[1]
+        ws = self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
+        self.check(self.lib.gccnmf_klnmf(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, int(iterations),
+                                         float(sparsity_alpha), float(epsilon), 1 if update_W else 0, _ptr(ws),
+                                         ws.numel(), self.stream))
+        return W, H
+
+    def klnmf_update_H(self, V, W, H, sparsity_alpha=0.0, epsilon=1e-16):
+        F, T2 = V.shape
+        K = W.shape[1]
+        ws = self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
+        self.check(self.lib.gccnmf_klnmf_update_H(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, float(sparsity_alpha),
+                                                  float(epsilon), _ptr(ws), ws.numel(), self.stream))
+
+    def klnmf_partial_W(self, V, W, H, numer):
+        F, T2 = V.shape
+        K = W.shape[1]
+        ws = self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
+        self.check(self.lib.gccnmf_klnmf_partial_W(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, _ptr(numer), _ptr(ws),
+                                                   ws.numel(), self.stream))
+
+    def klnmf_apply_W(self, W, H, numer):
+        F, K = W.shape
+        T2 = H.shape[1]
+        ws = self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
+        self.check(self.lib.gccnmf_klnmf_apply_W(self.h, F, T2, _ptr(W), _ptr(H), K, _ptr(numer), _ptr(ws), ws.numel(),
+                                                 self.stream))
+
+    def phat_angspec(self, X, E=None, want_coherence=True, want_angular=True, want_mean=True):
+        """X (2, F, T) c64 mixture spectrogram -- or an (F, T) c64 coherence used as is -- and
+        E (F, D) c128 -> (coherence (F,T) c64, angular (D,T) f64, mean (D) f64)."""
+        torch = self.torch
+        is_coh = X.dim() == 2
+        F, T = X.shape[-2:]
+        D = E.shape[1] if E is not None else 0
+        coh = self.empty((F, T), torch.complex64) if want_coherence else None
+        ang = self.empty((D, T), torch.float64) if (want_angular and D) else None
+        mean = self.empty((D,), torch.float64) if (want_mean and D) else None
+        ws = self.workspace('angspec', self.lib.gccnmf_phat_angspec_workspace_bytes(F, T, max(D, 1)))
+        self.check(self.lib.gccnmf_phat_angspec(self.h, _ptr(X), F, T, 1 if is_coh else 0, _ptr(E), D, _ptr(coh), _ptr(ang), _ptr(mean),
+                                                _ptr(ws), ws.numel(), self.stream))
+        return coh, ang, mean
+
+    def tdoa_gccnmf(self, coherence, E, W, want_values=False, want_argmax=True):
+        """coherence (F,T) c64, E (F,D) c128, W (F,K) f32 -> (values (D,K,T) f32 | None, argmax (K,T) i32 | None)."""
+        torch = self.torch
+        F, T = coherence.shape
+        D = E.shape[1]
+        K = W.shape[1]
+        values = self.empty((D, K, T), torch.float32) if want_values else None
+        argmax = self.empty((K, T), torch.int32) if want_argmax else None
+        self.check(self.lib.gccnmf_tdoa_gccnmf(self.h, _ptr(coherence), F, T, _ptr(E), D, _ptr(W), K, _ptr(values),
+                                               _ptr(argmax), self.stream))
+        return values, argmax
+
+    def coeff_mask(self, gccnmfs):
+        torch = self.torch
+        S, K, T = gccnmfs.shape
+        masks = self.empty((S, K, T), torch.float32)
+        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.check(self.lib.gccnmf_coeff_mask(self.h, _ptr(gccnmfs), S, K, T, _ptr(masks), _ptr(flag), self.stream))
+        return masks, flag
+
+    def argmax_mask(self, argmax, lut):
+        torch = self.torch
+        K, T = argmax.shape
+        mask = self.empty((K, T), torch.float32)
+        self.check(self.lib.gccnmf_argmax_mask(self.h, _ptr(argmax), K, T, _ptr(lut), lut.numel(), _ptr(mask), self.stream))
+        return mask
+
+    def masked_recon_phase(self, masks, X, W, H):
+        """masks (S,K,T) f32, X (2,F,T) c64, W (F,K), H (K,2T) -> (S,2,F,T) c64."""
+        torch = self.torch
+        S, K, T = masks.shape
+        F = X.shape[1]
+        out = self.empty((S, 2, F, T), torch.complex64)
+        self.check(self.lib.gccnmf_masked_recon_phase(self.h, _ptr(masks), _ptr(X), _ptr(W), _ptr(H), S, F, T, K,
+                                                      _ptr(out), self.stream))
+        return out
+
+
+_default_handles = {}
+
+
+def default_handle(device=0):
+    """Process-wide handle per device (created lazily; raises without a GPU)."""
+    h = _default_handles.get(device)
+    if h is None:
+        h = _default_handles[device] = Handle(device)
+    return h

@@ -1,0 +1,72 @@
+// Handle management for the gccnmf_b200 C ABI.  There is no CPU fallback: without a CUDA device
+// gccnmf_create fails with GCCNMF_ERR_NO_DEVICE.
+#include "common.cuh"
+
+namespace {
+thread_local std::string g_create_error = "no error";
+}
+
+extern "C" {
+
+int gccnmf_abi_version(void) { return GCCNMF_ABI_VERSION; }
+
+int gccnmf_create(gccnmf_handle** out, int device) {
+  if (!out) return GCCNMF_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    g_create_error = std::string("gccnmf_create: no CUDA device (") + cudaGetErrorString(err) + "); there is no CPU fallback";
+    return GCCNMF_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "gccnmf_create: device index out of range";
+    return GCCNMF_ERR_INVALID_ARGUMENT;
+  }
+  err = cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, device);
+  if (err != cudaSuccess) {
+    g_create_error = std::string("gccnmf_create: ") + cudaGetErrorString(err);
+    return GCCNMF_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "gccnmf_create: this library is built for sm_100a (B200) only, found compute capability " +
+                     std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    return GCCNMF_ERR_UNSUPPORTED;
+  }
+  gccnmf_handle* h = new gccnmf_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->last_error = "no error";
+  *out = h;
+  return GCCNMF_OK;
+}
+
+int gccnmf_destroy(gccnmf_handle* h) {
+  if (!h) return GCCNMF_OK;
+  for (int i = 0; i < gccnmf_handle::kMaxPlans; ++i) {
+    if (h->plan_tw64[i]) cudaFree(h->plan_tw64[i]);
+    if (h->plan_tw32[i]) cudaFree(h->plan_tw32[i]);
+  }
+  delete h;
+  return GCCNMF_OK;
+}
+
+const char* gccnmf_last_error(const gccnmf_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+const char* gccnmf_status_string(int status) {
+  switch (status) {
+    case GCCNMF_OK: return "ok";
+    case GCCNMF_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case GCCNMF_ERR_CUDA: return "CUDA error";
+    case GCCNMF_ERR_WORKSPACE: return "workspace missing or too small";
+    case GCCNMF_ERR_UNSUPPORTED: return "unsupported shape or device";
+    case GCCNMF_ERR_NO_DEVICE: return "no CUDA device (no CPU fallback)";
+    default: return "unknown status";
+  }
+}
+
+int64_t gccnmf_launch_count(const gccnmf_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

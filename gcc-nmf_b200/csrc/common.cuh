@@ -1,0 +1,77 @@
+// Shared host-side plumbing for the gccnmf_b200 C ABI: handle, error capture, launch counting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/gccnmf_b200.h"
+
+struct gccnmf_handle {
+  int device = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string last_error;
+  // twiddle tables e^{-2 pi i j / n}, j < n/2, float64 and float32, cached per FFT size
+  static constexpr int kMaxPlans = 8;
+  int plan_n[kMaxPlans] = {0};
+  double* plan_tw64[kMaxPlans] = {nullptr};
+  float* plan_tw32[kMaxPlans] = {nullptr};
+};
+
+inline int gccnmf_fail(gccnmf_handle* h, int status, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+#include <cstdarg>
+inline int gccnmf_fail(gccnmf_handle* h, int status, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->last_error = buf;
+  return status;
+}
+
+#define GCCNMF_CHECK_CUDA(h, expr)                                                              \
+  do {                                                                                          \
+    cudaError_t err__ = (expr);                                                                 \
+    if (err__ != cudaSuccess)                                                                   \
+      return gccnmf_fail((h), GCCNMF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                         cudaGetErrorString(err__), __FILE__, __LINE__);                        \
+  } while (0)
+
+// Every kernel launch goes through this so that launch errors are captured and counted.
+#define GCCNMF_LAUNCH(h, kernel, grid, block, smem, stream, ...)                                \
+  do {                                                                                          \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                   \
+    cudaError_t err__ = cudaGetLastError();                                                     \
+    if (err__ != cudaSuccess)                                                                   \
+      return gccnmf_fail((h), GCCNMF_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,      \
+                         cudaGetErrorString(err__), __FILE__, __LINE__);                        \
+    (h)->launches++;                                                                            \
+  } while (0)
+
+#define GCCNMF_REQUIRE(h, cond, ...)                                                            \
+  do {                                                                                          \
+    if (!(cond)) return gccnmf_fail((h), GCCNMF_ERR_INVALID_ARGUMENT, __VA_ARGS__);             \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Carves aligned sub-buffers out of a caller-owned workspace.
+struct WorkspaceCarver {
+  char* base;
+  size_t size, used = 0;
+  WorkspaceCarver(void* p, size_t n) : base(static_cast<char*>(p)), size(n) {}
+  template <typename T>
+  T* take(size_t count) {
+    used = align_up(used, 256);
+    T* p = reinterpret_cast<T*>(base + used);
+    used += count * sizeof(T);
+    return p;
+  }
+  bool ok() const { return base != nullptr && used <= size; }
+};
+
+int gccnmf_get_twiddles(gccnmf_handle* h, int n, const double** tw64, const float** tw32);

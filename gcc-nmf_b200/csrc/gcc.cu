@@ -1,0 +1,351 @@
+// GCC-PHAT localisation and GCC-NMF masking kernels.
+//   phat_angspec       runGCCNMF.py:44 + gccNMFFunctions.py:85-92      (a3, a4)
+//   tdoa_gccnmf        gccNMFFunctions.py:118-135; offlineSpeechEnhancement.ipynb:444-450; online :422  (a6, a10, a11)
+//   coeff_mask         gccNMFFunctions.py:137-143                        (a7)
+//   argmax_mask        offlineSpeechEnhancement.ipynb:466-472            (a10 mask)
+//   masked_recon_phase gccNMFFunctions.py:145-151                        (a8)
+// Contractions that the reference evaluates in complex128 / float64 are accumulated in float64 here
+// so that the integer decisions taken on them (peak picking, argmax over TDOA) are the reference's.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ a3 + a4: coherence + angular spectrogram
+constexpr int kAngT = 32;     // frames per block (one per lane)
+constexpr int kAngGroups = 8; // TDOA groups (one per warp)
+constexpr int kAngBF = 8;     // frequency bins staged per step
+constexpr int kAngMaxD = 128;
+
+// numpy's complex64 arithmetic for  X0 * conj(X1) / |X0| / |X1|  (runGCCNMF.py:44): float32 products,
+// magnitude correctly rounded (hypotf), division by a real done as multiplication by the float32
+// reciprocal (numpy's complex division with a zero imaginary divisor).
+__device__ __forceinline__ float2 phat_coherence(float2 a, float2 b) {
+  float re = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+  float im = __fsub_rn(__fmul_rn(a.y, b.x), __fmul_rn(a.x, b.y));
+  const float ma = (float)sqrt((double)a.x * a.x + (double)a.y * a.y);
+  const float mb = (float)sqrt((double)b.x * b.x + (double)b.y * b.y);
+  const float ia = 1.0f / ma, ib = 1.0f / mb;
+  re = __fmul_rn(re, ia); im = __fmul_rn(im, ia);
+  re = __fmul_rn(re, ib); im = __fmul_rn(im, ib);
+  return float2{re, im};
+}
+
+__global__ void __launch_bounds__(kAngT * kAngGroups)
+phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coherence, const double2* __restrict__ E, int D,
+                    float2* __restrict__ coherence, double* __restrict__ angular, double* __restrict__ tile_sums) {
+  __shared__ double2 Cs[kAngBF][kAngT];
+  __shared__ double2 Es[kAngBF][kAngMaxD];
+  const int lane = threadIdx.x % kAngT, group = threadIdx.x / kAngT;
+  const int t0 = blockIdx.x * kAngT;
+  const int t = t0 + lane;
+  constexpr int kMaxPerThread = kAngMaxD / kAngGroups;
+  double acc[kMaxPerThread];
+#pragma unroll
+  for (int j = 0; j < kMaxPerThread; ++j) acc[j] = 0.0;
+  const int per_thread = (D + kAngGroups - 1) / kAngGroups;
+
+  for (int f0 = 0; f0 < F; f0 += kAngBF) {
+    for (int e = threadIdx.x; e < kAngBF * kAngT; e += blockDim.x) {
+      const int ff = e / kAngT, tt = e % kAngT;
+      const int f = f0 + ff;
+      double2 c = double2{0.0, 0.0};
+      if (f < F && t0 + tt < T) {
+        const float2 coh = x_is_coherence ? X[(int64_t)f * T + t0 + tt]
+                                          : phat_coherence(X[(int64_t)f * T + t0 + tt], X[((int64_t)F + f) * T + t0 + tt]);
+        if (coherence) coherence[(int64_t)f * T + t0 + tt] = coh;
+        c = double2{(double)coh.x, (double)coh.y};
+      }
+      Cs[ff][tt] = c;
+    }
+    for (int e = threadIdx.x; e < kAngBF * D; e += blockDim.x) {
+      const int ff = e / D, d = e % D;
+      Es[ff][d] = (f0 + ff < F) ? E[(int64_t)(f0 + ff) * D + d] : double2{0.0, 0.0};
+    }
+    __syncthreads();
+    if (angular || tile_sums) {
+#pragma unroll 4
+      for (int ff = 0; ff < kAngBF; ++ff) {
+        const double2 c = Cs[ff][lane];
+#pragma unroll
+        for (int j = 0; j < kMaxPerThread; ++j) {
+          if (j < per_thread) {
+            const int d = group + j * kAngGroups;
+            if (d < D) {
+              const double2 e = Es[ff][d];
+              acc[j] += c.x * e.x - c.y * e.y;   // Re(C * E)
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxPerThread; ++j) {
+    if (j >= per_thread) break;
+    const int d = group + j * kAngGroups;
+    if (d >= D) continue;
+    const double v = (t < T) ? acc[j] : 0.0;
+    if (angular && t < T) angular[(int64_t)d * T + t] = v;
+    if (tile_sums) {
+      double s = v;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) tile_sums[(int64_t)blockIdx.x * D + d] = s;
+    }
+  }
+}
+
+__global__ void mean_tiles_kernel(const double* __restrict__ tile_sums, int tiles, int D, int T, double* __restrict__ mean) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double s = 0.0;
+  for (int i = 0; i < tiles; ++i) s += tile_sums[(int64_t)i * D + d];
+  mean[d] = s / (double)T;
+}
+
+// ------------------------------------------------------------------ a6 / a10 / a11: GCC-NMF per TDOA (float64 GEMM)
+constexpr int GM = 128, GN = 128, GK = 8, GTM = 8, GTN = 8;
+constexpr int kGccThreads = (GM / GTM) * (GN / GTN);
+
+struct LoadWAtoms {  // A(m = atom, k = f) = W[f][atom]
+  static constexpr bool kContigK = false;
+  const float* W; int K, F;
+  __device__ double operator()(int m, int f) const { return (m < K && f < F) ? (double)__ldg(W + (int64_t)f * K + m) : 0.0; }
+};
+struct LoadRealGCC {  // B(n = t * D + d, k = f) = Re(coherence[f][t] * E[f][d])
+  static constexpr bool kContigK = false;
+  const float2* coh; const double2* E; int F, T, D, N;
+  __device__ double operator()(int n, int f) const {
+    if (n >= N || f >= F) return 0.0;
+    const int t = n / D, d = n - t * D;
+    const float2 c = __ldg(coh + (int64_t)f * T + t);
+    const double2 e = __ldg(E + (int64_t)f * D + d);
+    return (double)c.x * e.x - (double)c.y * e.y;
+  }
+};
+
+// numpy.argmax ordering: NaN is a maximum, first occurrence wins.
+__device__ __forceinline__ bool argmax_better(double v, int i, double bv, int bi) {
+  const bool vn = isnan(v), bn = isnan(bv);
+  if (vn || bn) return vn && (!bn || i < bi);
+  return v > bv || (v == bv && i < bi);
+}
+
+template <bool ARGMAX>
+__global__ void __launch_bounds__(kGccThreads)
+tdoa_gccnmf_kernel(int K, int N, int F, LoadWAtoms aload, LoadRealGCC bload, int T, int D, float* __restrict__ values,
+                   int32_t* __restrict__ argmax) {
+  double acc[GTM][GTN];
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  gemm_simt_mainloop<double, GM, GN, GK, GTM, GTN>(acc, m0, n0, F, aload, bload);
+  constexpr int TX = GN / GTN;
+  if (values) {
+#pragma unroll
+    for (int i = 0; i < GTM; ++i) {
+      const int m = gemm_row<GM, GTM, TX>(m0, i);
+      if (m >= K) continue;
+#pragma unroll
+      for (int j = 0; j < GTN; ++j) {
+        const int n = gemm_col<GN, GTN, TX>(n0, j);
+        if (n >= N) continue;
+        const int t = n / D, d = n - t * D;
+        values[((int64_t)d * K + m) * T + t] = (float)acc[i][j];
+      }
+    }
+  }
+  if (ARGMAX) {
+    // D is a power of two in [4, 128] and divides GN, so n0 % D == 0 and every 4-column half-row of the
+    // register tile lies inside one frame.  D <= 64: a frame spans D/4 consecutive lanes of one half;
+    // D == 128: a frame is the whole tile row (both halves of all 16 lanes).
+    const int tx = threadIdx.x % TX;
+    const int lanes = min(D / 4, TX);
+#pragma unroll
+    for (int i = 0; i < GTM; ++i) {
+      const int m = gemm_row<GM, GTM, TX>(m0, i);
+      double bv[2];
+      int bi[2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int d0 = (half * (GN / 2) + tx * (GTN / 2)) % D;  // TDOA index of this half-row's first column
+        bv[half] = acc[i][half * (GTN / 2)];
+        bi[half] = d0;
+#pragma unroll
+        for (int j = 1; j < GTN / 2; ++j) {
+          const double v = acc[i][half * (GTN / 2) + j];
+          if (argmax_better(v, d0 + j, bv[half], bi[half])) { bv[half] = v; bi[half] = d0 + j; }
+        }
+      }
+      if (D == GN) {  // one frame per tile row: fold half 1 into half 0 before the lane reduction
+        if (argmax_better(bv[1], bi[1], bv[0], bi[0])) { bv[0] = bv[1]; bi[0] = bi[1]; }
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (D == GN && half == 1) break;
+        for (int o = 1; o < lanes; o <<= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv[half], o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi[half], o);
+          if (argmax_better(ov, oi, bv[half], bi[half])) { bv[half] = ov; bi[half] = oi; }
+        }
+        const int n_first = n0 + half * (GN / 2) + tx * (GTN / 2);
+        if ((tx % lanes) == 0 && m < K && n_first < N) argmax[(int64_t)m * T + n_first / D] = bi[half];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ a7: masks
+__global__ void coeff_mask_kernel(const float* __restrict__ G, int S, int64_t KT, float* __restrict__ masks, int32_t* all_nan_flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KT) return;
+  int best = -1;
+  float bv = 0.f;
+  for (int s = 0; s < S; ++s) {  // numpy.nanargmax: ignore NaN, first maximum wins
+    const float v = G[(int64_t)s * KT + i];
+    if (isnan(v)) continue;
+    if (best < 0 || v > bv) { best = s; bv = v; }
+  }
+  if (best < 0 && all_nan_flag) *all_nan_flag = 1;
+  for (int s = 0; s < S; ++s) masks[(int64_t)s * KT + i] = (s == best) ? 1.f : 0.f;
+}
+
+__global__ void argmax_mask_kernel(const int32_t* __restrict__ argmax, int64_t KT, const uint8_t* __restrict__ lut, int D, float* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KT) return;
+  const int a = argmax[i];
+  mask[i] = (a >= 0 && a < D && lut[a]) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------ a8: masked reconstruction with mixture phase
+constexpr int RM = 128, RN = 128, RK = 16, RTM = 8, RTN = 8;
+constexpr int kReconThreads = (RM / RTM) * (RN / RTN);
+
+struct LoadWRows {  // A(m = f, k = atom) = W[f][atom]
+  static constexpr bool kContigK = true;
+  const float* W; int F, K;
+  __device__ float operator()(int m, int k) const { return (m < F && k < K) ? __ldg(W + (int64_t)m * K + k) : 0.f; }
+};
+struct LoadMaskedH {  // B(n = t, k = atom) = H[atom][c*T + t] * mask[atom][t]   (gccNMFFunctions.py:150)
+  static constexpr bool kContigK = false;
+  const float* H; const float* mask; int K, T; int64_t ldh;
+  __device__ float operator()(int n, int k) const {
+    return (n < T && k < K) ? __ldg(H + (int64_t)k * ldh + n) * __ldg(mask + (int64_t)k * T + n) : 0.f;
+  }
+};
+
+__global__ void __launch_bounds__(kReconThreads)
+masked_recon_kernel(const float* __restrict__ masks, const float2* __restrict__ X, const float* __restrict__ W,
+                    const float* __restrict__ H, int F, int T, int K, float2* __restrict__ out) {
+  const int s = blockIdx.z / 2, c = blockIdx.z % 2;
+  float acc[RTM][RTN];
+  const int m0 = blockIdx.y * RM, n0 = blockIdx.x * RN;
+  LoadWRows a{W, F, K};
+  LoadMaskedH b{H + (int64_t)c * T, masks + (int64_t)s * K * T, K, T, (int64_t)2 * T};
+  gemm_simt_mainloop<float, RM, RN, RK, RTM, RTN>(acc, m0, n0, K, a, b);
+  const float2* Xc = X + (int64_t)c * F * T;
+  float2* o = out + ((int64_t)s * 2 + c) * F * T;
+#pragma unroll
+  for (int i = 0; i < RTM; ++i) {
+    const int m = gemm_row<RM, RTM, RN / RTN>(m0, i);
+    if (m >= F) continue;
+#pragma unroll
+    for (int j = 0; j < RTN; ++j) {
+      const int n = gemm_col<RN, RTN, RN / RTN>(n0, j);
+      if (n >= T) continue;
+      // exp(1j * angle(X)) (gccNMFFunctions.py:151): unit phasor of the mixture bin; angle(0) = 0.
+      const float2 x = Xc[(int64_t)m * T + n];
+      const double mag = sqrt((double)x.x * x.x + (double)x.y * x.y);
+      float pr = 1.f, pi = 0.f;
+      if (mag > 0.0) { pr = (float)((double)x.x / mag); pi = (float)((double)x.y / mag); }
+      else if (mag != mag) { pr = pi = __int_as_float(0x7fc00000); }
+      o[(int64_t)m * T + n] = float2{acc[i][j] * pr, acc[i][j] * pi};
+    }
+  }
+}
+
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+size_t gccnmf_phat_angspec_workspace_bytes(int F, int T, int D) {
+  (void)F;
+  if (T <= 0 || D <= 0) return 0;
+  return align_up((size_t)((T + kAngT - 1) / kAngT) * D * sizeof(double), 256);
+}
+
+int gccnmf_phat_angspec(gccnmf_handle* h, const float* X, int F, int T, int x_is_coherence, const double* expJOmegaTau, int D, float* coherence,
+                        double* angular, double* mean_angular, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, F > 0 && T > 0, "phat_angspec: F and T must be positive");
+  GCCNMF_REQUIRE(h, X != nullptr, "phat_angspec: NULL spectrogram");
+  const bool need_ang = angular || mean_angular;
+  if (need_ang) {
+    GCCNMF_REQUIRE(h, expJOmegaTau != nullptr && D > 0, "phat_angspec: TDOA table required");
+    if (D > kAngMaxD) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "phat_angspec: numTDOAs %d > %d", D, kAngMaxD);
+  }
+  double* tile_sums = nullptr;
+  const int tiles = (T + kAngT - 1) / kAngT;
+  if (mean_angular) {
+    if (!workspace || workspace_bytes < gccnmf_phat_angspec_workspace_bytes(F, T, D))
+      return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "phat_angspec workspace too small");
+    tile_sums = static_cast<double*>(workspace);
+  }
+  GCCNMF_LAUNCH(h, phat_angspec_kernel, tiles, kAngT * kAngGroups, 0, stream, reinterpret_cast<const float2*>(X), F, T, x_is_coherence,
+                reinterpret_cast<const double2*>(expJOmegaTau), need_ang ? D : 0, reinterpret_cast<float2*>(coherence),
+                angular, tile_sums);
+  if (mean_angular) GCCNMF_LAUNCH(h, mean_tiles_kernel, (D + 63) / 64, 64, 0, stream, tile_sums, tiles, D, T, mean_angular);
+  return GCCNMF_OK;
+}
+
+int gccnmf_tdoa_gccnmf(gccnmf_handle* h, const float* coherence, int F, int T, const double* E, int D, const float* W, int K,
+                       float* values, int32_t* argmax, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, F > 0 && T > 0 && D > 0 && K > 0, "tdoa_gccnmf: dimensions must be positive");
+  GCCNMF_REQUIRE(h, coherence && E && W, "tdoa_gccnmf: NULL pointer");
+  GCCNMF_REQUIRE(h, (int64_t)T * D < (int64_t)1 << 31, "tdoa_gccnmf: T * D overflows int32");
+  if (!values && !argmax) return GCCNMF_OK;
+  if (argmax && !(is_pow2(D) && D >= 4 && D <= GN))
+    return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "tdoa_gccnmf: fused argmax needs numTDOAs a power of two in [4, %d] (got %d)", GN, D);
+  const int N = T * D;
+  LoadWAtoms a{W, K, F};
+  LoadRealGCC b{reinterpret_cast<const float2*>(coherence), reinterpret_cast<const double2*>(E), F, T, D, N};
+  dim3 grid((N + GN - 1) / GN, (K + GM - 1) / GM);
+  if (argmax) {
+    auto k = tdoa_gccnmf_kernel<true>;
+    GCCNMF_LAUNCH(h, k, grid, kGccThreads, 0, stream, K, N, F, a, b, T, D, values, argmax);
+  } else {
+    auto k = tdoa_gccnmf_kernel<false>;
+    GCCNMF_LAUNCH(h, k, grid, kGccThreads, 0, stream, K, N, F, a, b, T, D, values, argmax);
+  }
+  return GCCNMF_OK;
+}
+
+int gccnmf_coeff_mask(gccnmf_handle* h, const float* gccnmfs, int S, int K, int T, float* masks, int32_t* all_nan_flag, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, S > 0 && K > 0 && T > 0 && gccnmfs && masks, "coeff_mask: bad arguments");
+  const int64_t KT = (int64_t)K * T;
+  GCCNMF_LAUNCH(h, coeff_mask_kernel, (unsigned)((KT + 255) / 256), 256, 0, stream, gccnmfs, S, KT, masks, all_nan_flag);
+  return GCCNMF_OK;
+}
+
+int gccnmf_argmax_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, const uint8_t* lut, int D, float* mask, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, K > 0 && T > 0 && D > 0 && argmax && lut && mask, "argmax_mask: bad arguments");
+  const int64_t KT = (int64_t)K * T;
+  GCCNMF_LAUNCH(h, argmax_mask_kernel, (unsigned)((KT + 255) / 256), 256, 0, stream, argmax, KT, lut, D, mask);
+  return GCCNMF_OK;
+}
+
+int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W, const float* H, int S, int F,
+                              int T, int K, float* out, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, S > 0 && F > 0 && T > 0 && K > 0 && masks && X && W && H && out, "masked_recon_phase: bad arguments");
+  dim3 grid((T + RN - 1) / RN, (F + RM - 1) / RM, S * 2);
+  GCCNMF_LAUNCH(h, masked_recon_kernel, grid, kReconThreads, 0, stream, masks, reinterpret_cast<const float2*>(X), W, H, F, T, K,
+                reinterpret_cast<float2*>(out));
+  return GCCNMF_OK;
+}
+
+}  // extern "C"

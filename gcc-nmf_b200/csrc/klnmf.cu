@@ -1,0 +1,292 @@
+// KL-NMF multiplicative updates (reference: gccNMF/gccNMFFunctions.py:69-83), float32 SIMT path.
+//
+// One iteration in reference order:
+//   R = V / (W.H)                          gemm  (F x T2) over K     -> fused epilogue, R only
+//   H *= (W^T.R) / (colsum(W) + a + eps)   gemm  (K x T2) over F     -> fused multiplicative epilogue
+//   R = V / (W.H)                          again with the new H
+//   numer = R.H^T, rowsum(H)               gemm  (F x K) over T2, split along T2 (output is small)
+//   W *= numer / rowsum(H); unit-L2 atoms; H *= norms
+// The float32 arithmetic follows numpy's (division, then multiply; column sums of W in row order).
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
+constexpr int kGemmThreads = (BM / TM) * (BN / TN);
+constexpr int kSplitT = 8;  // split of the T2 contraction for the (F x K) numerator
+
+struct LoadRowMajorK {  // element (row, k) at p[row * ld + k]  (k contiguous)
+  static constexpr bool kContigK = true;
+  const float* p; int rows, kc; int64_t ld;
+  __device__ float operator()(int r, int k) const { return (r < rows && k < kc) ? __ldg(p + (int64_t)r * ld + k) : 0.f; }
+};
+struct LoadColMajorK {  // element (row, k) at p[k * ld + row]  (row contiguous)
+  static constexpr bool kContigK = false;
+  const float* p; int rows, kc; int64_t ld;
+  __device__ float operator()(int r, int k) const { return (r < rows && k < kc) ? __ldg(p + (int64_t)k * ld + r) : 0.f; }
+};
+struct LoadRowMajorKRange {  // k offset window [k_begin, k_end) for split-K
+  static constexpr bool kContigK = true;
+  const float* p; int rows; int k_begin, k_end; int64_t ld;
+  __device__ float operator()(int r, int k) const {
+    const int kk = k_begin + k;
+    return (r < rows && kk < k_end) ? __ldg(p + (int64_t)r * ld + kk) : 0.f;
+  }
+};
+
+struct EpiRatio {  // R = V / acc                                  gccNMFFunctions.py:76,77  V / dot(W, H)
+  const float* V; float* R; int64_t ld;
+  __device__ void operator()(int m, int n, float acc) const { R[(int64_t)m * ld + n] = V[(int64_t)m * ld + n] / acc; }
+};
+struct EpiUpdateH {  // H *= acc / (colsum(W) + alpha + eps)        gccNMFFunctions.py:76
+  float* H; const float* colsumW; float alpha, eps; int64_t ld;
+  __device__ void operator()(int m, int n, float acc) const {
+    const float denom = (colsumW[m] + alpha) + eps;
+    float* h = H + (int64_t)m * ld + n;
+    *h = *h * (acc / denom);
+  }
+};
+struct EpiStore {
+  float* D; int64_t ld;
+  __device__ void operator()(int m, int n, float acc) const { D[(int64_t)m * ld + n] = acc; }
+};
+
+// split-K variant of the plain kernel: blockIdx.z selects the k range and the output slab.
+template <class Epi>
+__global__ void __launch_bounds__(kGemmThreads)
+numer_splitk_kernel(int M, int N, int T2, int chunk, const float* R, const float* H, float* partial) {
+  float acc[TM][TN];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * chunk;
+  const int k_end = min(T2, k_begin + chunk);
+  LoadRowMajorKRange a{R, M, k_begin, k_end, T2};
+  LoadRowMajorKRange b{H, N, k_begin, k_end, T2};
+  gemm_simt_mainloop<float, BM, BN, BK, TM, TN>(acc, m0, n0, max(0, k_end - k_begin), a, b);
+  float* out = partial + (int64_t)blockIdx.z * M * N;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = gemm_row<BM, TM, BN / TN>(m0, i);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = gemm_col<BN, TN, BN / TN>(n0, j);
+      if (n < N) out[(int64_t)m * N + n] = acc[i][j];
+    }
+  }
+}
+
+// numer[i] = sum_s partial[s][i] in split order (deterministic).
+__global__ void reduce_splits_kernel(const float* partial, int64_t n, int splits, float* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = partial[i];
+  for (int k = 1; k < splits; ++k) s += partial[(int64_t)k * n + i];
+  out[i] = s;
+}
+
+// colsum[k] = sum_f W[f][k], rows added in order like numpy.sum(W, axis=0)  (gccNMFFunctions.py:76).
+__global__ void colsum_kernel(const float* W, int F, int K, float* colsum) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int f = 0; f < F; ++f) s += W[(int64_t)f * K + k];
+  colsum[k] = s;
+}
+
+// rowsum[k] = sum_t H[k][t]   (gccNMFFunctions.py:77 sum(H, axis=1)); one block per row.
+__global__ void rowsum_kernel(const float* H, int T2, float* rowsum) {
+  __shared__ float warp_sums[32];
+  const float* row = H + (int64_t)blockIdx.x * T2;
+  float s = 0.f;
+  for (int t = threadIdx.x; t < T2; t += blockDim.x) s += row[t];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? warp_sums[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) rowsum[blockIdx.x] = s;
+  }
+}
+
+// W *= numer / rowsum(H) (:77); norms = sqrt(sum(W^2, 0)) (:79); W /= norms (:80).
+// Block = 32 columns x 32 row-groups; column reductions go through shared memory in row-group order.
+constexpr int kApplyCols = 32, kApplyGroups = 32;
+__global__ void __launch_bounds__(kApplyCols * kApplyGroups)
+apply_w_kernel(float* W, const float* numer, const float* rowsumH, int F, int K, float* norms) {
+  __shared__ float part[kApplyGroups][kApplyCols + 1];
+  __shared__ float norm_s[kApplyCols];
+  const int c = threadIdx.x % kApplyCols, g = threadIdx.x / kApplyCols;
+  const int k = blockIdx.x * kApplyCols + c;
+  const int rows_per_group = (F + kApplyGroups - 1) / kApplyGroups;
+  const int f0 = g * rows_per_group, f1 = min(F, f0 + rows_per_group);
+  float sumsq = 0.f;
+  if (k < K) {
+    const float rs = rowsumH[k];
+    for (int f = f0; f < f1; ++f) {
+      const int64_t i = (int64_t)f * K + k;
+      const float w = W[i] * (numer[i] / rs);
+      W[i] = w;
+      sumsq += w * w;
+    }
+  }
+  part[g][c] = sumsq;
+  __syncthreads();
+  if (g == 0) {
+    float s = 0.f;
+    for (int j = 0; j < kApplyGroups; ++j) s += part[j][c];
+    const float nrm = sqrtf(s);
+    norm_s[c] = nrm;
+    if (k < K) norms[k] = nrm;
+  }
+  __syncthreads();
+  if (k < K) {
+    const float nrm = norm_s[c];
+    for (int f = f0; f < f1; ++f) {
+      const int64_t i = (int64_t)f * K + k;
+      W[i] = W[i] / nrm;
+    }
+  }
+}
+
+// H *= norms[:, None]   (:81)
+__global__ void scale_rows_kernel(float* H, const float* norms, int K, int T2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)K * T2) return;
+  H[i] = H[i] * norms[i / T2];
+}
+
+struct Workspace {
+  float *R, *partial, *numer, *colsumW, *norms;
+  bool ok;
+};
+Workspace carve(void* ws, size_t bytes, int F, int T2, int K) {
+  WorkspaceCarver c(ws, bytes);
+  Workspace w;
+  w.R = c.take<float>((size_t)F * T2);
+  w.partial = c.take<float>((size_t)kSplitT * F * K);
+  w.numer = c.take<float>((size_t)F * K + K);
+  w.colsumW = c.take<float>(K);
+  w.norms = c.take<float>(K);
+  w.ok = c.ok();
+  return w;
+}
+
+dim3 gemm_grid(int M, int N) { return dim3((N + BN - 1) / BN, (M + BM - 1) / BM, 1); }
+
+int check_dims(gccnmf_handle* h, int F, int T2, int K) {
+  GCCNMF_REQUIRE(h, F > 0 && T2 > 0 && K > 0, "klnmf: F, T2, K must be positive (got %d, %d, %d)", F, T2, K);
+  return 0;
+}
+
+int ratio(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, float* R, void* stream) {
+  LoadRowMajorK a{W, F, K, K};
+  LoadColMajorK b{H, T2, K, T2};
+  EpiRatio e{V, R, T2};
+  auto kernel = gemm_simt_kernel<float, BM, BN, BK, TM, TN, LoadRowMajorK, LoadColMajorK, EpiRatio>;
+  GCCNMF_LAUNCH(h, kernel, gemm_grid(F, T2), kGemmThreads, 0, stream, F, T2, K, a, b, e);
+  return 0;
+}
+
+int update_H_impl(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha,
+                  float eps, const Workspace& w, bool have_colsum, void* stream) {
+  int st = ratio(h, V, F, T2, W, H, K, w.R, stream);
+  if (st) return st;
+  if (!have_colsum) GCCNMF_LAUNCH(h, colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsumW);
+  LoadColMajorK a{W, K, F, K};    // A(m = atom, k = f) = W[f][atom]
+  LoadColMajorK b{w.R, T2, F, T2};  // B(n = t,   k = f) = R[f][t]
+  EpiUpdateH e{H, w.colsumW, alpha, eps, T2};
+  auto kernel = gemm_simt_kernel<float, BM, BN, BK, TM, TN, LoadColMajorK, LoadColMajorK, EpiUpdateH>;
+  GCCNMF_LAUNCH(h, kernel, gemm_grid(K, T2), kGemmThreads, 0, stream, K, T2, F, a, b, e);
+  return 0;
+}
+
+int partial_W_impl(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
+                   float* numer, const Workspace& w, void* stream) {
+  int st = ratio(h, V, F, T2, W, H, K, w.R, stream);
+  if (st) return st;
+  const int chunk = ((T2 + kSplitT - 1) / kSplitT + BK - 1) / BK * BK;
+  const int splits = (T2 + chunk - 1) / chunk;
+  dim3 grid = gemm_grid(F, K);
+  grid.z = splits;
+  auto kernel = numer_splitk_kernel<EpiStore>;
+  GCCNMF_LAUNCH(h, kernel, grid, kGemmThreads, 0, stream, F, K, T2, chunk, w.R, H, w.partial);
+  const int64_t n = (int64_t)F * K;
+  GCCNMF_LAUNCH(h, reduce_splits_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, w.partial, n, splits, numer);
+  GCCNMF_LAUNCH(h, rowsum_kernel, K, 256, 0, stream, H, T2, numer + n);
+  return 0;
+}
+
+int apply_W_impl(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer, const Workspace& w, void* stream) {
+  GCCNMF_LAUNCH(h, apply_w_kernel, (K + kApplyCols - 1) / kApplyCols, kApplyCols * kApplyGroups, 0, stream,
+                W, numer, numer + (int64_t)F * K, F, K, w.norms);
+  const int64_t n = (int64_t)K * T2;
+  GCCNMF_LAUNCH(h, scale_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, H, w.norms, K, T2);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K) {
+  if (F <= 0 || T2 <= 0 || K <= 0) return 0;
+  size_t n = 0;
+  auto add = [&](size_t count) { n = align_up(n, 256) + count * sizeof(float); };
+  add((size_t)F * T2);
+  add((size_t)kSplitT * F * K);
+  add((size_t)F * K + K);
+  add(K);
+  add(K);
+  return align_up(n, 256);
+}
+
+int gccnmf_klnmf_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K,
+                          float sparsity_alpha, float epsilon, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (int st = check_dims(h, F, T2, K)) return st;
+  Workspace w = carve(workspace, workspace_bytes, F, T2, K);
+  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  return update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, false, stream);
+}
+
+int gccnmf_klnmf_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
+                           float* numer, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (int st = check_dims(h, F, T2, K)) return st;
+  Workspace w = carve(workspace, workspace_bytes, F, T2, K);
+  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  return partial_W_impl(h, V, F, T2, W, H, K, numer, w, stream);
+}
+
+int gccnmf_klnmf_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (int st = check_dims(h, F, T2, K)) return st;
+  Workspace w = carve(workspace, workspace_bytes, F, T2, K);
+  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  return apply_W_impl(h, F, T2, W, H, K, numer, w, stream);
+}
+
+int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, int iterations,
+                 float sparsity_alpha, float epsilon, int update_W, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (int st = check_dims(h, F, T2, K)) return st;
+  GCCNMF_REQUIRE(h, iterations >= 0, "klnmf: iterations must be >= 0 (got %d)", iterations);
+  Workspace w = carve(workspace, workspace_bytes, F, T2, K);
+  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  for (int it = 0; it < iterations; ++it) {
+    // with a fixed dictionary colsum(W) only has to be computed once
+    int st = update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, !update_W && it > 0, stream);
+    if (st) return st;
+    if (!update_W) continue;
+    st = partial_W_impl(h, V, F, T2, W, H, K, w.numer, w, stream);
+    if (st) return st;
+    st = apply_W_impl(h, F, T2, W, H, K, w.numer, w, stream);
+    if (st) return st;
+  }
+  return GCCNMF_OK;
+}
+
+}  // extern "C"

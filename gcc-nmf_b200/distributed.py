@@ -1,0 +1,195 @@
+"""Frame-sharded GCC-NMF across the GPUs of one box.
+
+One long recording is cut into contiguous frame ranges, one per rank (one process per GPU,
+torch.distributed / NCCL over NVLink).  Every stage of the path is independent per frame except:
+
+  1. the KL-NMF W update sums over ALL frames (gccNMFFunctions.py:77): each rank computes its partial
+     numerator (V_s/(W H_s)).H_s^T and rowsum(H_s); ONE all-reduce of F*K + K floats per iteration
+     makes W identical everywhere; normalisation (:79-81) is then computed redundantly per rank;
+  2. the mean angular spectrum used for peak picking (runGCCNMF.py:46): one D-float all-reduce;
+  3. the iSTFT overlap-add needs N - hop samples from the neighbouring rank at each seam.
+
+Column order matches the single-GPU run on the whole recording: the reference's V is
+[left frames | right frames] (runGCCNMF.py:40); rank r holds both channels of its own frames, and
+takes the matching column slices of the globally seeded H0, so 1-GPU and n-GPU runs agree up to
+float32 reduction order.
+
+`ShardComm` abstracts the three exchanges so the host logic is testable on CPU with gloo.
+"""
+import numpy as np
+
+from . import gccNMFFunctions as fn
+
+
+def shard_frames(total_frames, world, rank):
+    """Contiguous, balanced frame range [t0, t1) of `rank` (first `total % world` ranks get one more)."""
+    base, extra = divmod(total_frames, world)
+    t0 = rank * base + min(rank, extra)
+    return t0, t0 + base + (1 if rank < extra else 0)
+
+
+def shard_sample_range(t0, t1, windowSize, hopSize):
+    """Samples a rank needs to form frames [t0, t1): [t0 hop, (t1 - 1) hop + N)."""
+    return t0 * hopSize, (t1 - 1) * hopSize + windowSize
+
+
+def sharded_nmf_init(numFrequencies, totalFrames, dictionarySize, epsilon, seedValue, t0, t1):
+    """Global seeded draw (gccNMFFunctions.py:70-73 for V of shape (F, 2 T_total)), then this rank's
+    column slices [L frames t0:t1 | R frames t0:t1]."""
+    W0, H0 = fn._seededInit(numFrequencies, 2 * totalFrames, dictionarySize, epsilon, seedValue)
+    H0s = np.ascontiguousarray(np.concatenate([H0[:, t0:t1], H0[:, totalFrames + t0:totalFrames + t1]], axis=1))
+    return W0, H0s
+
+
+class ShardComm(object):
+    """The exchanges of the sharded path on torch.distributed (NCCL on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_reduce_sum(self, tensor):
+        if self.world > 1:
+            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+        return tensor
+
+    def seam_exchange(self, tail, head_like):
+        """Send `tail` (my samples past my last owned sample) to rank+1, receive rank-1's tail
+        (zeros for rank 0).  Returns the received halo, shaped like `head_like`."""
+        import torch
+        recv = torch.zeros_like(head_like)
+        if self.world == 1:
+            return recv
+        ops = []
+        if self.rank + 1 < self.world:
+            ops.append(self.dist.P2POp(self.dist.isend, tail.contiguous(), self.rank + 1, self.group))
+        if self.rank > 0:
+            ops.append(self.dist.P2POp(self.dist.irecv, recv, self.rank - 1, self.group))
+        for req in self.dist.batch_isend_irecv(ops):
+            req.wait()
+        return recv
+
+
+def klnmf_sharded(ops, comm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon, numer):
+    """gccNMFFunctions.py:75-81 on frame shards.  `ops` provides the three C-ABI building blocks
+    (klnmf_update_H, klnmf_partial_W, klnmf_apply_W); `numer` is an (F*K + K) float32 buffer."""
+    for _ in range(numIterations):
+        ops.klnmf_update_H(V_s, W, H_s, sparsityAlpha, epsilon)
+        ops.klnmf_partial_W(V_s, W, H_s, numer)
+        comm.all_reduce_sum(numer)
+        ops.klnmf_apply_W(W, H_s, numer)
+    return W, H_s
+
+
+def overlap_add_seams(comm, y_local, owned, halo):
+    """y_local: (B, owned + halo) un-trimmed local overlap-add.  Adds the left neighbour's tail onto
+    this rank's head and returns the owned part (the last rank keeps its tail)."""
+    import torch
+    tail = y_local[:, owned:owned + halo]
+    recv = comm.seam_exchange(tail, y_local[:, :halo])
+    y_local[:, :halo] += recv
+    if comm.rank + 1 < comm.world:
+        return y_local[:, :owned]
+    return y_local
+
+
+class ShardedGCCNMFPipeline(object):
+    """Enhancement flow (offlineSpeechEnhancement.ipynb cells 12-41) on one recording of
+    world x clip_seconds, frame-sharded; the dictionary is learnt jointly."""
+
+    def __init__(self, sampleRate, windowSize, hopSize, numTDOAs, microphoneSeparationInMetres, dictionarySize,
+                 numIterations, sparsityAlpha=0.0, epsilon=1e-16, seedValue=0, targetTDOAWindowSizePercent=0.05,
+                 device=0, clip_seconds=30.0, comm=None, handle=None):
+        import torch
+        from ._lib import Handle
+        self.torch = torch
+        self.comm = comm if comm is not None else ShardComm()
+        self.h = handle if handle is not None else Handle(device)
+        self.sr, self.N, self.hop, self.D = sampleRate, int(windowSize), int(hopSize), int(numTDOAs)
+        self.micSep, self.K, self.I = microphoneSeparationInMetres, int(dictionarySize), int(numIterations)
+        self.alpha, self.eps, self.seed = float(sparsityAlpha), float(epsilon), seedValue
+        self.windowPercent = targetTDOAWindowSizePercent
+        self.F = self.N // 2 + 1
+        world, rank = self.comm.world, self.comm.rank
+        self.total_samples = int(round(clip_seconds * sampleRate)) * world
+        self.total_frames = 1 + (self.total_samples - self.N) // self.hop
+        self.t0, self.t1 = shard_frames(self.total_frames, world, rank)
+        self.s0, self.s1 = shard_sample_range(self.t0, self.t1, self.N, self.hop)
+        self.clip_seconds = clip_seconds
+        self.frequenciesInHz = fn.getFrequenciesInHz(sampleRate, self.F)
+        self.hypothesisTDOAs = fn.getTDOAsInSeconds(microphoneSeparationInMetres, self.D)
+        self.E_host = np.ascontiguousarray(fn.getExpJOmegaTau(self.frequenciesInHz, self.hypothesisTDOAs))
+        self.window = self.h.to_device(np.hanning(self.N))
+        self.E = self.h.to_device(self.E_host)
+        W0, H0s = sharded_nmf_init(self.F, self.total_frames, self.K, self.eps, self.seed, self.t0, self.t1)
+        self.W0, self.H0s = self.h.to_device(W0), self.h.to_device(H0s)
+        self.numer = self.h.empty((self.F * self.K + self.K,), torch.float32)
+        self.stage_events = None
+
+    def local_samples(self):
+        """This rank's slice of the synthetic recording (each 30 s clip seeded by its index)."""
+        from .synth import synthetic_stereo
+        n_clip = int(round(self.clip_seconds * self.sr))
+        first, last = self.s0 // n_clip, (self.s1 - 1) // n_clip
+        x = np.concatenate([synthetic_stereo(self.clip_seconds, self.sr, seed=1234 + c) for c in range(first, last + 1)], axis=1)
+        return np.ascontiguousarray(x[:, self.s0 - first * n_clip:self.s1 - first * n_clip])
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = self.torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
+
+    def stage_times_ms(self):
+        ev = self.stage_events
+        return {ev[i + 1][0]: ev[i][1].elapsed_time(ev[i + 1][1]) for i in range(len(ev) - 1)}
+
+    def enhance(self, samples, collect_stage_times=False):
+        h, torch, comm = self.h, self.torch, self.comm
+        self.stage_events = [] if collect_stage_times else None
+        self._mark('start')
+        X, V = h.stft(samples, self.window, self.N, self.hop, conjugate=True, want_V=True)
+        Ts = X.shape[2]
+        assert Ts == self.t1 - self.t0
+        self._mark('stft')
+        coh, ang, mean = h.phat_angspec(X, self.E)
+        total = mean * float(Ts)                      # back to the local sum over frames
+        comm.all_reduce_sum(total)
+        mean_host = (total / float(self.total_frames)).cpu().numpy()
+        self._mark('angular')
+        W, H = self.W0.clone(), self.H0s.clone()
+        klnmf_sharded(h, comm, V, W, H, self.I, self.alpha, self.eps, self.numer)
+        self._mark('nmf')
+        _, argmax = h.tdoa_gccnmf(coh, self.E, W, want_values=False, want_argmax=True)
+        self._mark('gccnmf')
+        target = int(fn.estimateTargetTDOAIndexesFromAngularSpectrum(mean_host, self.micSep, self.D, 1)[0])
+        window = (self.hypothesisTDOAs[-1] - self.hypothesisTDOAs[0]) * self.windowPercent
+        lut = fn.getTargetTDOALookup(self.hypothesisTDOAs, target, window)
+        mask = h.argmax_mask(argmax, h.to_device(lut.astype(np.uint8)))
+        self._mark('mask')
+        est = h.masked_recon_phase(mask[None], X, W, H)
+        self._mark('recon')
+        y = h.istft_ola(est.reshape(2, self.F, Ts), self.window, self.N, self.hop,
+                        gain=np.float32(self.hop / float(self.N) * 2), center=False, conjugate=True)
+        y = overlap_add_seams(comm, y, self.hop * Ts, self.N - self.hop)
+        # global centre trim (librosaSTFT.py:283-284): N/2 samples off each end of the whole recording
+        if comm.rank == 0:
+            y = y[:, self.N // 2:]
+        if comm.rank == comm.world - 1:
+            y = y[:, :y.shape[1] - self.N // 2]
+        self._mark('istft')
+        return dict(X=X, V=V, W=W, H=H, coherence=coh, angularSpectrogram=ang, targetTDOAIndexes=[target],
+                    argMaxGCCNMF=argmax, targetCoefficientMasks=mask[None], targetSpectrogramEstimates=est,
+                    targetSignalEstimates=y.contiguous()[None])
+
+    def enhance_host(self, samples_host, out_host=None):
+        torch = self.torch
+        r = self.enhance(samples_host.to(self.h.device, non_blocking=True))
+        y = r['targetSignalEstimates']
+        if out_host is None:
+            out_host = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
+        out_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream(self.h.device).synchronize()
+        return out_host

@@ -1,0 +1,162 @@
+/*
+ * gccnmf_b200 -- C ABI of the B200-native GCC-NMF separation hot path.
+ *
+ * The reference (seanwood/gcc-nmf) has no FFI: its boundary is the Python call surface of
+ * gccNMF/gccNMFFunctions.py, gccNMF/librosaSTFT.py and gccNMF/realtime/gccNMFProcessor.py.
+ * Each entry point below is the device-side replacement of one of those Python functions
+ * (cited per function as file:line relative to the reference root) and is what a ctypes
+ * binding in the reference would call.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *  - the caller owns all buffers (including workspaces, sized by the *_workspace_bytes helpers);
+ *    the library borrows them for the duration of the call and never frees them;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream) and returns 0 on success or a negative gccnmf_status; no C++ exception crosses the ABI;
+ *  - array layouts are the reference's numpy C-order layouts: spectrograms (channel, F, T) with T
+ *    contiguous, W (F, K), H (K, 2T), masks (S, K, T), signals (S, 2, n);
+ *  - complex64 is interleaved (re, im) float pairs, complex128 interleaved double pairs;
+ *  - a handle is bound to one device and is not thread-safe (use one per host thread / stream).
+ */
+#ifndef GCCNMF_B200_H_
+#define GCCNMF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GCCNMF_API __attribute__((visibility("default")))
+#else
+#define GCCNMF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCCNMF_ABI_VERSION 1
+
+typedef struct gccnmf_handle gccnmf_handle;
+
+typedef enum gccnmf_status {
+  GCCNMF_OK = 0,
+  GCCNMF_ERR_INVALID_ARGUMENT = -1, /* librosaSTFT.ParameterError / ValueError in the reference   */
+  GCCNMF_ERR_CUDA = -2,             /* a CUDA runtime call failed; text in gccnmf_last_error       */
+  GCCNMF_ERR_WORKSPACE = -3,        /* workspace pointer NULL or too small                          */
+  GCCNMF_ERR_UNSUPPORTED = -4,      /* shape outside what the kernels were built for               */
+  GCCNMF_ERR_NO_DEVICE = -5         /* no CUDA device: there is NO CPU fallback                     */
+} gccnmf_status;
+
+/* ---- handle ------------------------------------------------------------------------------- */
+GCCNMF_API int gccnmf_abi_version(void);
+/* Binds to `device`; fails with GCCNMF_ERR_NO_DEVICE when no GPU is visible. */
+GCCNMF_API int gccnmf_create(gccnmf_handle** out, int device);
+GCCNMF_API int gccnmf_destroy(gccnmf_handle* h);
+/* Text of the last error recorded on this handle (never NULL; h may be NULL for create errors). */
+GCCNMF_API const char* gccnmf_last_error(const gccnmf_handle* h);
+GCCNMF_API const char* gccnmf_status_string(int status);
+/* Count of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
+GCCNMF_API int64_t gccnmf_launch_count(const gccnmf_handle* h);
+
+/* ---- a1: STFT  (gccNMF/librosaSTFT.py:20-181 via gccNMFFunctions.py:61-67) ------------------ */
+/* Frame count 1 + (num_samples - n_fft) / hop (librosaSTFT.py:425); <1 -> GCCNMF_ERR_INVALID_ARGUMENT. */
+GCCNMF_API int gccnmf_stft_num_frames(int64_t num_samples, int n_fft, int hop);
+/*
+ * samples (channels, num_samples) f32 with row stride `sample_stride`; window (n_fft) f64 on device;
+ * X (channels, F, T) c64.  Computation is float64 like the reference (window f64 * frame, double FFT)
+ * and rounded once to complex64.  conjugate != 0 reproduces librosaSTFT.py:179 (offline path);
+ * conjugate == 0 is numpy.fft.rfft (online / real-time path, onlineSpeechEnhancement.ipynb:410).
+ * V (F, channels*T) f32 = |X| with the channels concatenated in time (runGCCNMF.py:40); may be NULL.
+ * channels must be 1 or 2; n_fft a power of two in [32, 4096].
+ */
+GCCNMF_API int gccnmf_stft(gccnmf_handle* h, const float* samples, int64_t sample_stride, int channels,
+                int64_t num_samples, const double* window, int n_fft, int hop, int conjugate,
+                float* X, float* V, void* stream);
+
+/* ---- a9: iSTFT + overlap-add  (librosaSTFT.py:183-286 via gccNMFFunctions.py:153-163) ------- */
+/* Output length per signal: n_fft + hop (T-1) - (center ? n_fft : 0). */
+GCCNMF_API int64_t gccnmf_istft_length(int n_fft, int hop, int T, int center);
+GCCNMF_API size_t gccnmf_istft_workspace_bytes(int batch, int n_fft, int T);
+/*
+ * spec (batch, F, T) c64 -> y (batch, length) f32.  Per frame: Hermitian rebuild from conj(col)
+ * (librosaSTFT.py:278), single-precision inverse FFT (:279), real part times window (f64),
+ * sequential float32 overlap-add in frame order (:281), optional centre trim (:283-284), times
+ * `gain` (gccNMFFunctions.py:155,163).  conjugate == 0 skips the conj (numpy.fft.irfft convention).
+ */
+GCCNMF_API int gccnmf_istft_ola(gccnmf_handle* h, const float* spec, int batch, int n_fft, int hop, int T,
+                     const double* window, float gain, int center, int conjugate, float* y,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a2: KL-NMF  (gccNMFFunctions.py:69-83) -------------------------------------------------- */
+GCCNMF_API size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K);
+/*
+ * V (F, T2) f32 non-negative; W (F, K) and H (K, T2) f32 hold the initial values on entry (the
+ * seeded numpy draw of gccNMFFunctions.py:70-73 is made on the host) and the result on return.
+ * Runs `iterations` passes of lines :76-81 (H update, W update on the recomputed W.H, unit-L2 atoms).
+ * update_W == 0 runs only the H update (:76) with a fixed dictionary (the undefined
+ * inferCoefficientsKLNMF of onlineSpeechEnhancement.ipynb:433).
+ */
+GCCNMF_API int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K,
+                 int iterations, float sparsity_alpha, float epsilon, int update_W,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * Frame-sharded building blocks (multi-GPU dictionary learning).  One
+ * iteration on a rank holding columns V_s (F, T2s), H_s (K, T2s) and a replicated W is
+ *   gccnmf_klnmf_update_H   (H_s update, :76)
+ *   gccnmf_klnmf_partial_W  (numerator (V_s/(W H_s)).H_s^T (F,K) and rowsum(H_s) (K) into `numer`,
+ *                            laid out as F*K + K contiguous floats -> one all-reduce)
+ *   gccnmf_klnmf_apply_W    (W *= numer/rowsum (:77), unit-L2 atoms (:79-80), H_s *= norms (:81))
+ */
+GCCNMF_API int gccnmf_klnmf_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H,
+                          int K, float sparsity_alpha, float epsilon, void* workspace,
+                          size_t workspace_bytes, void* stream);
+GCCNMF_API int gccnmf_klnmf_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W,
+                           const float* H, int K, float* numer, void* workspace,
+                           size_t workspace_bytes, void* stream);
+GCCNMF_API int gccnmf_klnmf_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
+                         const float* numer, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a3 + a4: PHAT coherence and angular spectrogram  (runGCCNMF.py:44, gccNMFFunctions.py:85-92) */
+/*
+ * X (2, F, T) c64; expJOmegaTau (F, D) c128 = exp(-2 pi i f tau) built on the host in float64
+ * exactly as gccNMFFunctions.py:89.  coherence (F, T) c64 = X0 conj(X1) / |X0| / |X1| (unguarded,
+ * 0/0 -> NaN); angular (D, T) f64 = sum_f Re(coherence * E); mean_angular (D) f64 = mean over T
+ * (runGCCNMF.py:46).  coherence, angular and mean_angular may each be NULL.
+ * x_is_coherence != 0: X is an already-normalised (F, T) coherence (the argument
+ * gccNMFFunctions.getAngularSpectrogram takes, :85) and is used as is.
+ */
+GCCNMF_API size_t gccnmf_phat_angspec_workspace_bytes(int F, int T, int D);
+GCCNMF_API int gccnmf_phat_angspec(gccnmf_handle* h, const float* X, int F, int T, int x_is_coherence,
+                        const double* expJOmegaTau, int D, float* coherence, double* angular, double* mean_angular,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a6 / a10 / a11: GCC-NMF per TDOA  (gccNMFFunctions.py:118-135; offlineSpeechEnhancement.ipynb:444-450) */
+/*
+ * gccnmf[d, k, t] = sum_f Re(coherence[f, t] * E[f, d]) * W[f, k] accumulated in float64
+ * (the reference contracts in complex128 / float64).  E (F, D) c128 holds either the selected
+ * target TDOA columns (a6: D = number of targets) or all hypothesis TDOAs (a10/a11).
+ * values (D, K, T) f32 (a6's output dtype, gccNMFFunctions.py:131) and/or argmax (K, T) int32 over d
+ * with numpy.argmax semantics (first maximum; NaN counts as maximum).  Either may be NULL.
+ */
+GCCNMF_API int gccnmf_tdoa_gccnmf(gccnmf_handle* h, const float* coherence, int F, int T, const double* E,
+                       int D, const float* W, int K, float* values, int32_t* argmax, void* stream);
+
+/* ---- a7: coefficient masks  (gccNMFFunctions.py:137-143; offlineSpeechEnhancement.ipynb:466-472) */
+/* nanargmax over S -> one-hot (S, K, T) f32.  *all_nan_flag (device int32, may be NULL) is set to 1
+ * when some (k, t) is NaN for every target (numpy.nanargmax raises ValueError there). */
+GCCNMF_API int gccnmf_coeff_mask(gccnmf_handle* h, const float* gccnmfs, int S, int K, int T, float* masks,
+                      int32_t* all_nan_flag, void* stream);
+/* mask[k, t] = lut[argmax[k, t]] with lut (D) u8 built on the host in float64 from
+ * |tdoa[argmax] - tdoa[target]| < window (ipynb:468-471). */
+GCCNMF_API int gccnmf_argmax_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, const uint8_t* lut,
+                       int D, float* mask, void* stream);
+
+/* ---- a8: masked reconstruction with mixture phase  (gccNMFFunctions.py:145-151) -------------- */
+/* out[s, c] = (W . (H[:, c*T:(c+1)*T] * masks[s])) * exp(i angle(X[c])) ; out (S, 2, F, T) c64. */
+GCCNMF_API int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W,
+                              const float* H, int S, int F, int T, int K, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCCNMF_B200_H_ */

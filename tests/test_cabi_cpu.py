@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/gccnmf_b200.h declares,
+host-only helpers behave, and the product path refuses to run without a device (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as entry
+    entry.build()
+    from gcc_nmf_b200 import _lib
+    return _lib.load_library()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'gccnmf_b200.h')).read()
+    return sorted(set(re.findall(r'GCCNMF_API [\w\s\*]+?\b(gccnmf_\w+)\(', text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from gcc_nmf_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), 'missing export: ' + name
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_host_helpers(lib):
+    assert lib.gccnmf_abi_version() == 1
+    assert lib.gccnmf_stft_num_frames(160000, 1024, 512) == 311          # config 1
+    assert lib.gccnmf_stft_num_frames(480000, 1024, 256) == 1872         # config 2
+    assert lib.gccnmf_stft_num_frames(100, 1024, 256) < 0                # buffer too short
+    assert lib.gccnmf_stft_num_frames(4096, 1024, 0) < 0                 # invalid hop
+    assert lib.gccnmf_istft_length(1024, 256, 1872, 1) == 478976
+    assert lib.gccnmf_istft_length(1024, 512, 311, 1) == 158720
+    assert lib.gccnmf_klnmf_workspace_bytes(513, 3744, 1024) > 513 * 3744 * 4
+    assert lib.gccnmf_status_string(-5).decode().startswith('no CUDA device')
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from gcc_nmf_b200 import _lib
+    with pytest.raises(_lib.GCCNMFError):
+        _lib.Handle(0)
+    import gcc_nmf_b200.gccNMFFunctions as fn
+    import numpy as np
+    with pytest.raises(_lib.GCCNMFError):
+        fn.performKLNMF(np.ones((8, 8), np.float32), 2, 1, 0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'gcc-nmf_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
