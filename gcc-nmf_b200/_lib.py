@@ -78,8 +78,8 @@ def load_library():
 
 
 def _ptr(t):
-    """Device pointer of a torch tensor (None -> NULL)."""
-    if t is None:
+    """Device pointer of a torch tensor (None or empty -> NULL)."""
+    if t is None or t.numel() == 0:
         return None
     assert t.is_cuda and t.is_contiguous(), 'device-resident contiguous tensor required'
     return t.data_ptr()

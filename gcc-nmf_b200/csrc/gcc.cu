@@ -233,7 +233,7 @@ struct LoadMaskedH {  // B(n = t, k = atom) = H[atom][c*T + t] * mask[atom][t]  
   }
 };
 
-__global__ void __launch_bounds__(kReconThreads)
+__global__ void __launch_bounds__(kReconThreads, 2)
 masked_recon_kernel(const float* __restrict__ masks, const float2* __restrict__ X, const float* __restrict__ W,
                     const float* __restrict__ H, int F, int T, int K, float2* __restrict__ out) {
   const int s = blockIdx.z / 2, c = blockIdx.z % 2;

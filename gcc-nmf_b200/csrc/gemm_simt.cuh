@@ -132,7 +132,7 @@ __device__ __forceinline__ int gemm_col(int n0, int j) {
 
 // Plain kernel: per-element epilogue.
 template <typename T, int BM, int BN, int BK, int TM, int TN, class ALoad, class BLoad, class Epi>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+__global__ void __launch_bounds__((BM / TM) * (BN / TN), (sizeof(T) == 4 ? 2 : 1))
 gemm_simt_kernel(int M, int N, int Kc, ALoad aload, BLoad bload, Epi epi) {
   T acc[TM][TN];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;

@@ -54,7 +54,7 @@ struct EpiStore {
 
 // split-K variant of the plain kernel: blockIdx.z selects the k range and the output slab.
 template <class Epi>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 numer_splitk_kernel(int M, int N, int T2, int chunk, const float* R, const float* H, float* partial) {
   float acc[TM][TN];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;

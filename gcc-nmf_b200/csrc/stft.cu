@@ -267,7 +267,9 @@ int gccnmf_istft_ola(gccnmf_handle* h, const float* spec, int batch, int n_fft, 
   const int log2n = ilog2_exact(n_fft);
   if (log2n < 5 || log2n > 12) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "istft: n_fft must be a power of two in [32, 4096] (got %d)", n_fft);
   GCCNMF_REQUIRE(h, batch >= 1 && T >= 1 && hop >= 1, "istft: batch, T, hop must be positive");
-  GCCNMF_REQUIRE(h, spec && window && y, "istft: NULL pointer");
+  GCCNMF_REQUIRE(h, spec && window, "istft: NULL pointer");
+  if (gccnmf_istft_length(n_fft, hop, T, center) <= 0) return GCCNMF_OK;  // centre trim leaves nothing (single frame)
+  GCCNMF_REQUIRE(h, y != nullptr, "istft: NULL output pointer");
   if (!workspace || workspace_bytes < gccnmf_istft_workspace_bytes(batch, n_fft, T))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "istft workspace too small: need %zu bytes", gccnmf_istft_workspace_bytes(batch, n_fft, T));
   const float* tw = nullptr;
