@@ -45,6 +45,7 @@ SIGNATURES = {
     'gccnmf_istft_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_istft_ola': (c_int, [_H, _P, c_int, c_int, c_int, c_int, _P, c_float, c_int, c_int, _P, _P, c_size_t, _S]),
     'gccnmf_klnmf_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'gccnmf_klnmf_uses_tensor_cores': (c_int, [_H, c_int, c_int, c_int]),
     'gccnmf_klnmf': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_int, c_float, c_float, c_int, _P, c_size_t, _S]),
     'gccnmf_klnmf_update_H': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, _P, c_size_t, _S]),
     'gccnmf_klnmf_partial_W': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
@@ -55,6 +56,7 @@ SIGNATURES = {
     'gccnmf_coeff_mask': (c_int, [_H, _P, c_int, c_int, c_int, _P, _P, _S]),
     'gccnmf_argmax_mask': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, _S]),
     'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
+    'gccnmf_gemm_tn_3xtf32': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _S]),
 }
 
 _lib = None
@@ -262,6 +264,17 @@ class Handle(object):
         self.check(self.lib.gccnmf_masked_recon_phase(self.h, _ptr(masks), _ptr(X), _ptr(W), _ptr(H), S, F, T, K,
                                                       _ptr(out), self.stream))
         return out
+
+
+    def gemm_tn_3xtf32(self, A, B, Kc=None, tile_n=128):
+        """D = A[:, :Kc] . B[:, :Kc]^T on the tensor cores (3xTF32).  A (M, lda), B (N, ldb) f32 cuda."""
+        torch = self.torch
+        M, N = A.shape[0], B.shape[0]
+        Kc = A.shape[1] if Kc is None else Kc
+        D = self.empty((M, N), torch.float32)
+        self.check(self.lib.gccnmf_gemm_tn_3xtf32(self.h, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(D), D.stride(0),
+                                                  M, N, Kc, tile_n, self.stream))
+        return D
 
 
 _default_handles = {}

@@ -1,5 +1,7 @@
 // Handle management for the gccnmf_b200 C ABI.  There is no CPU fallback: without a CUDA device
 // gccnmf_create fails with GCCNMF_ERR_NO_DEVICE.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -39,6 +41,8 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->last_error = "no error";
+  const char* path = getenv("GCCNMF_NMF_PATH");
+  h->force_simt_nmf = path && strcmp(path, "simt") == 0;
   *out = h;
   return GCCNMF_OK;
 }

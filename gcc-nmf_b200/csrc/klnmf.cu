@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
@@ -228,7 +230,24 @@ int apply_W_impl(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, con
 
 }  // namespace
 
+// tensor-core path (klnmf_tc.cu)
+bool gccnmf_klnmf_tc_supported(int F, int T2, int K);
+size_t gccnmf_klnmf_tc_workspace_bytes(int F, int T2, int K);
+int gccnmf_klnmf_tc_prepare(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
+                            size_t workspace_bytes, bool need_vt, bool need_wt, bool need_ht, void* stream);
+int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
+                             void* workspace, size_t workspace_bytes, bool have_colsum, void* stream);
+int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int gccnmf_klnmf_tc_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
+
+static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tc_supported(F, T2, K); }
+
 extern "C" {
+
+int gccnmf_klnmf_uses_tensor_cores(const gccnmf_handle* h, int F, int T2, int K) { return h && use_tc(h, F, T2, K) ? 1 : 0; }
 
 size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K) {
   if (F <= 0 || T2 <= 0 || K <= 0) return 0;
@@ -239,13 +258,19 @@ size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K) {
   add((size_t)F * K + K);
   add(K);
   add(K);
-  return align_up(n, 256);
+  n = align_up(n, 256);
+  if (gccnmf_klnmf_tc_supported(F, T2, K)) n = std::max(n, gccnmf_klnmf_tc_workspace_bytes(F, T2, K));
+  return n;
 }
 
 int gccnmf_klnmf_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K,
                           float sparsity_alpha, float epsilon, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
+  if (use_tc(h, F, T2, K)) {
+    if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
+    return gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, false, stream);
+  }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   return update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, false, stream);
@@ -255,6 +280,11 @@ int gccnmf_klnmf_partial_W(gccnmf_handle* h, const float* V, int F, int T2, cons
                            float* numer, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
+  if (use_tc(h, F, T2, K)) {
+    if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, false, false, true, stream)) return st;
+    if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, stream)) return st;
+    return gccnmf_klnmf_tc_pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
+  }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   return partial_W_impl(h, V, F, T2, W, H, K, numer, w, stream);
@@ -264,6 +294,7 @@ int gccnmf_klnmf_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, in
                          void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, numer, workspace, workspace_bytes, stream);
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   return apply_W_impl(h, F, T2, W, H, K, numer, w, stream);
@@ -274,8 +305,21 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
   GCCNMF_REQUIRE(h, iterations >= 0, "klnmf: iterations must be >= 0 (got %d)", iterations);
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  if (iterations == 0) return GCCNMF_OK;
+  if (use_tc(h, F, T2, K)) {
+    if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
+    for (int it = 0; it < iterations; ++it) {
+      // colsum(W) comes out of the previous W update; with a fixed dictionary it is computed once
+      if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, it > 0, stream)) return st;
+      if (!update_W) continue;
+      if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, stream)) return st;
+      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, nullptr, workspace, workspace_bytes, stream)) return st;
+    }
+    return GCCNMF_OK;
+  }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
-  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   for (int it = 0; it < iterations; ++it) {
     // with a fixed dictionary colsum(W) only has to be computed once
     int st = update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, !update_W && it > 0, stream);

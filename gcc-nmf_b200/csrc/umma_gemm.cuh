@@ -1,0 +1,291 @@
+// 3xTF32 error-compensated GEMM on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]        A (M x Kc), B (N x Kc): float32, row-major, k contiguous
+//
+// KL-NMF needs float32-level accuracy over 100 multiplicative iterations (plain TF32 drifts to 1e-3,
+// SURVEY.md section 7), so every float32 operand x is split into hi = tf32(x) and lo = tf32(x - hi)
+// and each k-step issues three tcgen05.mma.kind::tf32 instructions into the same float32 TMEM
+// accumulator:  lo.hi + hi.lo + hi.hi  (the lo.lo term is below float32 resolution).
+//
+// CTA = one 128 x BN output tile.  Warp roles:
+//   warps 0 .. LW-1  loaders: coalesced 16-byte global loads (register double-buffered), split into
+//                    hi / lo, stored to shared memory in the canonical K-major SWIZZLE_128B UMMA layout
+//                    (rows of 32 floats = 128 B, 8-row groups of 1024 B, 16-byte chunk index XOR row%8);
+//                    after the main loop the same warps are the epilogue (tcgen05.ld -> functor).
+//   warp LW          allocates TMEM, and its lane 0 issues every tcgen05.mma / tcgen05.commit.
+// Pipelines: shared-memory stages guarded by full[] (loaders -> MMA, 1 arrival per loader thread after
+// fence.proxy.async) and empty[] (tcgen05.commit -> loaders); accum_full (tcgen05.commit -> epilogue).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace umma {
+
+constexpr int kBM = 128;      // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int kBK = 32;       // floats per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 8;     // K of one kind::tf32 instruction (32 bytes)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (sticky CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread.
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane base + i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct GemmArgs {
+  const float* A;   // (M, Kc) row-major, leading dimension lda (multiple of 4 floats, 16-byte aligned rows)
+  const float* B;   // (N, Kc) row-major, leading dimension ldb
+  int M, N, Kc;     // Kc may be any value; columns in [Kc, round_up(Kc, 4)) must hold zeros
+  int64_t lda, ldb;
+  int kblocks_per_split;  // k-blocks of 32 handled by one blockIdx.z
+};
+
+template <int BN, int LW>
+struct GemmSmem {
+  static constexpr int kStageBytes = (kBM + BN) * kBK * 4 * 2;  // A and B tiles, hi and lo
+  static constexpr int kStages = (BN <= 128) ? 3 : 2;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+};
+
+// Loads one [ROWS x 32] float tile (rows row0.., k columns k0..k0+31) as 16-byte chunks into registers.
+template <int ROWS, int NT>
+__device__ __forceinline__ void tile_fetch(float4 (&regs)[ROWS * 8 / NT], const float* __restrict__ src, int64_t ld,
+                                           int row0, int rows_valid, int k0, int kc4, int tid) {
+#pragma unroll
+  for (int i = 0; i < ROWS * 8 / NT; ++i) {
+    const int e = tid + i * NT;
+    const int r = e >> 3, c = e & 7;
+    const int row = row0 + r, k = k0 + c * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_valid && k < kc4) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)row * ld + k));
+    regs[i] = v;
+  }
+}
+
+// Splits and stores to the swizzled hi / lo tiles.
+template <int ROWS, int NT>
+__device__ __forceinline__ void tile_stash(const float4 (&regs)[ROWS * 8 / NT], unsigned char* hi, unsigned char* lo, int tid) {
+#pragma unroll
+  for (int i = 0; i < ROWS * 8 / NT; ++i) {
+    const int e = tid + i * NT;
+    const int r = e >> 3, c = e & 7;
+    const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    const float4 x = regs[i];
+    float4 h, l;
+    h.x = tf32_round(x.x); h.y = tf32_round(x.y); h.z = tf32_round(x.z); h.w = tf32_round(x.w);
+    l.x = tf32_round(x.x - h.x); l.y = tf32_round(x.y - h.y); l.z = tf32_round(x.z - h.z); l.w = tf32_round(x.w - h.w);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+// Epilogue concept:  struct E { __device__ void operator()(int m, int n0, const float (&v)[32], int z) const; };
+// called by every thread of the epilogue warps with its row m (possibly >= M: the functor must
+// predicate) and the 32 accumulator columns n0 .. n0+31; z = blockIdx.z (split index).
+template <int BN, int LW, class Epilogue>
+__global__ void __launch_bounds__((LW + 1) * 32, 1)
+gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
+  using S = GemmSmem<BN, LW>;
+  constexpr int NT = LW * 32;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + S::kStages;      // [kStages]
+  uint64_t* accum_full = bars + 2 * S::kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int kc4 = (args.Kc + 3) & ~3;
+  const int total_kblocks = (args.Kc + kBK - 1) / kBK;
+  const int kb_begin = blockIdx.z * args.kblocks_per_split;
+  const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
+  const int num_kb = max(0, kb_end - kb_begin);
+
+  if (tid == 0) {
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), NT);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == LW) tmem_alloc(smem_u32(tmem_base_slot), BN);   // BN float32 accumulator columns (power of two >= 32)
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * S::kStageBytes; };
+  // stage layout: A_hi | A_lo | B_hi | B_lo
+  constexpr int kATile = kBM * kBK * 4, kBTile = BN * kBK * 4;
+
+  if (warp < LW) {
+    // ------------------------------------------------------------------ loaders
+    // two register sets: the global loads of k-block i+2 are in flight while k-block i+1 is split and stored
+    float4 a0[kBM * 8 / NT], b0[BN * 8 / NT], a1[kBM * 8 / NT], b1[BN * 8 / NT];
+    auto fetch = [&](float4 (&ar)[kBM * 8 / NT], float4 (&br)[BN * 8 / NT], int kb) {
+      tile_fetch<kBM, NT>(ar, args.A, args.lda, m0, args.M, kb * kBK, kc4, tid);
+      tile_fetch<BN, NT>(br, args.B, args.ldb, n0, args.N, kb * kBK, kc4, tid);
+    };
+    auto produce = [&](float4 (&ar)[kBM * 8 / NT], float4 (&br)[BN * 8 / NT], int i) {
+      const int s = i % S::kStages;
+      const uint32_t use = i / S::kStages;
+      if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // MMAs that read this stage have retired
+      unsigned char* st = stage_ptr(s);
+      tile_stash<kBM, NT>(ar, st, st + kATile, tid);
+      tile_stash<BN, NT>(br, st + 2 * kATile, st + 2 * kATile + kBTile, tid);
+      if (i + 2 < num_kb) fetch(ar, br, kb_begin + i + 2);
+      fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&full[s]));
+    };
+    if (num_kb > 0) fetch(a0, b0, kb_begin);
+    if (num_kb > 1) fetch(a1, b1, kb_begin + 1);
+    for (int i = 0; i < num_kb; i += 2) {
+      produce(a0, b0, i);
+      if (i + 1 < num_kb) produce(a1, b1, i + 1);
+    }
+    // ------------------------------------------------------------------ epilogue
+    if (num_kb > 0) {
+      mbar_wait(smem_u32(accum_full), 0);
+      tc_fence_after_sync();
+    }
+    const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
+    const int m = m0 + quarter * 32 + lane;
+    constexpr int kColsPerWarp = BN / (LW / 4);
+    const int col0 = (warp >> 2) * kColsPerWarp;
+#pragma unroll 1
+    for (int c = 0; c < kColsPerWarp; c += 32) {
+      float v[32];
+      if (num_kb > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(col0 + c), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      epi(m, n0 + col0 + c, v, (int)blockIdx.z);
+    }
+    tc_fence_before_sync();
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % S::kStages;
+        mbar_wait(smem_u32(&full[s]), (i / S::kStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t base = smem_u32(stage_ptr(s));
+        const uint64_t a_hi = make_desc_kmajor_sw128(base), a_lo = make_desc_kmajor_sw128(base + kATile);
+        const uint64_t b_hi = make_desc_kmajor_sw128(base + 2 * kATile), b_lo = make_desc_kmajor_sw128(base + 2 * kATile + kBTile);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);   // +32 bytes per k-step inside the 128-byte swizzle row
+          mma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (i | k) != 0);
+          mma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+          mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+        }
+        mma_commit(smem_u32(&empty[s]));      // stage reusable once these MMAs retire
+      }
+      if (num_kb > 0) mma_commit(smem_u32(accum_full));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == LW) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace umma

@@ -89,6 +89,9 @@ GCCNMF_API int gccnmf_istft_ola(gccnmf_handle* h, const float* spec, int batch, 
 
 /* ---- a2: KL-NMF  (gccNMFFunctions.py:69-83) -------------------------------------------------- */
 GCCNMF_API size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K);
+/* 1 when the contractions of this shape run on tcgen05 (3xTF32, K % 4 == 0, T2 % 4 == 0, F, T2 >= 128),
+ * 0 when they run on the float32 SIMT kernels (small or odd shapes, or GCCNMF_NMF_PATH=simt). */
+GCCNMF_API int gccnmf_klnmf_uses_tensor_cores(const gccnmf_handle* h, int F, int T2, int K);
 /*
  * V (F, T2) f32 non-negative; W (F, K) and H (K, T2) f32 hold the initial values on entry (the
  * seeded numpy draw of gccNMFFunctions.py:70-73 is made on the host) and the result on return.
@@ -155,6 +158,17 @@ GCCNMF_API int gccnmf_argmax_mask(gccnmf_handle* h, const int32_t* argmax, int K
 /* out[s, c] = (W . (H[:, c*T:(c+1)*T] * masks[s])) * exp(i angle(X[c])) ; out (S, 2, F, T) c64. */
 GCCNMF_API int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W,
                               const float* H, int S, int F, int T, int K, float* out, void* stream);
+
+/* ---- tensor-core building block of a2 (the four contractions of gccNMFFunctions.py:76-77) ------ */
+/*
+ * D (M, N) row-major (ldd) = A (M, Kc; lda) . B (N, Kc; ldb)^T, float32 in / float32 out, computed with
+ * 3-pass error-compensated TF32 on tcgen05 (hi.hi + hi.lo + lo.hi, float32 TMEM accumulator): the accuracy
+ * class of the reference's float32 numpy.dot, which plain TF32 is not.
+ * lda, ldb: multiples of 4 floats, rows 16-byte aligned, zero padding in [Kc, round_up(Kc, 4)).
+ * tile_n selects the 128 x 128 or 128 x 256 CTA tile.
+ */
+GCCNMF_API int gccnmf_gemm_tn_3xtf32(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb,
+                          float* D, int64_t ldd, int M, int N, int Kc, int tile_n, void* stream);
 
 #ifdef __cplusplus
 }

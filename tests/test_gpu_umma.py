@@ -1,0 +1,83 @@
+"""GPU: the tcgen05 3xTF32 GEMM building block against a float64 product (and against what plain
+TF32 would give, to show the error compensation is doing its job)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def h():
+    from gcc_nmf_b200._lib import default_handle
+    return default_handle()
+
+
+def _check(h, M, N, Kc, tile_n, positive):
+    import torch
+    g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + Kc)
+    ld = (Kc + 3) // 4 * 4
+    A = torch.zeros(M, ld)
+    B = torch.zeros(N, ld)
+    A[:, :Kc] = torch.rand(M, Kc, generator=g) if positive else torch.randn(M, Kc, generator=g)
+    B[:, :Kc] = torch.rand(N, Kc, generator=g) if positive else torch.randn(N, Kc, generator=g)
+    Ad, Bd = A.to(h.device), B.to(h.device)
+    D = h.gemm_tn_3xtf32(Ad, Bd, Kc=Kc, tile_n=tile_n)
+    torch.cuda.synchronize()
+    ref = (Ad[:, :Kc].double() @ Bd[:, :Kc].double().T)
+    scale = (Ad[:, :Kc].abs().double() @ Bd[:, :Kc].abs().double().T)     # |a|.|b| bound for the error
+    err = ((D.double() - ref).abs() / scale).max().item()
+    return err
+
+
+@pytest.mark.parametrize('tile_n', [128, 256])
+@pytest.mark.parametrize('shape', [(128, 128, 32), (128, 256, 64), (256, 384, 1024), (100, 70, 40), (513, 3744, 1024),
+                                   (1024, 3744, 513), (513, 1024, 3744)])
+def test_gemm_3xtf32_matches_float64(h, shape, tile_n):
+    M, N, Kc = shape
+    for positive in (True, False):
+        err = _check(h, M, N, Kc, tile_n, positive)
+        # The operand split recovers float32 products (plain TF32 would give ~5e-4); what remains is the tensor
+        # core's float32 accumulator, which truncates on every accumulation: a bias of up to ~2^-24 per MMA
+        # into the same accumulator (3 Kc / 8 of them), fully coherent for all-positive data.
+        bound = 2e-6 + 4e-8 * (3 * Kc / 8)
+        assert err < bound, (shape, tile_n, positive, err, bound)
+
+
+def test_klnmf_tensor_core_path_matches_oracle(h):
+    """KL-NMF with the contractions on tcgen05 (F, T2 >= 128, K % 4 == 0) against the CPU oracle."""
+    import torch
+    from oracle import gccnmf_oracle as orc
+    F, T2, K = 257, 512, 64
+    assert h.lib.gccnmf_klnmf_uses_tensor_cores(h.h, F, T2, K) == 1
+    rng = np.random.default_rng(5)
+    V = (rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32)
+    W0, H0 = orc.initKLNMF(F, T2, K)
+
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    for iters, tol in ((1, 5e-6), (30, 1e-4)):
+        W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
+        h.klnmf(h.to_device(V), W, H, iters)
+        Wo, Ho = orc.performKLNMF(V, K, iters, 0, W0=W0, H0=H0)
+        eW, eH = rel(W.cpu().numpy(), Wo), rel(H.cpu().numpy(), Ho)
+        print('tensor-core KL-NMF %d iterations: rel W %.2e  rel H %.2e' % (iters, eW, eH))
+        assert eW < tol and eH < tol, (iters, eW, eH)
+    # building blocks (multi-GPU protocol) equal the fused loop bit for bit
+    V_d = h.to_device(V)
+    W1, H1 = h.to_device(W0.copy()), h.to_device(H0.copy())
+    W2, H2 = W1.clone(), H1.clone()
+    h.klnmf(V_d, W1, H1, 2)
+    numer = torch.empty(F * K + K, dtype=torch.float32, device=V_d.device)
+    for _ in range(2):
+        h.klnmf_update_H(V_d, W2, H2)
+        h.klnmf_partial_W(V_d, W2, H2, numer)
+        h.klnmf_apply_W(W2, H2, numer)
+    assert rel(W2.cpu().numpy(), W1.cpu().numpy()) < 1e-6 and rel(H2.cpu().numpy(), H1.cpu().numpy()) < 1e-6
+    # fixed dictionary (H-only inference)
+    Hi = h.to_device(H0.copy())
+    h.klnmf(V_d, h.to_device(Wo), Hi, 5, update_W=False)
+    Href = H0.copy()
+    denom = np.sum(Wo, axis=0)[:, None] + np.float32(1e-16)
+    for _ in range(5):
+        Href *= np.dot(Wo.T, V / np.dot(Wo, Href)) / denom
+    assert rel(Hi.cpu().numpy(), Href) < 2e-5
