@@ -236,11 +236,12 @@ size_t gccnmf_klnmf_tc_workspace_bytes(int F, int T2, int K);
 int gccnmf_klnmf_tc_prepare(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
                             size_t workspace_bytes, bool need_vt, bool need_wt, bool need_ht, void* stream);
 int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
-                             void* workspace, size_t workspace_bytes, bool have_colsum, void* stream);
+                             void* workspace, size_t workspace_bytes, bool have_colsum, bool pending_norms, void* stream);
 int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
-                              size_t workspace_bytes, void* stream);
+                              size_t workspace_bytes, bool have_rowsum, void* stream);
 int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            size_t workspace_bytes, bool scale_h, bool scale_ht, void* stream);
+int gccnmf_klnmf_tc_flush_scale(gccnmf_handle* h, int F, int T2, float* H, int K, void* workspace, size_t workspace_bytes, void* stream);
 int gccnmf_klnmf_tc_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
 
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tc_supported(F, T2, K); }
@@ -269,7 +270,7 @@ int gccnmf_klnmf_update_H(gccnmf_handle* h, const float* V, int F, int T2, const
   if (int st = check_dims(h, F, T2, K)) return st;
   if (use_tc(h, F, T2, K)) {
     if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
-    return gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, false, stream);
+    return gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, false, false, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
@@ -282,7 +283,7 @@ int gccnmf_klnmf_partial_W(gccnmf_handle* h, const float* V, int F, int T2, cons
   if (int st = check_dims(h, F, T2, K)) return st;
   if (use_tc(h, F, T2, K)) {
     if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, false, false, true, stream)) return st;
-    if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, stream)) return st;
+    if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, false, stream)) return st;
     return gccnmf_klnmf_tc_pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
@@ -294,7 +295,7 @@ int gccnmf_klnmf_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, in
                          void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
-  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, numer, workspace, workspace_bytes, stream);
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, numer, workspace, workspace_bytes, true, false, stream);
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   return apply_W_impl(h, F, T2, W, H, K, numer, w, stream);
@@ -312,11 +313,14 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
     if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
     for (int it = 0; it < iterations; ++it) {
       // colsum(W) comes out of the previous W update; with a fixed dictionary it is computed once
-      if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, it > 0, stream)) return st;
+      // and the H *= norms of :81 stays pending: the next iteration's G1 loader and G2 epilogue apply it
+      if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, it > 0,
+                                            update_W && it > 0, stream)) return st;
       if (!update_W) continue;
-      if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, stream)) return st;
-      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, nullptr, workspace, workspace_bytes, stream)) return st;
+      if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, nullptr, workspace, workspace_bytes, false, false, stream)) return st;
     }
+    if (update_W) return gccnmf_klnmf_tc_flush_scale(h, F, T2, H, K, workspace, workspace_bytes, stream);
     return GCCNMF_OK;
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);

@@ -115,10 +115,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Round-to-nearest (ties away) to TF32 with two integer ops: add half an ulp of the 10-bit mantissa,
+// clear the 13 low bits.  Same result as cvt.rna.tf32.f32 for finite inputs that do not round up to
+// infinity (the cvt compiles to a ~7-instruction sequence because it also handles those).
 __device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 struct GemmArgs {
@@ -127,9 +128,15 @@ struct GemmArgs {
   int M, N, Kc;     // Kc may be any value; columns in [Kc, round_up(Kc, 4)) must hold zeros
   int64_t lda, ldb;
   int kblocks_per_split;  // k-blocks of 32 handled by one blockIdx.z
+  int m_tiles;            // 128-row tiles on the tensor cores; blockIdx.y == m_tiles -> SIMT tail rows [128 m_tiles, M)
+  const float* b_scale;   // optional per-k scale of B (length >= round_up(Kc, 4)): B[n][k] * b_scale[k], or NULL
 };
 
-template <int BN, int LW>
+constexpr int kLoaderWarps = 8;
+constexpr int kLoaderThreads = kLoaderWarps * 32;
+constexpr int kThreads = kLoaderThreads + 32;
+
+template <int BN>
 struct GemmSmem {
   static constexpr int kStageBytes = (kBM + BN) * kBK * 4 * 2;  // A and B tiles, hi and lo
   static constexpr int kStages = (BN <= 128) ? 3 : 2;
@@ -137,71 +144,120 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
 };
 
-// Loads one [ROWS x 32] float tile (rows row0.., k columns k0..k0+31) as 16-byte chunks into registers.
-template <int ROWS, int NT>
-__device__ __forceinline__ void tile_fetch(float4 (&regs)[ROWS * 8 / NT], const float* __restrict__ src, int64_t ld,
-                                           int row0, int rows_valid, int k0, int kc4, int tid) {
+// One thread's share of a [ROWS x 32] float tile: chunk column c = tid % 8 (4 floats), rows tid / 8 + 32 i.
+template <int ROWS>
+struct TileLoader {
+  static constexpr int kChunks = ROWS * 8 / kLoaderThreads;
+  const float* ptr;       // first chunk of this thread at k-block 0
+  int64_t row_stride;     // 32 rows further down
+  uint32_t valid;         // bit i: row of chunk i is inside the matrix
+  int kcol;               // c * 4
+  uint32_t smem_off;      // swizzled byte offset of chunk 0 inside the tile; chunk i is + 4096 i
+
+  __device__ __forceinline__ void init(const float* src, int64_t ld, int row0, int rows_valid, int tid) {
+    const int r = tid >> 3, c = tid & 7;
+    ptr = src + (int64_t)(row0 + r) * ld + c * 4;
+    row_stride = 32 * ld;
+    kcol = c * 4;
+    valid = 0;
 #pragma unroll
-  for (int i = 0; i < ROWS * 8 / NT; ++i) {
-    const int e = tid + i * NT;
-    const int r = e >> 3, c = e & 7;
-    const int row = row0 + r, k = k0 + c * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < rows_valid && k < kc4) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)row * ld + k));
-    regs[i] = v;
+    for (int i = 0; i < kChunks; ++i) valid |= (row0 + r + 32 * i < rows_valid ? 1u : 0u) << i;
+    smem_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
   }
+  __device__ __forceinline__ void fetch(float4 (&regs)[kChunks], int k0, int kc4) const {
+    const bool kok = k0 + kcol < kc4;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kok && ((valid >> i) & 1u)) v = __ldg(reinterpret_cast<const float4*>(ptr + (int64_t)i * row_stride + k0));
+      regs[i] = v;
+    }
+  }
+  __device__ __forceinline__ void stash(const float4 (&regs)[kChunks], unsigned char* hi, unsigned char* lo) const {
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      const float4 x = regs[i];
+      float4 h, l;
+      h.x = tf32_round(x.x); h.y = tf32_round(x.y); h.z = tf32_round(x.z); h.w = tf32_round(x.w);
+      l.x = tf32_round(x.x - h.x); l.y = tf32_round(x.y - h.y); l.z = tf32_round(x.z - h.z); l.w = tf32_round(x.w - h.w);
+      *reinterpret_cast<float4*>(hi + smem_off + i * 4096) = h;
+      *reinterpret_cast<float4*>(lo + smem_off + i * 4096) = l;
+    }
+  }
+};
+
+// 32 x 32 register transpose through a per-warp shared scratch (33-float rows): in: v[j] = D[row lane][col j];
+// out: v[i] = D[row i][col lane].
+__device__ __forceinline__ void warp_transpose_32x32(float (&v)[32], float* scratch, int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = scratch[i * 33 + lane];
+  __syncwarp();
 }
 
-// Splits and stores to the swizzled hi / lo tiles.
-template <int ROWS, int NT>
-__device__ __forceinline__ void tile_stash(const float4 (&regs)[ROWS * 8 / NT], unsigned char* hi, unsigned char* lo, int tid) {
-#pragma unroll
-  for (int i = 0; i < ROWS * 8 / NT; ++i) {
-    const int e = tid + i * NT;
-    const int r = e >> 3, c = e & 7;
-    const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-    const float4 x = regs[i];
-    float4 h, l;
-    h.x = tf32_round(x.x); h.y = tf32_round(x.y); h.z = tf32_round(x.z); h.w = tf32_round(x.w);
-    l.x = tf32_round(x.x - h.x); l.y = tf32_round(x.y - h.y); l.z = tf32_round(x.z - h.z); l.w = tf32_round(x.w - h.w);
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
-  }
-}
-
-// Epilogue concept:  struct E { __device__ void operator()(int m, int n0, const float (&v)[32], int z) const; };
-// called by every thread of the epilogue warps with its row m (possibly >= M: the functor must
-// predicate) and the 32 accumulator columns n0 .. n0+31; z = blockIdx.z (split index).
-template <int BN, int LW, class Epilogue>
-__global__ void __launch_bounds__((LW + 1) * 32, 1)
+// Epilogue concept (see klnmf_tc.cu for the functors):
+//   __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int z, int slot, float* scratch) const;
+//       called by each epilogue warp per 32-column chunk; the thread holds row m_base + lane, columns
+//       n0 .. n0 + 31; slot = which column part of the tile this warp owns (for per-CTA partial outputs);
+//       scratch = 32 x 33 floats of shared memory private to the warp (for warp_transpose_32x32).
+//   __device__ void elem(int m, int n, float acc, int z) const;      // SIMT tail rows
+template <int BN, bool SCALE_B, class Epilogue>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
-  using S = GemmSmem<BN, LW>;
-  constexpr int NT = LW * 32;
+  using S = GemmSmem<BN>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
-  uint64_t* full = bars;                    // [kStages]
-  uint64_t* empty = bars + S::kStages;      // [kStages]
-  uint64_t* accum_full = bars + 2 * S::kStages;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int n0 = blockIdx.x * BN;
   const int kc4 = (args.Kc + 3) & ~3;
   const int total_kblocks = (args.Kc + kBK - 1) / kBK;
   const int kb_begin = blockIdx.z * args.kblocks_per_split;
   const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
   const int num_kb = max(0, kb_end - kb_begin);
 
+  if ((int)blockIdx.y >= args.m_tiles) {
+    // ---------------------------------------------------------------- SIMT tail rows (runs on SMs the tile grid leaves idle)
+    const int k_begin = kb_begin * kBK, k_end = min(kc4, kb_end * kBK);
+    for (int m = args.m_tiles * kBM; m < args.M; ++m) {
+      const float4* a = reinterpret_cast<const float4*>(args.A + (int64_t)m * args.lda);
+      for (int n = n0 + warp; n < min(args.N, n0 + BN); n += kThreads / 32) {
+        const float4* b = reinterpret_cast<const float4*>(args.B + (int64_t)n * args.ldb);
+        float acc = 0.f;
+        for (int k4 = k_begin / 4 + lane; k4 < k_end / 4; k4 += 32) {
+          const float4 x = __ldg(a + k4);
+          float4 y = __ldg(b + k4);
+          if (SCALE_B) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(args.b_scale) + k4);
+            y.x *= sc.x; y.y *= sc.y; y.z *= sc.z; y.w *= sc.w;
+          }
+          acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) epi.elem(m, n, acc, (int)blockIdx.z);
+      }
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + S::kStages;      // [kStages]
+  uint64_t* accum_full = bars + 2 * S::kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+  const int m0 = blockIdx.y * kBM;
+
   if (tid == 0) {
     for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(smem_u32(&full[s]), NT);
+      mbar_init(smem_u32(&full[s]), kLoaderThreads);
       mbar_init(smem_u32(&empty[s]), 1);
     }
     mbar_init(smem_u32(accum_full), 1);
     fence_barrier_init();
   }
-  if (warp == LW) tmem_alloc(smem_u32(tmem_base_slot), BN);   // BN float32 accumulator columns (power of two >= 32)
+  if (warp == kLoaderWarps) tmem_alloc(smem_u32(tmem_base_slot), BN);   // BN float32 accumulator columns (power of two >= 32)
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -211,40 +267,52 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
   // stage layout: A_hi | A_lo | B_hi | B_lo
   constexpr int kATile = kBM * kBK * 4, kBTile = BN * kBK * 4;
 
-  if (warp < LW) {
+  if (warp < kLoaderWarps) {
     // ------------------------------------------------------------------ loaders
+    TileLoader<kBM> la;
+    TileLoader<BN> lb;
+    la.init(args.A, args.lda, m0, min(args.M, args.m_tiles * kBM), tid);
+    lb.init(args.B, args.ldb, n0, args.N, tid);
     // two register sets: the global loads of k-block i+2 are in flight while k-block i+1 is split and stored
-    float4 a0[kBM * 8 / NT], b0[BN * 8 / NT], a1[kBM * 8 / NT], b1[BN * 8 / NT];
-    auto fetch = [&](float4 (&ar)[kBM * 8 / NT], float4 (&br)[BN * 8 / NT], int kb) {
-      tile_fetch<kBM, NT>(ar, args.A, args.lda, m0, args.M, kb * kBK, kc4, tid);
-      tile_fetch<BN, NT>(br, args.B, args.ldb, n0, args.N, kb * kBK, kc4, tid);
+    float4 a0[TileLoader<kBM>::kChunks], b0[TileLoader<BN>::kChunks], a1[TileLoader<kBM>::kChunks], b1[TileLoader<BN>::kChunks];
+    float4 s0, s1;
+    auto fetch = [&](float4 (&ar)[TileLoader<kBM>::kChunks], float4 (&br)[TileLoader<BN>::kChunks], float4& sc, int kb) {
+      la.fetch(ar, kb * kBK, kc4);
+      lb.fetch(br, kb * kBK, kc4);
+      if (SCALE_B) sc = (kb * kBK + lb.kcol < kc4) ? __ldg(reinterpret_cast<const float4*>(args.b_scale + kb * kBK + lb.kcol))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto produce = [&](float4 (&ar)[kBM * 8 / NT], float4 (&br)[BN * 8 / NT], int i) {
+    auto produce = [&](float4 (&ar)[TileLoader<kBM>::kChunks], float4 (&br)[TileLoader<BN>::kChunks], float4& sc, int i) {
       const int s = i % S::kStages;
       const uint32_t use = i / S::kStages;
+      if (SCALE_B) {
+#pragma unroll
+        for (int j = 0; j < TileLoader<BN>::kChunks; ++j) { br[j].x *= sc.x; br[j].y *= sc.y; br[j].z *= sc.z; br[j].w *= sc.w; }
+      }
       if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // MMAs that read this stage have retired
       unsigned char* st = stage_ptr(s);
-      tile_stash<kBM, NT>(ar, st, st + kATile, tid);
-      tile_stash<BN, NT>(br, st + 2 * kATile, st + 2 * kATile + kBTile, tid);
-      if (i + 2 < num_kb) fetch(ar, br, kb_begin + i + 2);
+      la.stash(ar, st, st + kATile);
+      lb.stash(br, st + 2 * kATile, st + 2 * kATile + kBTile);
+      if (i + 2 < num_kb) fetch(ar, br, sc, kb_begin + i + 2);
       fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&full[s]));
     };
-    if (num_kb > 0) fetch(a0, b0, kb_begin);
-    if (num_kb > 1) fetch(a1, b1, kb_begin + 1);
+    if (num_kb > 0) fetch(a0, b0, s0, kb_begin);
+    if (num_kb > 1) fetch(a1, b1, s1, kb_begin + 1);
     for (int i = 0; i < num_kb; i += 2) {
-      produce(a0, b0, i);
-      if (i + 1 < num_kb) produce(a1, b1, i + 1);
+      produce(a0, b0, s0, i);
+      if (i + 1 < num_kb) produce(a1, b1, s1, i + 1);
     }
     // ------------------------------------------------------------------ epilogue
     if (num_kb > 0) {
-      mbar_wait(smem_u32(accum_full), 0);
+      mbar_wait(smem_u32(accum_full), 0);   // every MMA has retired: accumulator complete, pipeline stages free
       tc_fence_after_sync();
     }
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
-    const int m = m0 + quarter * 32 + lane;
-    constexpr int kColsPerWarp = BN / (LW / 4);
-    const int col0 = (warp >> 2) * kColsPerWarp;
+    constexpr int kColsPerWarp = BN / 2;                  // warps w and w + 4 split the columns of a lane quarter
+    const int slot = warp >> 2;
+    const int col0 = slot * kColsPerWarp;
+    float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // aliases stage 0 (idle now)
 #pragma unroll 1
     for (int c = 0; c < kColsPerWarp; c += 32) {
       float v[32];
@@ -254,7 +322,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      epi(m, n0 + col0 + c, v, (int)blockIdx.z);
+      epi.tile(m0 + quarter * 32, lane, n0 + col0 + c, v, (int)blockIdx.z, (int)blockIdx.x * 2 + slot, scratch);
     }
     tc_fence_before_sync();
   } else {
@@ -282,7 +350,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
     __syncwarp();
   }
   __syncthreads();
-  if (warp == LW) {
+  if (warp == kLoaderWarps) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, BN);
   }
