@@ -39,6 +39,7 @@ SIGNATURES = {
     'gccnmf_last_error': (c_char_p, [_H]),
     'gccnmf_status_string': (c_char_p, [c_int]),
     'gccnmf_launch_count': (c_int64, [_H]),
+    'gccnmf_set_option': (c_int, [_H, c_char_p, c_int]),
     'gccnmf_stft_num_frames': (c_int, [c_int64, c_int, c_int]),
     'gccnmf_stft': (c_int, [_H, _P, c_int64, c_int, c_int64, _P, c_int, c_int, c_int, _P, _P, _S]),
     'gccnmf_istft_length': (c_int64, [c_int, c_int, c_int, c_int]),
@@ -47,9 +48,10 @@ SIGNATURES = {
     'gccnmf_klnmf_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_klnmf_uses_tensor_cores': (c_int, [_H, c_int, c_int, c_int]),
     'gccnmf_klnmf': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_int, c_float, c_float, c_int, _P, c_size_t, _S]),
-    'gccnmf_klnmf_update_H': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, _P, c_size_t, _S]),
-    'gccnmf_klnmf_partial_W': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
-    'gccnmf_klnmf_apply_W': (c_int, [_H, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
+    'gccnmf_klnmf_begin': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, _P, c_size_t, _S]),
+    'gccnmf_klnmf_step_numer': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, c_int, _P, _P, c_size_t, _S]),
+    'gccnmf_klnmf_step_apply': (c_int, [_H, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
+    'gccnmf_klnmf_end': (c_int, [_H, c_int, c_int, _P, _P, c_int, c_int, _P, c_size_t, _S]),
     'gccnmf_phat_angspec_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_phat_angspec': (c_int, [_H, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _S]),
     'gccnmf_tdoa_gccnmf': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _S]),
@@ -135,6 +137,12 @@ class Handle(object):
             raise ParameterError(msg)
         raise GCCNMFError('%s: %s' % (self.lib.gccnmf_status_string(status).decode(), msg))
 
+    def set_option(self, name, value):
+        self.check(self.lib.gccnmf_set_option(self.h, name.encode(), int(value)))
+
+    def klnmf_uses_tensor_cores(self, F, T2, K):
+        return bool(self.lib.gccnmf_klnmf_uses_tensor_cores(self.h, F, T2, K))
+
     def workspace(self, key, nbytes):
         """Caller-owned scratch, cached per purpose and grown on demand."""
         ws = self._workspaces.get(key)
@@ -192,26 +200,33 @@ class Handle(object):
                                          ws.numel(), self.stream))
         return W, H
 
-    def klnmf_update_H(self, V, W, H, sparsity_alpha=0.0, epsilon=1e-16):
+    def _klnmf_ws(self, F, T2, K):
+        return self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
+
+    def klnmf_begin(self, V, W, H):
         F, T2 = V.shape
         K = W.shape[1]
-        ws = self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
-        self.check(self.lib.gccnmf_klnmf_update_H(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, float(sparsity_alpha),
-                                                  float(epsilon), _ptr(ws), ws.numel(), self.stream))
+        ws = self._klnmf_ws(F, T2, K)
+        self.check(self.lib.gccnmf_klnmf_begin(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, _ptr(ws), ws.numel(), self.stream))
 
-    def klnmf_partial_W(self, V, W, H, numer):
+    def klnmf_step_numer(self, V, W, H, iteration, numer, sparsity_alpha=0.0, epsilon=1e-16):
         F, T2 = V.shape
         K = W.shape[1]
-        ws = self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
-        self.check(self.lib.gccnmf_klnmf_partial_W(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, _ptr(numer), _ptr(ws),
-                                                   ws.numel(), self.stream))
+        ws = self._klnmf_ws(F, T2, K)
+        self.check(self.lib.gccnmf_klnmf_step_numer(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, float(sparsity_alpha),
+                                                    float(epsilon), int(iteration), _ptr(numer), _ptr(ws), ws.numel(), self.stream))
 
-    def klnmf_apply_W(self, W, H, numer):
+    def klnmf_step_apply(self, W, H, numer):
         F, K = W.shape
         T2 = H.shape[1]
-        ws = self.workspace('klnmf', self.lib.gccnmf_klnmf_workspace_bytes(F, T2, K))
-        self.check(self.lib.gccnmf_klnmf_apply_W(self.h, F, T2, _ptr(W), _ptr(H), K, _ptr(numer), _ptr(ws), ws.numel(),
-                                                 self.stream))
+        ws = self._klnmf_ws(F, T2, K)
+        self.check(self.lib.gccnmf_klnmf_step_apply(self.h, F, T2, _ptr(W), _ptr(H), K, _ptr(numer), _ptr(ws), ws.numel(), self.stream))
+
+    def klnmf_end(self, W, H, iterations_done):
+        F, K = W.shape
+        T2 = H.shape[1]
+        ws = self._klnmf_ws(F, T2, K)
+        self.check(self.lib.gccnmf_klnmf_end(self.h, F, T2, _ptr(W), _ptr(H), K, int(iterations_done), _ptr(ws), ws.numel(), self.stream))
 
     def phat_angspec(self, X, E=None, want_coherence=True, want_angular=True, want_mean=True):
         """X (2, F, T) c64 mixture spectrogram -- or an (F, T) c64 coherence used as is -- and

@@ -73,4 +73,10 @@ const char* gccnmf_status_string(int status) {
 
 int64_t gccnmf_launch_count(const gccnmf_handle* h) { return h ? h->launches : 0; }
 
+int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
+  if (!h || !name) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (strcmp(name, "force_simt_nmf") == 0) { h->force_simt_nmf = value != 0; return GCCNMF_OK; }
+  return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
+}
+
 }  // extern "C"

@@ -121,12 +121,12 @@ apply_w_kernel(float* W, const float* numer, const float* rowsumH, int F, int K,
   __shared__ float norm_s[kApplyCols];
   const int c = threadIdx.x % kApplyCols, g = threadIdx.x / kApplyCols;
   const int k = blockIdx.x * kApplyCols + c;
-  const int rows_per_group = (F + kApplyGroups - 1) / kApplyGroups;
-  const int f0 = g * rows_per_group, f1 = min(F, f0 + rows_per_group);
+  // rows f = g, g + 32, ... (the same partition and reduction order as tc_apply_w_kernel: a rank on the SIMT
+  // path and a rank on the tensor-core path produce bit-identical W from the same all-reduced numerator)
   float sumsq = 0.f;
   if (k < K) {
     const float rs = rowsumH[k];
-    for (int f = f0; f < f1; ++f) {
+    for (int f = g; f < F; f += kApplyGroups) {
       const int64_t i = (int64_t)f * K + k;
       const float w = W[i] * (numer[i] / rs);
       W[i] = w;
@@ -145,7 +145,7 @@ apply_w_kernel(float* W, const float* numer, const float* rowsumH, int F, int K,
   __syncthreads();
   if (k < K) {
     const float nrm = norm_s[c];
-    for (int f = f0; f < f1; ++f) {
+    for (int f = g; f < F; f += kApplyGroups) {
       const int64_t i = (int64_t)f * K + k;
       W[i] = W[i] / nrm;
     }
@@ -236,12 +236,13 @@ size_t gccnmf_klnmf_tc_workspace_bytes(int F, int T2, int K);
 int gccnmf_klnmf_tc_prepare(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
                             size_t workspace_bytes, bool need_vt, bool need_wt, bool need_ht, void* stream);
 int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
-                             void* workspace, size_t workspace_bytes, bool have_colsum, bool pending_norms, void* stream);
+                             void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream);
 int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
                               size_t workspace_bytes, bool have_rowsum, void* stream);
-int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer, void* workspace,
-                            size_t workspace_bytes, bool scale_h, bool scale_ht, void* stream);
-int gccnmf_klnmf_tc_flush_scale(gccnmf_handle* h, int F, int T2, float* H, int K, void* workspace, size_t workspace_bytes, void* stream);
+int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int gccnmf_klnmf_tc_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
+                           size_t workspace_bytes, void* stream);
 int gccnmf_klnmf_tc_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
 
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tc_supported(F, T2, K); }
@@ -264,41 +265,54 @@ size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K) {
   return n;
 }
 
-int gccnmf_klnmf_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K,
-                          float sparsity_alpha, float epsilon, void* workspace, size_t workspace_bytes, void* stream) {
+int gccnmf_klnmf_begin(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
+                       void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
-  if (use_tc(h, F, T2, K)) {
-    if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
-    return gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, false, false, stream);
-  }
-  Workspace w = carve(workspace, workspace_bytes, F, T2, K);
-  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  return update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, false, stream);
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream);
+  return GCCNMF_OK;
 }
 
-int gccnmf_klnmf_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
-                           float* numer, void* workspace, size_t workspace_bytes, void* stream) {
+int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K,
+                            float sparsity_alpha, float epsilon, int iteration, float* numer, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
+  GCCNMF_REQUIRE(h, numer != nullptr && iteration >= 0, "klnmf_step_numer: bad arguments");
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (use_tc(h, F, T2, K)) {
-    if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, false, false, true, stream)) return st;
-    if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, false, stream)) return st;
+    if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0,
+                                          iteration > 0, stream)) return st;
+    if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
     return gccnmf_klnmf_tc_pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
-  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  if (int st = update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, false, stream)) return st;
   return partial_W_impl(h, V, F, T2, W, H, K, numer, w, stream);
 }
 
-int gccnmf_klnmf_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer,
+                            void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
-  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, numer, workspace, workspace_bytes, true, false, stream);
+  GCCNMF_REQUIRE(h, numer != nullptr, "klnmf_step_apply: NULL numerator");
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, numer, workspace, workspace_bytes, stream);
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
-  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   return apply_W_impl(h, F, T2, W, H, K, numer, w, stream);
+}
+
+int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (int st = check_dims(h, F, T2, K)) return st;
+  (void)W;
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream);
+  return GCCNMF_OK;
 }
 
 int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, int iterations,
@@ -314,14 +328,13 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
     for (int it = 0; it < iterations; ++it) {
       // colsum(W) comes out of the previous W update; with a fixed dictionary it is computed once
       // and the H *= norms of :81 stays pending: the next iteration's G1 loader and G2 epilogue apply it
-      if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, it > 0,
-                                            update_W && it > 0, stream)) return st;
+      if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes,
+                                            it == 0 ? 0 : (update_W ? 2 : 1), update_W && it > 0, stream)) return st;
       if (!update_W) continue;
       if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
-      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, H, K, nullptr, workspace, workspace_bytes, false, false, stream)) return st;
+      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, nullptr, workspace, workspace_bytes, stream)) return st;
     }
-    if (update_W) return gccnmf_klnmf_tc_flush_scale(h, F, T2, H, K, workspace, workspace_bytes, stream);
-    return GCCNMF_OK;
+    return gccnmf_klnmf_tc_finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   for (int it = 0; it < iterations; ++it) {

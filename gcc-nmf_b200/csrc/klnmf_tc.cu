@@ -3,10 +3,11 @@
 // Every contraction is a "TN" product with both operands k-contiguous (umma_gemm.cuh), so each
 // matrix is kept in the orientation(s) its consumers contract over; the producing epilogue writes them:
 //   W  (F, K)   ld K      A of G1/G3 (contract over atoms)        WT (K, Fp)  A of G2 (contract over f)
-//   H  (K, T2)  ld T2     B of G4   (contract over frames)        HT (T2, K)  B of G1/G3
+//   Hp (K, T2p)           B of G4   (contract over frames)        HT (T2, K)  B of G1/G3
 //   V  (F, T2)  ld T2     epilogue of G3                          VT (T2, Fp) epilogue of G1
-//   R  (F, T2)            A of G4, written by G3                  RT (T2, Fp) B of G2, written by G1
-// Fp = F rounded up to 4 floats (16-byte rows); pad columns hold zeros.
+//   R  (F, T2p)           A of G4, written by G3                  RT (T2, Fp) B of G2, written by G1
+// Fp, T2p = F, T2 rounded up to 4 floats (16-byte rows); pad columns hold zeros.  Hp is the working copy of
+// the caller's H (any T2): it is read once at the start and written once at the end (gccnmf_klnmf_tc_finish).
 //
 // One iteration, reference order (:76-:81):
 //   G1  RT = VT / (W.(n*H))          M = f, N = t, over atoms     n = pending atom norms (see below)
@@ -83,9 +84,14 @@ struct EpiRatioRow {  // R[m][n] = V[m][n] / acc       (G3; transposed through s
 // shared-memory transpose, and the per-row partial sums of the new H go to rowsum_part[slot][m].
 struct EpiUpdateHBoth {
   float* __restrict__ H; float* __restrict__ HT; const float* __restrict__ colsumW; const float* __restrict__ pending;
-  float* __restrict__ rowsum_part; float alpha, eps; int64_t ldh, ldht; int M, N;
+  float* __restrict__ rowsum_part; float alpha, eps; int64_t ldh, ldht; int M, N; int colsum_slots;
+  __device__ float colsum(int m) const {   // colsum(W): sum of the W update's per-row-block partials
+    float s = colsumW[m];
+    for (int b = 1; b < colsum_slots; ++b) s += colsumW[(int64_t)b * M + m];
+    return s;
+  }
   __device__ float update(int m, int n, float acc) const {
-    const float denom = (colsumW[m] + alpha) + eps;
+    const float denom = (colsum(m) + alpha) + eps;
     float old = HT[(int64_t)n * ldht + m];
     if (pending) old = old * pending[m];
     return old * (acc / denom);
@@ -99,7 +105,7 @@ struct EpiUpdateHBoth {
     const int m = m_base + lane;
     float rsum = 0.f;
     if (m < M) {
-      const float denom = (colsumW[m] + alpha) + eps;
+      const float denom = (colsum(m) + alpha) + eps;
       const float pn = pending ? pending[m] : 1.f;
       float old[32];
 #pragma unroll
@@ -166,18 +172,19 @@ __global__ void tc_rowsum_kernel(const float* H, int T2, int64_t ld, float* rows
   }
 }
 
-// W *= (sum_z partial[z]) / rowsum(H) (:77); unit-L2 atoms (:79-80); also W^T, norms and colsum(W) for the next
-// iteration.  rowsum(H) = sum of `rowsum_slots` partial vectors (from G2's epilogue) or one full vector.
-// Block = 32 atoms x 32 row groups; W^T is written through a shared-memory transpose.
-constexpr int kApplyCols = 32, kApplyGroups = 32;
-__global__ void __launch_bounds__(kApplyCols * kApplyGroups)
-tc_apply_w_kernel(float* __restrict__ W, float* __restrict__ WT, int64_t ldwt, const float* __restrict__ partial, int splits,
-                  const float* __restrict__ rowsum, int rowsum_slots, int F, int K, float* __restrict__ norms,
-                  float* __restrict__ colsum) {
-  __shared__ float part[kApplyGroups][kApplyCols + 1];
-  __shared__ float norm_s[kApplyCols], rs_s[kApplyCols];
-  const int c = threadIdx.x % kApplyCols, g = threadIdx.x / kApplyCols;
-  const int k = blockIdx.x * kApplyCols + c;
+// W update, two fully parallel passes over 32 x 32 tiles (grid: atoms / 32 x rows / 32):
+//   pass 1  W' = W * (sum_z partial[z]) / rowsum(H)  (:77), per-tile column sums of squares -> sumsq_part[row block][atom]
+//   pass 2  norm = sqrt(sum of the row-block partials) (:79); W = W' / norm (:80); W^T through a shared-memory transpose;
+//           per-tile column sums -> colsum_part[row block][atom] (the next H update's colsum(W)); norms[atom].
+// rowsum(H) = sum of `rowsum_slots` partial vectors (G2's epilogue) or one all-reduced vector.
+constexpr int kApplyTile = 32;
+__global__ void __launch_bounds__(kApplyTile * 8)
+tc_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, int splits, const float* __restrict__ rowsum,
+                   int rowsum_slots, int F, int K, float* __restrict__ sumsq_part) {
+  __shared__ float rs_s[kApplyTile];
+  __shared__ float part[8][kApplyTile + 1];
+  const int c = threadIdx.x, g = threadIdx.y;
+  const int k = blockIdx.x * kApplyTile + c;
   const int64_t slab = (int64_t)F * K;
   if (g == 0) {
     float rs = 0.f;
@@ -186,35 +193,54 @@ tc_apply_w_kernel(float* __restrict__ W, float* __restrict__ WT, int64_t ldwt, c
     rs_s[c] = rs;
   }
   __syncthreads();
-  // rows f = g, g + 32, ...: row-interleaved so that a warp reads 32 consecutive atoms of one row (coalesced)
   float sumsq = 0.f;
   if (k < K) {
     const float rs = rs_s[c];
-#pragma unroll 4
-    for (int f = g; f < F; f += kApplyGroups) {
-      const int64_t i = (int64_t)f * K + k;
-      float numer = partial[i];
-      for (int z = 1; z < splits; ++z) numer += partial[(int64_t)z * slab + i];
-      const float w = W[i] * (numer / rs);
-      W[i] = w;
-      sumsq += w * w;
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {
+      const int f = blockIdx.y * kApplyTile + g + 8 * r;
+      if (f < F) {
+        const int64_t i = (int64_t)f * K + k;
+        float numer = partial[i];
+        for (int z = 1; z < splits; ++z) numer += partial[(int64_t)z * slab + i];
+        const float w = W[i] * (numer / rs);
+        W[i] = w;
+        sumsq += w * w;
+      }
     }
   }
   part[g][c] = sumsq;
   __syncthreads();
+  if (g == 0 && k < K) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][c];
+    sumsq_part[(int64_t)blockIdx.y * K + k] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kApplyTile * 8)
+tc_apply_w2_kernel(float* __restrict__ W, float* __restrict__ WT, int64_t ldwt, const float* __restrict__ sumsq_part, int row_blocks,
+                   int F, int K, float* __restrict__ norms, float* __restrict__ colsum_part) {
+  __shared__ float norm_s[kApplyTile];
+  __shared__ float part[8][kApplyTile + 1];
+  __shared__ float tile[kApplyTile][kApplyTile + 1];
+  const int c = threadIdx.x, g = threadIdx.y;
+  const int k = blockIdx.x * kApplyTile + c;
   if (g == 0) {
     float s = 0.f;
-    for (int j = 0; j < kApplyGroups; ++j) s += part[j][c];
+    if (k < K)
+      for (int b = 0; b < row_blocks; ++b) s += sumsq_part[(int64_t)b * K + k];
     const float nrm = sqrtf(s);
     norm_s[c] = nrm;
-    if (k < K) norms[k] = nrm;
+    if (k < K && blockIdx.y == 0) norms[k] = nrm;
   }
   __syncthreads();
-  float csum = 0.f;
   const float nrm = norm_s[c];
-  __shared__ float tile[kApplyGroups][kApplyCols + 1];
-  for (int fb = 0; fb < F; fb += kApplyGroups) {   // 32 rows x 32 atoms per step
-    const int f = fb + g;
+  float csum = 0.f;
+#pragma unroll
+  for (int r = 0; r < kApplyTile / 8; ++r) {
+    const int fl = g + 8 * r, f = blockIdx.y * kApplyTile + fl;
     float w = 0.f;
     if (k < K && f < F) {
       const int64_t i = (int64_t)f * K + k;
@@ -222,32 +248,39 @@ tc_apply_w_kernel(float* __restrict__ W, float* __restrict__ WT, int64_t ldwt, c
       W[i] = w;
       csum += w;
     }
-    tile[g][c] = w;
-    __syncthreads();
-    // transposed write: thread (c, g) -> WT[atom = block*32 + g][f = fb + c]
-    const int kt = blockIdx.x * kApplyCols + g, ft = fb + c;
-    if (kt < K && ft < F) WT[(int64_t)kt * ldwt + ft] = tile[c][g];
-    __syncthreads();
+    tile[fl][c] = w;
   }
   part[g][c] = csum;
   __syncthreads();
   if (g == 0 && k < K) {
     float s = 0.f;
-    for (int j = 0; j < kApplyGroups; ++j) s += part[j][c];
-    colsum[k] = s;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][c];
+    colsum_part[(int64_t)blockIdx.y * K + k] = s;
+  }
+  // transposed write: WT[atom = block.x*32 + row-of-thread][f = block.y*32 + c]
+#pragma unroll
+  for (int r = 0; r < kApplyTile / 8; ++r) {
+    const int kl = g + 8 * r, kt = blockIdx.x * kApplyTile + kl, ft = blockIdx.y * kApplyTile + c;
+    if (kt < K && ft < F) WT[(int64_t)kt * ldwt + ft] = tile[c][kl];
   }
 }
 
-// H[k][t] *= norms[k] and HT[t][k] *= norms[k]   (:81, materialised)
-__global__ void tc_scale_h_kernel(float* H, int64_t ldh, float* HT, int64_t ldht, const float* norms, int K, int T2, int scale_ht) {
+// dst (rows, ld_dst) = src (rows, cols; ld_src), zero in the pad columns.
+__global__ void tc_copy_pad_kernel(const float* __restrict__ src, int64_t ld_src, int cols, float* __restrict__ dst, int64_t ld_dst, int rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * ld_dst) return;
+  const int r = (int)(i / ld_dst), c = (int)(i - (int64_t)r * ld_dst);
+  dst[i] = c < cols ? src[(int64_t)r * ld_src + c] : 0.f;
+}
+
+// H (caller, ld T2) = Hp * norms (pending :81) or a plain copy.
+__global__ void tc_finish_h_kernel(const float* __restrict__ Hp, int64_t ldp, const float* __restrict__ norms, float* __restrict__ H, int K, int T2) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)K * T2) return;
   const int k = (int)(i / T2), t = (int)(i - (int64_t)k * T2);
-  H[(int64_t)k * ldh + t] *= norms[k];
-  if (scale_ht) {
-    const int t2 = (int)(i / K), k2 = (int)(i - (int64_t)t2 * K);
-    HT[(int64_t)t2 * ldht + k2] *= norms[k2];
-  }
+  const float v = Hp[(int64_t)k * ldp + t];
+  H[i] = norms ? v * norms[k] : v;
 }
 
 // numer = [sum_z partial[z] (F*K) | sum_s rowsum_part[s] (K)] for the cross-rank all-reduce.
@@ -298,8 +331,9 @@ int tc_gemm(gccnmf_handle* h, GemmArgs args, int splits, const Epi& epi, void* s
 }
 
 struct TcWorkspace {
-  float *HT, *WT, *VT, *R, *RT, *partial, *colsum, *rowsum_part, *norms;
-  int64_t Fp;
+  float *HT, *WT, *VT, *R, *RT, *Hp, *partial, *colsum, *sumsq_part, *rowsum_part, *norms;
+  int row_blocks;
+  int64_t Fp, T2p;
   int splits, rowsum_slots;
   bool ok;
 };
@@ -319,16 +353,20 @@ TcWorkspace tc_carve(const gccnmf_handle* h, void* ws, size_t bytes, int F, int 
   WorkspaceCarver c(ws, bytes);
   TcWorkspace w;
   w.Fp = (F + 3) & ~3;
+  w.T2p = (T2 + 3) & ~3;
   w.splits = tc_pick_splits(m_tiles_of(F) * ((K + 127) / 128), (T2 + umma::kBK - 1) / umma::kBK, h->sm_count);
   const int bn = tile_width(h, m_tiles_of(K), T2, 1);          // G2's tile width decides the number of row-sum slots
   w.rowsum_slots = ((T2 + bn - 1) / bn) * 2;
   w.HT = c.take<float>((size_t)T2 * K);
   w.WT = c.take<float>((size_t)K * w.Fp);
   w.VT = c.take<float>((size_t)T2 * w.Fp);
-  w.R = c.take<float>((size_t)F * T2);
+  w.R = c.take<float>((size_t)F * w.T2p);
   w.RT = c.take<float>((size_t)T2 * w.Fp);
+  w.Hp = c.take<float>((size_t)K * w.T2p);
   w.partial = c.take<float>((size_t)kMaxSplits * F * K);
-  w.colsum = c.take<float>(K);
+  w.row_blocks = (F + kApplyTile - 1) / kApplyTile;
+  w.colsum = c.take<float>((size_t)w.row_blocks * K);
+  w.sumsq_part = c.take<float>((size_t)w.row_blocks * K);
   w.rowsum_part = c.take<float>((size_t)(2 * ((T2 + 127) / 128)) * K);
   w.norms = c.take<float>(K);
   w.ok = c.ok();
@@ -336,11 +374,12 @@ TcWorkspace tc_carve(const gccnmf_handle* h, void* ws, size_t bytes, int F, int 
 }
 
 size_t tc_workspace_bytes(int F, int T2, int K) {
-  const size_t Fp = (F + 3) & ~3;
+  const size_t Fp = (F + 3) & ~3, T2p = (T2 + 3) & ~3;
   size_t n = 0;
   auto add = [&](size_t count) { n = align_up(n, 256) + count * sizeof(float); };
-  add((size_t)T2 * K); add((size_t)K * Fp); add((size_t)T2 * Fp); add((size_t)F * T2); add((size_t)T2 * Fp);
-  add((size_t)kMaxSplits * F * K); add(K); add((size_t)(2 * ((T2 + 127) / 128)) * K); add(K);
+  add((size_t)T2 * K); add((size_t)K * Fp); add((size_t)T2 * Fp); add((size_t)F * T2p); add((size_t)T2 * Fp); add((size_t)K * T2p);
+  add((size_t)kMaxSplits * F * K); add((size_t)((F + 31) / 32) * K); add((size_t)((F + 31) / 32) * K);
+  add((size_t)(2 * ((T2 + 127) / 128)) * K); add(K);
   return align_up(n, 256);
 }
 
@@ -351,7 +390,7 @@ size_t tc_workspace_bytes(int F, int T2, int K) {
 }  // namespace
 
 // Whether the tensor-core path supports this problem (else the SIMT path in klnmf.cu is used).
-bool gccnmf_klnmf_tc_supported(int F, int T2, int K) { return K % 4 == 0 && T2 % 4 == 0 && F >= 128 && T2 >= 128 && K >= 32; }
+bool gccnmf_klnmf_tc_supported(int F, int T2, int K) { return K % 4 == 0 && F >= 128 && T2 >= 128 && K >= 32; }
 size_t gccnmf_klnmf_tc_workspace_bytes(int F, int T2, int K) { return tc_workspace_bytes(F, T2, K); }
 
 // Transposes / pads the caller's V, W, H into the k-contiguous operand set.
@@ -364,14 +403,20 @@ int gccnmf_klnmf_tc_prepare(gccnmf_handle* h, const float* V, int F, int T2, con
     GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.RT, 0, (size_t)T2 * w.Fp * sizeof(float), (cudaStream_t)stream));
   }
   if (need_wt) GCCNMF_LAUNCH(h, transpose_pad_kernel, dim3((K + 31) / 32, (F + 31) / 32 + 1), block, 0, stream, W, F, K, (int64_t)K, w.WT, w.Fp);
-  if (need_ht) GCCNMF_LAUNCH(h, transpose_pad_kernel, dim3((T2 + 31) / 32, (K + 31) / 32), block, 0, stream, H, K, T2, (int64_t)T2, w.HT, (int64_t)K);
+  if (need_ht) {
+    GCCNMF_LAUNCH(h, transpose_pad_kernel, dim3((T2 + 31) / 32, (K + 31) / 32), block, 0, stream, H, K, T2, (int64_t)T2, w.HT, (int64_t)K);
+    GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.R, 0, (size_t)F * w.T2p * sizeof(float), (cudaStream_t)stream));
+    const int64_t n = (int64_t)K * w.T2p;
+    GCCNMF_LAUNCH(h, tc_copy_pad_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, H, (int64_t)T2, T2, w.Hp, w.T2p, K);
+  }
   return 0;
 }
 
 // :76 (preceded by the pending :81 when pending_norms): H = (n*H) * (W^T (V / (W (n*H)))) / (colsum(W) + alpha + eps).
 // Requires prepare(); keeps H and HT in sync and leaves per-row partial sums of the new H in the workspace.
 int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
-                             void* workspace, size_t workspace_bytes, bool have_colsum, bool pending_norms, void* stream) {
+                             void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream) {
+  // colsum_state: 0 = compute colsum(W) now; 1 = reuse the one computed before (fixed dictionary); 2 = per-row-block partials left by the W update
   TC_CARVE_OR_FAIL(w);
   (void)V;
   const float* pending = pending_norms ? w.norms : nullptr;
@@ -381,11 +426,12 @@ int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, co
     const int st = pending ? tc_gemm<true>(h, a, 1, e, stream) : tc_gemm<false>(h, a, 1, e, stream);
     if (st) return st;
   }
-  if (!have_colsum) GCCNMF_LAUNCH(h, tc_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
+  if (colsum_state == 0) GCCNMF_LAUNCH(h, tc_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
   GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.rowsum_part, 0, (size_t)w.rowsum_slots * K * sizeof(float), (cudaStream_t)stream));
   {  // G2: H, HT = (n*H) * (WT.RT^T) / denom
     GemmArgs a{w.WT, w.RT, K, T2, F, w.Fp, w.Fp, 0, 0, nullptr};
-    EpiUpdateHBoth e{H, w.HT, w.colsum, pending, w.rowsum_part, alpha, eps, (int64_t)T2, (int64_t)K, K, T2};
+    EpiUpdateHBoth e{w.Hp, w.HT, w.colsum, pending, w.rowsum_part, alpha, eps, w.T2p, (int64_t)K, K, T2, colsum_state == 2 ? w.row_blocks : 1};
+    (void)H;
     const int bn = tile_width(h, m_tiles_of(K), T2, 1);
     if (int st = tc_gemm<false>(h, a, 1, e, stream, bn)) return st;
   }
@@ -398,43 +444,42 @@ int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, c
   TC_CARVE_OR_FAIL(w);
   {  // G3: R = V / (W.H)
     GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, nullptr};
-    EpiRatioRow e{V, w.R, (int64_t)T2, (int64_t)T2, F, T2};
+    EpiRatioRow e{V, w.R, (int64_t)T2, w.T2p, F, T2};
     if (int st = tc_gemm<false>(h, a, 1, e, stream)) return st;
   }
   if (!have_rowsum) {   // stateless building block: H may not be the one update_H just wrote
     GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.rowsum_part, 0, (size_t)w.rowsum_slots * K * sizeof(float), (cudaStream_t)stream));
-    GCCNMF_LAUNCH(h, tc_rowsum_kernel, K, 256, 0, stream, H, T2, (int64_t)T2, w.rowsum_part);
+    GCCNMF_LAUNCH(h, tc_rowsum_kernel, K, 256, 0, stream, w.Hp, T2, w.T2p, w.rowsum_part);
   }
   {  // G4: partial[z] = R.H^T
-    GemmArgs a{w.R, H, F, K, T2, (int64_t)T2, (int64_t)T2, 0, 0, nullptr};
+    (void)H;
+    GemmArgs a{w.R, w.Hp, F, K, T2, w.T2p, w.T2p, 0, 0, nullptr};
     EpiStoreRowMajor e{w.partial, (int64_t)K, F, K, (int64_t)F * K};
     if (int st = tc_gemm<false>(h, a, w.splits, e, stream)) return st;
   }
   return 0;
 }
 
-// :77-:80 (and :81 when scale_h).  Numerator and row sums come from `numer` (F*K + K floats, all-reduced
-// across ranks) when given, else from this rank's split partials and row-sum slots.
-int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer,
-                            void* workspace, size_t workspace_bytes, bool scale_h, bool scale_ht, void* stream) {
+// :77-:80; the H rescale of :81 stays pending (applied by the next update_H, or by finish).  Numerator and row
+// sums come from `numer` (F*K + K floats, all-reduced across ranks) when given, else from this rank's partials.
+int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer,
+                            void* workspace, size_t workspace_bytes, void* stream) {
   TC_CARVE_OR_FAIL(w);
   const float* partial = numer ? numer : w.partial;
   const float* rowsum = numer ? numer + (int64_t)F * K : w.rowsum_part;
-  GCCNMF_LAUNCH(h, tc_apply_w_kernel, (K + kApplyCols - 1) / kApplyCols, kApplyCols * kApplyGroups, 0, stream, W, w.WT, w.Fp,
-                partial, numer ? 1 : w.splits, rowsum, numer ? 1 : w.rowsum_slots, F, K, w.norms, w.colsum);
-  if (scale_h) {
-    const int64_t n = (int64_t)K * T2;
-    GCCNMF_LAUNCH(h, tc_scale_h_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, H, (int64_t)T2, w.HT, (int64_t)K, w.norms, K, T2,
-                  scale_ht ? 1 : 0);
-  }
+  const dim3 grid((K + kApplyTile - 1) / kApplyTile, w.row_blocks), block(kApplyTile, 8);
+  GCCNMF_LAUNCH(h, tc_apply_w1_kernel, grid, block, 0, stream, W, partial, numer ? 1 : w.splits, rowsum, numer ? 1 : w.rowsum_slots,
+                F, K, w.sumsq_part);
+  GCCNMF_LAUNCH(h, tc_apply_w2_kernel, grid, block, 0, stream, W, w.WT, w.Fp, w.sumsq_part, w.row_blocks, F, K, w.norms, w.colsum);
   return 0;
 }
 
-// Materialises a pending H *= norms (after the last lazily-scaled iteration).
-int gccnmf_klnmf_tc_flush_scale(gccnmf_handle* h, int F, int T2, float* H, int K, void* workspace, size_t workspace_bytes, void* stream) {
+// Writes the caller's H from the working copy, applying a pending H *= norms (:81) when there is one.
+int gccnmf_klnmf_tc_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   TC_CARVE_OR_FAIL(w);
   const int64_t n = (int64_t)K * T2;
-  GCCNMF_LAUNCH(h, tc_scale_h_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, H, (int64_t)T2, w.HT, (int64_t)K, w.norms, K, T2, 1);
+  GCCNMF_LAUNCH(h, tc_finish_h_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, w.Hp, w.T2p, pending_norms ? w.norms : nullptr, H, K, T2);
   return 0;
 }
 

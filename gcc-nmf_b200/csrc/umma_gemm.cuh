@@ -145,41 +145,43 @@ struct GemmSmem {
 };
 
 // One thread's share of a [ROWS x 32] float tile: chunk column c = tid % 8 (4 floats), rows tid / 8 + 32 i.
+// Rows past the end of the matrix are clamped to its last row (their products land in accumulator rows /
+// columns the epilogue never stores), so the only predicate left is the k tail, uniform per thread.
 template <int ROWS>
 struct TileLoader {
   static constexpr int kChunks = ROWS * 8 / kLoaderThreads;
-  const float* ptr;       // first chunk of this thread at k-block 0
-  int64_t row_stride;     // 32 rows further down
-  uint32_t valid;         // bit i: row of chunk i is inside the matrix
-  int kcol;               // c * 4
-  uint32_t smem_off;      // swizzled byte offset of chunk 0 inside the tile; chunk i is + 4096 i
+  const float* ptr[kChunks];   // chunk i of this thread at the current k-block; advanced by 32 floats per fetch
+  int kcol;                    // c * 4
+  uint32_t smem_off;           // swizzled byte offset of chunk 0 inside the tile; chunk i is + 4096 i
 
-  __device__ __forceinline__ void init(const float* src, int64_t ld, int row0, int rows_valid, int tid) {
+  __device__ __forceinline__ void init(const float* src, int64_t ld, int row0, int rows_valid, int k0, int tid) {
     const int r = tid >> 3, c = tid & 7;
-    ptr = src + (int64_t)(row0 + r) * ld + c * 4;
-    row_stride = 32 * ld;
     kcol = c * 4;
-    valid = 0;
 #pragma unroll
-    for (int i = 0; i < kChunks; ++i) valid |= (row0 + r + 32 * i < rows_valid ? 1u : 0u) << i;
+    for (int i = 0; i < kChunks; ++i) ptr[i] = src + (int64_t)min(row0 + r + 32 * i, rows_valid - 1) * ld + k0 + kcol;
     smem_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
   }
-  __device__ __forceinline__ void fetch(float4 (&regs)[kChunks], int k0, int kc4) const {
-    const bool kok = k0 + kcol < kc4;
+  // loads the k-block starting at column k0 (the pointers already point there) and advances to the next one
+  __device__ __forceinline__ void fetch(float4 (&regs)[kChunks], int k0, int kc4) {
+    if (k0 + kcol < kc4) {
 #pragma unroll
-    for (int i = 0; i < kChunks; ++i) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kok && ((valid >> i) & 1u)) v = __ldg(reinterpret_cast<const float4*>(ptr + (int64_t)i * row_stride + k0));
-      regs[i] = v;
+      for (int i = 0; i < kChunks; ++i) regs[i] = __ldg(reinterpret_cast<const float4*>(ptr[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) regs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) ptr[i] += kBK;
   }
+  // hi = tf32(x) (round to nearest), lo = x - hi exactly (|lo| <= 2^-11 |x|; the tensor core drops its bits
+  // below tf32 resolution: <= 2^-21 |x|, sign-symmetric)
   __device__ __forceinline__ void stash(const float4 (&regs)[kChunks], unsigned char* hi, unsigned char* lo) const {
 #pragma unroll
     for (int i = 0; i < kChunks; ++i) {
       const float4 x = regs[i];
       float4 h, l;
       h.x = tf32_round(x.x); h.y = tf32_round(x.y); h.z = tf32_round(x.z); h.w = tf32_round(x.w);
-      l.x = tf32_round(x.x - h.x); l.y = tf32_round(x.y - h.y); l.z = tf32_round(x.z - h.z); l.w = tf32_round(x.w - h.w);
+      l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
       *reinterpret_cast<float4*>(hi + smem_off + i * 4096) = h;
       *reinterpret_cast<float4*>(lo + smem_off + i * 4096) = l;
     }
@@ -271,8 +273,8 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
     // ------------------------------------------------------------------ loaders
     TileLoader<kBM> la;
     TileLoader<BN> lb;
-    la.init(args.A, args.lda, m0, min(args.M, args.m_tiles * kBM), tid);
-    lb.init(args.B, args.ldb, n0, args.N, tid);
+    la.init(args.A, args.lda, m0, min(args.M, args.m_tiles * kBM), kb_begin * kBK, tid);
+    lb.init(args.B, args.ldb, n0, args.N, kb_begin * kBK, tid);
     // two register sets: the global loads of k-block i+2 are in flight while k-block i+1 is split and stored
     float4 a0[TileLoader<kBM>::kChunks], b0[TileLoader<BN>::kChunks], a1[TileLoader<kBM>::kChunks], b1[TileLoader<BN>::kChunks];
     float4 s0, s1;

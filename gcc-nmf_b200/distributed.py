@@ -73,13 +73,15 @@ class ShardComm(object):
 
 
 def klnmf_sharded(ops, comm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon, numer):
-    """gccNMFFunctions.py:75-81 on frame shards.  `ops` provides the three C-ABI building blocks
-    (klnmf_update_H, klnmf_partial_W, klnmf_apply_W); `numer` is an (F*K + K) float32 buffer."""
-    for _ in range(numIterations):
-        ops.klnmf_update_H(V_s, W, H_s, sparsityAlpha, epsilon)
-        ops.klnmf_partial_W(V_s, W, H_s, numer)
+    """gccNMFFunctions.py:75-81 on frame shards.  `ops` provides the C-ABI step protocol
+    (klnmf_begin / klnmf_step_numer / klnmf_step_apply / klnmf_end, include/gccnmf_b200.h);
+    `numer` is an (F*K + K) float32 buffer: the single all-reduce per iteration."""
+    ops.klnmf_begin(V_s, W, H_s)
+    for it in range(numIterations):
+        ops.klnmf_step_numer(V_s, W, H_s, it, numer, sparsityAlpha, epsilon)
         comm.all_reduce_sum(numer)
-        ops.klnmf_apply_W(W, H_s, numer)
+        ops.klnmf_step_apply(W, H_s, numer)
+    ops.klnmf_end(W, H_s, numIterations)
     return W, H_s
 
 
@@ -146,6 +148,19 @@ class ShardedGCCNMFPipeline(object):
         ev = self.stage_events
         return {ev[i + 1][0]: ev[i][1].elapsed_time(ev[i + 1][1]) for i in range(len(ev) - 1)}
 
+    def _agree_on_nmf_path(self, T2):
+        """All ranks must run the W update with the same kernels (bit-identical W): if any rank's shard
+        shape falls back to the SIMT contractions, every rank does.  Decided once."""
+        if getattr(self, '_path_agreed', False):
+            return
+        flag = self.torch.tensor([1 if self.h.klnmf_uses_tensor_cores(self.F, T2, self.K) else 0],
+                                 dtype=self.torch.int32, device=self.h.device)
+        if self.comm.world > 1:
+            self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+        if int(flag.item()) == 0:
+            self.h.set_option('force_simt_nmf', 1)
+        self._path_agreed = True
+
     def enhance(self, samples, collect_stage_times=False):
         h, torch, comm = self.h, self.torch, self.comm
         self.stage_events = [] if collect_stage_times else None
@@ -160,6 +175,7 @@ class ShardedGCCNMFPipeline(object):
         mean_host = (total / float(self.total_frames)).cpu().numpy()
         self._mark('angular')
         W, H = self.W0.clone(), self.H0s.clone()
+        self._agree_on_nmf_path(V.shape[1])
         klnmf_sharded(h, comm, V, W, H, self.I, self.alpha, self.eps, self.numer)
         self._mark('nmf')
         _, argmax = h.tdoa_gccnmf(coh, self.E, W, want_values=False, want_argmax=True)

@@ -57,6 +57,9 @@ GCCNMF_API const char* gccnmf_last_error(const gccnmf_handle* h);
 GCCNMF_API const char* gccnmf_status_string(int status);
 /* Count of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 GCCNMF_API int64_t gccnmf_launch_count(const gccnmf_handle* h);
+/* Options: "force_simt_nmf" (0/1): run the KL-NMF contractions on the float32 SIMT kernels even where the
+ * tcgen05 path applies (all ranks of a sharded run must use the same path so that W stays bit-identical). */
+GCCNMF_API int gccnmf_set_option(gccnmf_handle* h, const char* name, int value);
 
 /* ---- a1: STFT  (gccNMF/librosaSTFT.py:20-181 via gccNMFFunctions.py:61-67) ------------------ */
 /* Frame count 1 + (num_samples - n_fft) / hop (librosaSTFT.py:425); <1 -> GCCNMF_ERR_INVALID_ARGUMENT. */
@@ -103,21 +106,28 @@ GCCNMF_API int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, flo
                  int iterations, float sparsity_alpha, float epsilon, int update_W,
                  void* workspace, size_t workspace_bytes, void* stream);
 /*
- * Frame-sharded building blocks (multi-GPU dictionary learning).  One
- * iteration on a rank holding columns V_s (F, T2s), H_s (K, T2s) and a replicated W is
- *   gccnmf_klnmf_update_H   (H_s update, :76)
- *   gccnmf_klnmf_partial_W  (numerator (V_s/(W H_s)).H_s^T (F,K) and rowsum(H_s) (K) into `numer`,
- *                            laid out as F*K + K contiguous floats -> one all-reduce)
- *   gccnmf_klnmf_apply_W    (W *= numer/rowsum (:77), unit-L2 atoms (:79-80), H_s *= norms (:81))
+ * Frame-sharded dictionary learning (multi-GPU).  A rank holds the columns V_s
+ * (F, T2s), H_s (K, T2s) of its frames and a replica of W.  The loop of gccNMFFunctions.py:75-81 becomes
+ *
+ *   gccnmf_klnmf_begin(...)                       once (operand re-layout for the tensor-core path)
+ *   for it in range(iterations):
+ *       gccnmf_klnmf_step_numer(..., it, numer)   H_s update (:76); numer = [ (V_s/(W H_s)).H_s^T (F*K) | rowsum(H_s) (K) ]
+ *       all-reduce(sum) of numer over the ranks   ONE collective of F*K + K floats per iteration
+ *       gccnmf_klnmf_step_apply(..., numer)       W *= numer / rowsum (:77), unit-L2 atoms (:79-80), H_s *= norms (:81)
+ *   gccnmf_klnmf_end(..., iterations)             materialises the last (lazily applied) H_s rescale
+ *
+ * All state lives in W, H and the caller-owned workspace (gccnmf_klnmf_workspace_bytes), which must not be
+ * touched between begin and end.  Every rank computes a bit-identical W from the same all-reduced numer.
  */
-GCCNMF_API int gccnmf_klnmf_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H,
-                          int K, float sparsity_alpha, float epsilon, void* workspace,
-                          size_t workspace_bytes, void* stream);
-GCCNMF_API int gccnmf_klnmf_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W,
-                           const float* H, int K, float* numer, void* workspace,
-                           size_t workspace_bytes, void* stream);
-GCCNMF_API int gccnmf_klnmf_apply_W(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
-                         const float* numer, void* workspace, size_t workspace_bytes, void* stream);
+GCCNMF_API int gccnmf_klnmf_begin(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H,
+                       int K, void* workspace, size_t workspace_bytes, void* stream);
+GCCNMF_API int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H,
+                            int K, float sparsity_alpha, float epsilon, int iteration, float* numer,
+                            void* workspace, size_t workspace_bytes, void* stream);
+GCCNMF_API int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
+                            const float* numer, void* workspace, size_t workspace_bytes, void* stream);
+GCCNMF_API int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a3 + a4: PHAT coherence and angular spectrogram  (runGCCNMF.py:44, gccNMFFunctions.py:85-92) */
 /*

@@ -16,29 +16,33 @@ from oracle import gccnmf_oracle as orc
 
 
 class NumpyOps(object):
-    """Stand-in for Handle.klnmf_update_H / klnmf_partial_W / klnmf_apply_W on CPU tensors
+    """Stand-in for Handle.klnmf_begin / klnmf_step_numer / klnmf_step_apply / klnmf_end on CPU tensors
     (gccNMFFunctions.py:76, :77 numerator, :77-81 apply)."""
 
     @staticmethod
-    def klnmf_update_H(V, W, H, alpha, eps):
-        Vn, Wn, Hn = V.numpy(), W.numpy(), H.numpy()
-        Hn *= np.dot(Wn.T, Vn / np.dot(Wn, Hn)) / (np.sum(Wn, axis=0)[:, None] + np.float32(alpha) + np.float32(eps))
+    def klnmf_begin(V, W, H):
+        pass
 
     @staticmethod
-    def klnmf_partial_W(V, W, H, numer):
+    def klnmf_step_numer(V, W, H, iteration, numer, alpha, eps):
         Vn, Wn, Hn = V.numpy(), W.numpy(), H.numpy()
+        Hn *= np.dot(Wn.T, Vn / np.dot(Wn, Hn)) / (np.sum(Wn, axis=0)[:, None] + np.float32(alpha) + np.float32(eps))
         F, K = Wn.shape
         numer.numpy()[:F * K] = np.dot(Vn / np.dot(Wn, Hn), Hn.T).ravel()
         numer.numpy()[F * K:] = np.sum(Hn, axis=1)
 
     @staticmethod
-    def klnmf_apply_W(W, H, numer):
+    def klnmf_step_apply(W, H, numer):
         Wn, Hn = W.numpy(), H.numpy()
         F, K = Wn.shape
         Wn *= numer.numpy()[:F * K].reshape(F, K) / numer.numpy()[F * K:]
         norms = np.sqrt(np.sum(Wn ** 2, 0))
         Wn /= norms
         Hn *= norms[:, None]
+
+    @staticmethod
+    def klnmf_end(W, H, iterations_done):
+        pass
 
 
 def _free_port():

@@ -104,10 +104,11 @@ def test_klnmf_building_blocks_equal_fused(golden, h):
     h.klnmf(V, W1, H1, 2, 0.0, 1e-16)
     F, K = W2.shape
     numer = torch.empty(F * K + K, dtype=torch.float32, device=V.device)
-    for _ in range(2):
-        h.klnmf_update_H(V, W2, H2)
-        h.klnmf_partial_W(V, W2, H2, numer)
-        h.klnmf_apply_W(W2, H2, numer)
+    h.klnmf_begin(V, W2, H2)
+    for it in range(2):
+        h.klnmf_step_numer(V, W2, H2, it, numer)
+        h.klnmf_step_apply(W2, H2, numer)
+    h.klnmf_end(W2, H2, 2)
     assert torch.equal(W1, W2) and torch.equal(H1, H2)
 
 

@@ -62,16 +62,17 @@ def test_klnmf_tensor_core_path_matches_oracle(h):
         eW, eH = rel(W.cpu().numpy(), Wo), rel(H.cpu().numpy(), Ho)
         print('tensor-core KL-NMF %d iterations: rel W %.2e  rel H %.2e' % (iters, eW, eH))
         assert eW < tol and eH < tol, (iters, eW, eH)
-    # building blocks (multi-GPU protocol) equal the fused loop bit for bit
+    # step protocol (multi-GPU) against the fused loop
     V_d = h.to_device(V)
     W1, H1 = h.to_device(W0.copy()), h.to_device(H0.copy())
     W2, H2 = W1.clone(), H1.clone()
     h.klnmf(V_d, W1, H1, 2)
     numer = torch.empty(F * K + K, dtype=torch.float32, device=V_d.device)
-    for _ in range(2):
-        h.klnmf_update_H(V_d, W2, H2)
-        h.klnmf_partial_W(V_d, W2, H2, numer)
-        h.klnmf_apply_W(W2, H2, numer)
+    h.klnmf_begin(V_d, W2, H2)
+    for it in range(2):
+        h.klnmf_step_numer(V_d, W2, H2, it, numer)
+        h.klnmf_step_apply(W2, H2, numer)
+    h.klnmf_end(W2, H2, 2)
     assert rel(W2.cpu().numpy(), W1.cpu().numpy()) < 1e-6 and rel(H2.cpu().numpy(), H1.cpu().numpy()) < 1e-6
     # fixed dictionary (H-only inference)
     Hi = h.to_device(H0.copy())
