@@ -55,6 +55,9 @@ SIGNATURES = {
     'gccnmf_phat_angspec_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_phat_angspec': (c_int, [_H, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _S]),
     'gccnmf_tdoa_gccnmf': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _S]),
+    'gccnmf_tdoa_argmax_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'gccnmf_tdoa_argmax_refine_capacity': (c_int, [c_int, c_int]),
+    'gccnmf_tdoa_argmax': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_size_t, _S]),
     'gccnmf_coeff_mask': (c_int, [_H, _P, c_int, c_int, c_int, _P, _P, _S]),
     'gccnmf_argmax_mask': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, _S]),
     'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
@@ -108,6 +111,7 @@ class Handle(object):
                                                                  self.lib.gccnmf_last_error(None).decode()))
         self.h = h
         self._workspaces = {}
+        self._buffers = {}
 
     def close(self):
         if getattr(self, 'h', None):
@@ -154,6 +158,18 @@ class Handle(object):
     def empty(self, shape, dtype):
         return self.torch.empty(shape, dtype=dtype, device=self.device)
 
+    def buffer(self, key, shape, dtype):
+        """Persistent device buffer per (key, shape, dtype): allocated once (plan time), reused by every
+        later call, so steady-state pipelines never enter the allocator (a cudaMalloc costs milliseconds)."""
+        full_key = (key, tuple(int(v) for v in shape), dtype)
+        t = self._buffers.get(full_key)
+        if t is None:
+            t = self._buffers[full_key] = self.torch.empty(shape, dtype=dtype, device=self.device)
+        return t
+
+    def _out(self, out_key, name, shape, dtype):
+        return self.empty(shape, dtype) if out_key is None else self.buffer((out_key, name), shape, dtype)
+
     def to_device(self, array, dtype=None):
         t = self.torch.as_tensor(array)
         if dtype is not None:
@@ -161,7 +177,7 @@ class Handle(object):
         return t.contiguous().to(self.device, non_blocking=True)
 
     # ------------------------------------------------------------------ ops (device tensors in / out)
-    def stft(self, samples, window, n_fft, hop, conjugate=True, want_V=False):
+    def stft(self, samples, window, n_fft, hop, conjugate=True, want_V=False, out_key=None):
         """samples (C, n) f32 cuda, window (n_fft) f64 cuda -> X (C, F, T) c64 [, V (F, C*T) f32]."""
         torch = self.torch
         C, n = samples.shape
@@ -171,18 +187,18 @@ class Handle(object):
                 raise ParameterError('Invalid hop_length: %d' % hop)
             raise ParameterError('Buffer is too short (n=%d) for frame_length=%d' % (n, n_fft))
         F = n_fft // 2 + 1
-        X = self.empty((C, F, T), torch.complex64)
-        V = self.empty((F, C * T), torch.float32) if want_V else None
+        X = self._out(out_key, 'X', (C, F, T), torch.complex64)
+        V = self._out(out_key, 'V', (F, C * T), torch.float32) if want_V else None
         self.check(self.lib.gccnmf_stft(self.h, _ptr(samples), samples.stride(0), C, n, _ptr(window), n_fft, hop,
                                         1 if conjugate else 0, _ptr(X), _ptr(V), self.stream))
         return (X, V) if want_V else X
 
-    def istft_ola(self, spec, window, n_fft, hop, gain=1.0, center=True, conjugate=True):
+    def istft_ola(self, spec, window, n_fft, hop, gain=1.0, center=True, conjugate=True, out_key=None):
         """spec (B, F, T) c64 cuda -> y (B, length) f32."""
         torch = self.torch
         B, F, T = spec.shape
         length = self.lib.gccnmf_istft_length(n_fft, hop, T, 1 if center else 0)
-        y = self.empty((B, max(int(length), 0)), torch.float32)
+        y = self._out(out_key, 'y', (B, max(int(length), 0)), torch.float32)
         nbytes = self.lib.gccnmf_istft_workspace_bytes(B, n_fft, T)
         ws = self.workspace('istft', nbytes)
         self.check(self.lib.gccnmf_istft_ola(self.h, _ptr(spec), B, n_fft, hop, T, _ptr(window), float(gain),
@@ -228,16 +244,16 @@ class Handle(object):
         ws = self._klnmf_ws(F, T2, K)
         self.check(self.lib.gccnmf_klnmf_end(self.h, F, T2, _ptr(W), _ptr(H), K, int(iterations_done), _ptr(ws), ws.numel(), self.stream))
 
-    def phat_angspec(self, X, E=None, want_coherence=True, want_angular=True, want_mean=True):
+    def phat_angspec(self, X, E=None, want_coherence=True, want_angular=True, want_mean=True, out_key=None):
         """X (2, F, T) c64 mixture spectrogram -- or an (F, T) c64 coherence used as is -- and
         E (F, D) c128 -> (coherence (F,T) c64, angular (D,T) f64, mean (D) f64)."""
         torch = self.torch
         is_coh = X.dim() == 2
         F, T = X.shape[-2:]
         D = E.shape[1] if E is not None else 0
-        coh = self.empty((F, T), torch.complex64) if want_coherence else None
-        ang = self.empty((D, T), torch.float64) if (want_angular and D) else None
-        mean = self.empty((D,), torch.float64) if (want_mean and D) else None
+        coh = self._out(out_key, 'coh', (F, T), torch.complex64) if want_coherence else None
+        ang = self._out(out_key, 'ang', (D, T), torch.float64) if (want_angular and D) else None
+        mean = self._out(out_key, 'mean', (D,), torch.float64) if (want_mean and D) else None
         ws = self.workspace('angspec', self.lib.gccnmf_phat_angspec_workspace_bytes(F, T, max(D, 1)))
         self.check(self.lib.gccnmf_phat_angspec(self.h, _ptr(X), F, T, 1 if is_coh else 0, _ptr(E), D, _ptr(coh), _ptr(ang), _ptr(mean),
                                                 _ptr(ws), ws.numel(), self.stream))
@@ -255,6 +271,19 @@ class Handle(object):
                                                _ptr(argmax), self.stream))
         return values, argmax
 
+    def tdoa_argmax(self, coherence, E, W, out_key=None):
+        """argmax over all TDOAs (K, T) int32: tensor-core GEMM + exact float64 refinement of near-ties
+        (float64 kernel for shapes the fast path does not cover).  Returns (argmax, refined_count tensor)."""
+        torch = self.torch
+        F, T = coherence.shape
+        D, K = E.shape[1], W.shape[1]
+        argmax = self._out(out_key, 'argmax', (K, T), torch.int32)
+        refined = self._out(out_key, 'refined', (1,), torch.int32)
+        ws = self.workspace('tdoa_argmax', self.lib.gccnmf_tdoa_argmax_workspace_bytes(F, T, D, K))
+        self.check(self.lib.gccnmf_tdoa_argmax(self.h, _ptr(coherence), F, T, _ptr(E), D, _ptr(W), K, _ptr(argmax), _ptr(refined),
+                                               _ptr(ws), ws.numel(), self.stream))
+        return argmax, refined
+
     def coeff_mask(self, gccnmfs):
         torch = self.torch
         S, K, T = gccnmfs.shape
@@ -263,19 +292,19 @@ class Handle(object):
         self.check(self.lib.gccnmf_coeff_mask(self.h, _ptr(gccnmfs), S, K, T, _ptr(masks), _ptr(flag), self.stream))
         return masks, flag
 
-    def argmax_mask(self, argmax, lut):
+    def argmax_mask(self, argmax, lut, out_key=None):
         torch = self.torch
         K, T = argmax.shape
-        mask = self.empty((K, T), torch.float32)
+        mask = self._out(out_key, 'mask', (K, T), torch.float32)
         self.check(self.lib.gccnmf_argmax_mask(self.h, _ptr(argmax), K, T, _ptr(lut), lut.numel(), _ptr(mask), self.stream))
         return mask
 
-    def masked_recon_phase(self, masks, X, W, H):
+    def masked_recon_phase(self, masks, X, W, H, out_key=None):
         """masks (S,K,T) f32, X (2,F,T) c64, W (F,K), H (K,2T) -> (S,2,F,T) c64."""
         torch = self.torch
         S, K, T = masks.shape
         F = X.shape[1]
-        out = self.empty((S, 2, F, T), torch.complex64)
+        out = self._out(out_key, 'est', (S, 2, F, T), torch.complex64)
         self.check(self.lib.gccnmf_masked_recon_phase(self.h, _ptr(masks), _ptr(X), _ptr(W), _ptr(H), S, F, T, K,
                                                       _ptr(out), self.stream))
         return out

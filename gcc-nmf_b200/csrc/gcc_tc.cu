@@ -1,0 +1,240 @@
+// All-TDOA GCC-NMF argmax on the tensor cores with exact float64 refinement
+// (reference: notebooks/offlineSpeechEnhancement.ipynb cells 27+29, :444-467; online :422-423).
+//
+//   gccNMF[k, tau, t] = sum_f W[f, k] * Re(C[f, t] E[f, tau])        argmax over tau per (k, t)
+//
+// The reference evaluates this in float64 and the argmax must be the reference's, bit for bit.  A
+// float64 contraction is 126 GFLOP at the headline shape (10.9 ms on the SIMT float64 kernel), so:
+//   1. build  G[(t, tau), f] = Re(C E)  once, float64 product rounded to float32            (HBM-bound)
+//   2. argmax over tau of  W^T . G^T  with the 3xTF32 tcgen05 GEMM (M = atoms, N = (t, tau), over f):
+//      the epilogue keeps, per (atom, frame), the best and second-best value and the index of the best;
+//   3. every (atom, frame) whose margin best - second is below the worst-case error of step 2
+//      (kMarginFactor * sum_f |W[f, atom]|, since |G| <= 1) is appended to a list and recomputed EXACTLY in
+//      float64 from C, E and W by a warp (the same arithmetic as the float64 kernel in gcc.cu).
+// Decisions with a safe margin cannot differ from the float64 ones; the others are the float64 ones.
+#include <algorithm>
+
+#include "common.cuh"
+#include "umma_gemm.cuh"
+
+namespace {
+
+using umma::GemmArgs;
+
+// Error budget of step 2 relative to sum_f |W| (|G| <= 1): operand split 2^-21, float32 rounding of G 2^-24,
+// accumulator truncation <= 2^-24 per accumulation x (3 F / 8) accumulations (measured 1.2e-5 at 384, tests/test_gpu_umma.py).
+// Margin = 2 x (1.5e-5 + slack): two values each off by the bound.
+constexpr float kMarginFactor = 6e-5f;
+
+// ------------------------------------------------------------------ step 1: G[(t, tau)][f]
+__global__ void __launch_bounds__(256)
+build_gcc_matrix_kernel(const float2* __restrict__ coh, int F, int T, const double2* __restrict__ E, int D, float* __restrict__ G, int64_t ldg) {
+  __shared__ float2 Cs[32][33];   // [f][t]
+  const int f0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = w; i < 32; i += 8) {
+    const int f = f0 + i, t = t0 + lane;
+    Cs[i][lane] = (f < F && t < T) ? coh[(int64_t)f * T + t] : float2{0.f, 0.f};
+  }
+  __syncthreads();
+  const int f = f0 + lane;
+  // each warp handles frames w, w+8, ...; lane = f (coalesced 128-byte row segments of G)
+  for (int tt = w; tt < 32; tt += 8) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    const float2 c = Cs[lane][tt];
+    for (int d = 0; d < D; ++d) {
+      float v = 0.f;
+      if (f < F) {
+        const double2 e = __ldg(E + (int64_t)f * D + d);
+        v = (float)((double)c.x * e.x - (double)c.y * e.y);
+      }
+      if (f < ldg) G[((int64_t)t * D + d) * ldg + f] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ step 2: epilogue
+struct EpiArgmaxTDOA {
+  struct State { float best, second; int idx; int nan; };
+  int32_t* __restrict__ argmax;        // (K, T)
+  const float* __restrict__ colsumW;   // (K) sum_f |W[f,k]| = colsum (W >= 0)
+  int2* __restrict__ list; int* __restrict__ count; int capacity;
+  int K, T, D, N;
+  __device__ void init(State& s) const { s.best = -INFINITY; s.second = -INFINITY; s.idx = 0; s.nan = 0; }
+  __device__ void elem(int, int, float, int) const {}   // M = atoms is tiled without SIMT tail rows (K % 128 handled by predication)
+  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int, float*, State& s) const {
+    const int d0 = n0 % D;
+    if (d0 == 0) init(s);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = v[j];
+      if (x != x) s.nan = 1;                 // NaN anywhere: let float64 decide with numpy's NaN rules
+      if (x > s.best) { s.second = s.best; s.best = x; s.idx = d0 + j; }
+      else if (x > s.second) s.second = x;
+    }
+    if (d0 + 32 == D) {
+      const int m = m_base + lane, t = n0 / D;
+      if (m < K && n0 < N) {
+        argmax[(int64_t)m * T + t] = s.idx;
+        const float margin = kMarginFactor * colsumW[m];
+        if (s.nan || !(s.best - s.second > margin)) {
+          const int slot = atomicAdd(count, 1);
+          if (slot < capacity) list[slot] = make_int2(m, t);
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ step 3: exact float64 recomputation of flagged (atom, frame) pairs
+__device__ __forceinline__ bool argmax_better64(double v, int i, double bv, int bi) {   // numpy.argmax: NaN is a maximum, first wins
+  const bool vn = v != v, bn = bv != bv;
+  if (vn || bn) return vn && (!bn || i < bi);
+  return v > bv || (v == bv && i < bi);
+}
+
+__global__ void __launch_bounds__(256)
+refine_argmax_kernel(const int2* __restrict__ list, const int* __restrict__ count, int capacity, const float2* __restrict__ coh,
+                     int F, int T, const double2* __restrict__ E, int D, const float* __restrict__ W, int K, int32_t* __restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int n = min(*count, capacity);
+  for (int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n; p += warps) {
+    const int k = list[p].x, t = list[p].y;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // TDOAs lane, lane + 32, lane + 64, lane + 96 (D <= 128)
+    for (int f = 0; f < F; ++f) {
+      const float2 c = __ldg(coh + (int64_t)f * T + t);
+      const double w = (double)__ldg(W + (int64_t)f * K + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = lane + 32 * j;
+        if (d < D) {
+          const double2 e = __ldg(E + (int64_t)f * D + d);
+          acc[j] = fma((double)c.x * e.x - (double)c.y * e.y, w, acc[j]);
+        }
+      }
+    }
+    double bv = acc[0];
+    int bi = lane;
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+      if (lane + 32 * j < D && argmax_better64(acc[j], lane + 32 * j, bv, bi)) { bv = acc[j]; bi = lane + 32 * j; }
+    if (lane >= D) { bv = -INFINITY; bi = 1 << 30; }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (argmax_better64(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) argmax[(int64_t)k * T + t] = bi;
+  }
+}
+
+__global__ void transpose_w_kernel(const float* __restrict__ W, int F, int K, float* __restrict__ WT, int64_t ldwt, float* __restrict__ colsum) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int f = f0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (f < F && k < K) ? W[(int64_t)f * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, f = f0 + threadIdx.x;
+    if (k < K && f < ldwt) WT[(int64_t)k * ldwt + f] = tile[threadIdx.x][i];
+  }
+  (void)colsum;
+}
+
+__global__ void abs_colsum_kernel(const float* __restrict__ W, int F, int K, float* __restrict__ colsum) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int f = 0; f < F; ++f) s += fabsf(W[(int64_t)f * K + k]);
+  colsum[k] = s;
+}
+
+struct ArgmaxWorkspace {
+  float *G, *WT, *colsum;
+  int2* list;
+  int* count;
+  int64_t Fp;
+  int capacity;
+  bool ok;
+};
+
+int list_capacity(int K, int T) { return (int)std::min<int64_t>((int64_t)K * T, std::max<int64_t>(1 << 16, (int64_t)K * T / 8)); }
+
+ArgmaxWorkspace carve_argmax(void* ws, size_t bytes, int F, int T, int D, int K) {
+  WorkspaceCarver c(ws, bytes);
+  ArgmaxWorkspace w;
+  w.Fp = (F + 3) & ~3;
+  w.capacity = list_capacity(K, T);
+  w.G = c.take<float>((size_t)T * D * w.Fp);
+  w.WT = c.take<float>((size_t)K * w.Fp);
+  w.colsum = c.take<float>(K);
+  w.list = c.take<int2>(w.capacity);
+  w.count = c.take<int>(4);
+  w.ok = c.ok();
+  return w;
+}
+
+template <class Epi>
+int launch_argmax_gemm(gccnmf_handle* h, const GemmArgs& args, const Epi& epi, void* stream) {
+  using S = umma::GemmSmem<128>;
+  auto kernel = umma::gemm_tn_3xtf32_kernel<128, false, Epi>;
+  static bool configured = false;
+  if (!configured) {
+    GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  // x = atom tiles (fastest) so that the CTAs sharing one slab of G run together and it is read from HBM once
+  dim3 grid(args.m_tiles, (args.N + 127) / 128, 1);
+  GCCNMF_LAUNCH(h, kernel, grid, umma::kThreads, S::kTotal, stream, args, epi);
+  return 0;
+}
+
+}  // namespace
+
+bool gccnmf_tdoa_argmax_tc_supported(int F, int T, int D, int K) {
+  return (D == 32 || D == 64) && K % 4 == 0 && K >= 32 && F >= 64 && (int64_t)T * D >= 128 && (int64_t)T * D < ((int64_t)1 << 31);
+}
+
+extern "C" {
+
+int gccnmf_tdoa_argmax_refine_capacity(int K, int T) { return (K > 0 && T > 0) ? list_capacity(K, T) : 0; }
+
+size_t gccnmf_tdoa_argmax_workspace_bytes(int F, int T, int D, int K) {
+  if (F <= 0 || T <= 0 || D <= 0 || K <= 0) return 0;
+  if (!gccnmf_tdoa_argmax_tc_supported(F, T, D, K)) return 256;
+  const size_t Fp = (F + 3) & ~3;
+  size_t n = 0;
+  auto add = [&](size_t b) { n = align_up(n, 256) + b; };
+  add((size_t)T * D * Fp * 4); add((size_t)K * Fp * 4); add((size_t)K * 4); add((size_t)list_capacity(K, T) * 8); add(16);
+  return align_up(n, 256);
+}
+
+int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, const double* E, int D, const float* W, int K,
+                       int32_t* argmax, int32_t* overflow_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, F > 0 && T > 0 && D > 0 && K > 0 && coherence && E && W && argmax, "tdoa_argmax: bad arguments");
+  if (h->force_simt_nmf || !gccnmf_tdoa_argmax_tc_supported(F, T, D, K))
+    return gccnmf_tdoa_gccnmf(h, coherence, F, T, E, D, W, K, nullptr, argmax, stream);   // exact float64 SIMT kernel
+  ArgmaxWorkspace w = carve_argmax(workspace, workspace_bytes, F, T, D, K);
+  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "tdoa_argmax workspace too small: need %zu bytes", gccnmf_tdoa_argmax_workspace_bytes(F, T, D, K));
+  GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.count, 0, 16, (cudaStream_t)stream));
+  GCCNMF_LAUNCH(h, build_gcc_matrix_kernel, dim3((int)((w.Fp + 31) / 32), (T + 31) / 32), 256, 0, stream,
+                reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, w.G, w.Fp);
+  GCCNMF_LAUNCH(h, transpose_w_kernel, dim3((K + 31) / 32, (int)((w.Fp + 31) / 32)), dim3(32, 8), 0, stream, W, F, K, w.WT, w.Fp, w.colsum);
+  GCCNMF_LAUNCH(h, abs_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
+  const int N = T * D;
+  GemmArgs args{w.WT, w.G, K, N, F, w.Fp, w.Fp, (F + umma::kBK - 1) / umma::kBK, (K + umma::kBM - 1) / umma::kBM, nullptr, 1};
+  EpiArgmaxTDOA epi{argmax, w.colsum, w.list, w.count, w.capacity, K, T, D, N};
+  if (int st = launch_argmax_gemm(h, args, epi, stream)) return st;
+  GCCNMF_LAUNCH(h, refine_argmax_kernel, h->sm_count * 4, 256, 0, stream, w.list, w.count, w.capacity,
+                reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, W, K, argmax);
+  // more near-ties than the list holds (never seen: the list holds 1/8 of all decisions): the caller must fall back
+  if (overflow_flag) GCCNMF_CHECK_CUDA(h, cudaMemcpyAsync(overflow_flag, w.count, sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return GCCNMF_OK;
+}
+
+}  // extern "C"

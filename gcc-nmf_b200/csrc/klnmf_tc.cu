@@ -35,9 +35,10 @@ constexpr int kMaxSplits = 8;
 
 // ------------------------------------------------------------------------------------------------ epilogues
 struct EpiStoreRowMajor {  // D[z][m][n] = acc   (test entry, G4 partials)
+  UMMA_EPILOGUE_STATELESS
   float* __restrict__ D; int64_t ldd; int M, N; int64_t slab;
   __device__ void elem(int m, int n, float acc, int z) const { D[(int64_t)z * slab + (int64_t)m * ldd + n] = acc; }
-  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int z, int, float* scratch) const {
+  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int z, int, float* scratch, State&) const {
     warp_transpose_32x32(v, scratch, lane);             // v[i] = D[m_base + i][n0 + lane]
     const int n = n0 + lane;
     if (n >= N) return;
@@ -49,9 +50,10 @@ struct EpiStoreRowMajor {  // D[z][m][n] = acc   (test entry, G4 partials)
 };
 
 struct EpiRatioT {   // RT[n][m] = VT[n][m] / acc     (G1; lanes run along m: coalesced as is)
+  UMMA_EPILOGUE_STATELESS
   const float* __restrict__ VT; float* __restrict__ RT; int64_t ld; int M, N;
   __device__ void elem(int m, int n, float acc, int) const { RT[(int64_t)n * ld + m] = VT[(int64_t)n * ld + m] / acc; }
-  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int, float*) const {
+  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int, float*, State&) const {
     const int m = m_base + lane;
     if (m >= M) return;
     float vt[32];
@@ -64,9 +66,10 @@ struct EpiRatioT {   // RT[n][m] = VT[n][m] / acc     (G1; lanes run along m: co
 };
 
 struct EpiRatioRow {  // R[m][n] = V[m][n] / acc       (G3; transposed through shared memory for coalesced rows)
+  UMMA_EPILOGUE_STATELESS
   const float* __restrict__ V; float* __restrict__ R; int64_t ldv, ldr; int M, N;
   __device__ void elem(int m, int n, float acc, int) const { R[(int64_t)m * ldr + n] = V[(int64_t)m * ldv + n] / acc; }
-  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int, float* scratch) const {
+  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int, float* scratch, State&) const {
     warp_transpose_32x32(v, scratch, lane);
     const int n = n0 + lane;
     if (n >= N) return;
@@ -83,6 +86,7 @@ struct EpiRatioRow {  // R[m][n] = V[m][n] / acc       (G3; transposed through s
 // The old value is read from H^T (coalesced along m), H^T is rewritten in place, H is written through the
 // shared-memory transpose, and the per-row partial sums of the new H go to rowsum_part[slot][m].
 struct EpiUpdateHBoth {
+  UMMA_EPILOGUE_STATELESS
   float* __restrict__ H; float* __restrict__ HT; const float* __restrict__ colsumW; const float* __restrict__ pending;
   float* __restrict__ rowsum_part; float alpha, eps; int64_t ldh, ldht; int M, N; int colsum_slots;
   __device__ float colsum(int m) const {   // colsum(W): sum of the W update's per-row-block partials
@@ -101,7 +105,7 @@ struct EpiUpdateHBoth {
     HT[(int64_t)n * ldht + m] = hv;
     H[(int64_t)m * ldh + n] = hv;
   }
-  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int slot, float* scratch) const {
+  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int slot, float* scratch, State&) const {
     const int m = m_base + lane;
     float rsum = 0.f;
     if (m < M) {
@@ -421,7 +425,7 @@ int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, co
   (void)V;
   const float* pending = pending_norms ? w.norms : nullptr;
   {  // G1: RT = VT / (W.(n*H))
-    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, pending};
+    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, pending, 0};
     EpiRatioT e{w.VT, w.RT, w.Fp, F, T2};
     const int st = pending ? tc_gemm<true>(h, a, 1, e, stream) : tc_gemm<false>(h, a, 1, e, stream);
     if (st) return st;
@@ -429,7 +433,7 @@ int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, co
   if (colsum_state == 0) GCCNMF_LAUNCH(h, tc_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
   GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.rowsum_part, 0, (size_t)w.rowsum_slots * K * sizeof(float), (cudaStream_t)stream));
   {  // G2: H, HT = (n*H) * (WT.RT^T) / denom
-    GemmArgs a{w.WT, w.RT, K, T2, F, w.Fp, w.Fp, 0, 0, nullptr};
+    GemmArgs a{w.WT, w.RT, K, T2, F, w.Fp, w.Fp, 0, 0, nullptr, 0};
     EpiUpdateHBoth e{w.Hp, w.HT, w.colsum, pending, w.rowsum_part, alpha, eps, w.T2p, (int64_t)K, K, T2, colsum_state == 2 ? w.row_blocks : 1};
     (void)H;
     const int bn = tile_width(h, m_tiles_of(K), T2, 1);
@@ -443,7 +447,7 @@ int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, c
                               void* workspace, size_t workspace_bytes, bool have_rowsum, void* stream) {
   TC_CARVE_OR_FAIL(w);
   {  // G3: R = V / (W.H)
-    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, nullptr};
+    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, nullptr, 0};
     EpiRatioRow e{V, w.R, (int64_t)T2, w.T2p, F, T2};
     if (int st = tc_gemm<false>(h, a, 1, e, stream)) return st;
   }
@@ -453,7 +457,7 @@ int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, c
   }
   {  // G4: partial[z] = R.H^T
     (void)H;
-    GemmArgs a{w.R, w.Hp, F, K, T2, w.T2p, w.T2p, 0, 0, nullptr};
+    GemmArgs a{w.R, w.Hp, F, K, T2, w.T2p, w.T2p, 0, 0, nullptr, 0};
     EpiStoreRowMajor e{w.partial, (int64_t)K, F, K, (int64_t)F * K};
     if (int st = tc_gemm<false>(h, a, w.splits, e, stream)) return st;
   }
@@ -504,7 +508,7 @@ int gccnmf_gemm_tn_3xtf32(gccnmf_handle* h, const float* A, int64_t lda, const f
   GCCNMF_REQUIRE(h, (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0),
                  "gemm_tn_3xtf32: operands must be 16-byte aligned");
   if (tile_n != 128 && tile_n != 256) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "gemm_tn_3xtf32: tile_n must be 128 or 256");
-  GemmArgs args{A, B, M, N, Kc, lda, ldb, 0, 0, nullptr};
+  GemmArgs args{A, B, M, N, Kc, lda, ldb, 0, 0, nullptr, 0};
   EpiStoreRowMajor epi{D, ldd, M, N, 0};
   return tc_gemm<false>(h, args, 1, epi, stream, tile_n);
 }

@@ -130,6 +130,7 @@ struct GemmArgs {
   int kblocks_per_split;  // k-blocks of 32 handled by one blockIdx.z
   int m_tiles;            // 128-row tiles on the tensor cores; blockIdx.y == m_tiles -> SIMT tail rows [128 m_tiles, M)
   const float* b_scale;   // optional per-k scale of B (length >= round_up(Kc, 4)): B[n][k] * b_scale[k], or NULL
+  int m_fastest;          // 0: grid (n tiles, m tiles + tail, splits); 1: grid (m tiles, n tiles, splits) -- CTAs sharing a B slab are co-scheduled
 };
 
 constexpr int kLoaderWarps = 8;
@@ -188,6 +189,11 @@ struct TileLoader {
   }
 };
 
+// Boilerplate for epilogues without cross-chunk state (kept as members so the functors stay aggregates).
+#define UMMA_EPILOGUE_STATELESS \
+  struct State {};            \
+  __device__ void init(State&) const {}
+
 // 32 x 32 register transpose through a per-warp shared scratch (33-float rows): in: v[j] = D[row lane][col j];
 // out: v[i] = D[row i][col lane].
 __device__ __forceinline__ void warp_transpose_32x32(float (&v)[32], float* scratch, int lane) {
@@ -200,10 +206,12 @@ __device__ __forceinline__ void warp_transpose_32x32(float (&v)[32], float* scra
 }
 
 // Epilogue concept (see klnmf_tc.cu for the functors):
-//   __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int z, int slot, float* scratch) const;
-//       called by each epilogue warp per 32-column chunk; the thread holds row m_base + lane, columns
-//       n0 .. n0 + 31; slot = which column part of the tile this warp owns (for per-CTA partial outputs);
-//       scratch = 32 x 33 floats of shared memory private to the warp (for warp_transpose_32x32).
+//   struct State;  __device__ void init(State&) const;
+//   __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int z, int slot, float* scratch, State&) const;
+//       called by each epilogue warp per 32-column chunk, in increasing n0 over the warp's BN/2 columns; the
+//       thread holds row m_base + lane, columns n0 .. n0 + 31; slot = which column half of which tile this
+//       warp owns (for per-CTA partial outputs); scratch = 32 x 33 floats of shared memory private to the
+//       warp (for warp_transpose_32x32); State = per-thread registers carried across the chunks.
 //   __device__ void elem(int m, int n, float acc, int z) const;      // SIMT tail rows
 template <int BN, bool SCALE_B, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -213,14 +221,16 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * BN;
+  const int tile_m = args.m_fastest ? blockIdx.x : blockIdx.y;
+  const int tile_n = args.m_fastest ? blockIdx.y : blockIdx.x;
+  const int n0 = tile_n * BN;
   const int kc4 = (args.Kc + 3) & ~3;
   const int total_kblocks = (args.Kc + kBK - 1) / kBK;
   const int kb_begin = blockIdx.z * args.kblocks_per_split;
   const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
   const int num_kb = max(0, kb_end - kb_begin);
 
-  if ((int)blockIdx.y >= args.m_tiles) {
+  if (tile_m >= args.m_tiles) {
     // ---------------------------------------------------------------- SIMT tail rows (runs on SMs the tile grid leaves idle)
     const int k_begin = kb_begin * kBK, k_end = min(kc4, kb_end * kBK);
     for (int m = args.m_tiles * kBM; m < args.M; ++m) {
@@ -249,7 +259,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
   uint64_t* empty = bars + S::kStages;      // [kStages]
   uint64_t* accum_full = bars + 2 * S::kStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
-  const int m0 = blockIdx.y * kBM;
+  const int m0 = tile_m * kBM;
 
   if (tid == 0) {
     for (int s = 0; s < S::kStages; ++s) {
@@ -315,6 +325,8 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
     const int slot = warp >> 2;
     const int col0 = slot * kColsPerWarp;
     float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // aliases stage 0 (idle now)
+    typename Epilogue::State epi_state;
+    epi.init(epi_state);
 #pragma unroll 1
     for (int c = 0; c < kColsPerWarp; c += 32) {
       float v[32];
@@ -324,7 +336,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      epi.tile(m0 + quarter * 32, lane, n0 + col0 + c, v, (int)blockIdx.z, (int)blockIdx.x * 2 + slot, scratch);
+      epi.tile(m0 + quarter * 32, lane, n0 + col0 + c, v, (int)blockIdx.z, tile_n * 2 + slot, scratch, epi_state);
     }
     tc_fence_before_sync();
   } else {

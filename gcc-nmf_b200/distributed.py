@@ -165,30 +165,35 @@ class ShardedGCCNMFPipeline(object):
         h, torch, comm = self.h, self.torch, self.comm
         self.stage_events = [] if collect_stage_times else None
         self._mark('start')
-        X, V = h.stft(samples, self.window, self.N, self.hop, conjugate=True, want_V=True)
+        key = id(self)
+        X, V = h.stft(samples, self.window, self.N, self.hop, conjugate=True, want_V=True, out_key=key)
         Ts = X.shape[2]
         assert Ts == self.t1 - self.t0
         self._mark('stft')
-        coh, ang, mean = h.phat_angspec(X, self.E)
+        coh, ang, mean = h.phat_angspec(X, self.E, out_key=key)
         total = mean * float(Ts)                      # back to the local sum over frames
         comm.all_reduce_sum(total)
         mean_host = (total / float(self.total_frames)).cpu().numpy()
         self._mark('angular')
-        W, H = self.W0.clone(), self.H0s.clone()
+        W, H = h.buffer((key, 'W'), self.W0.shape, self.W0.dtype), h.buffer((key, 'H'), self.H0s.shape, self.H0s.dtype)
+        W.copy_(self.W0)
+        H.copy_(self.H0s)
         self._agree_on_nmf_path(V.shape[1])
         klnmf_sharded(h, comm, V, W, H, self.I, self.alpha, self.eps, self.numer)
         self._mark('nmf')
-        _, argmax = h.tdoa_gccnmf(coh, self.E, W, want_values=False, want_argmax=True)
+        argmax, refined = h.tdoa_argmax(coh, self.E, W, out_key=key)
         self._mark('gccnmf')
+        if int(refined.item()) > h.lib.gccnmf_tdoa_argmax_refine_capacity(self.K, Ts):
+            _, argmax = h.tdoa_gccnmf(coh, self.E, W, want_values=False, want_argmax=True)   # exact float64 kernel
         target = int(fn.estimateTargetTDOAIndexesFromAngularSpectrum(mean_host, self.micSep, self.D, 1)[0])
         window = (self.hypothesisTDOAs[-1] - self.hypothesisTDOAs[0]) * self.windowPercent
         lut = fn.getTargetTDOALookup(self.hypothesisTDOAs, target, window)
-        mask = h.argmax_mask(argmax, h.to_device(lut.astype(np.uint8)))
+        mask = h.argmax_mask(argmax, h.to_device(lut.astype(np.uint8)), out_key=key)
         self._mark('mask')
-        est = h.masked_recon_phase(mask[None], X, W, H)
+        est = h.masked_recon_phase(mask[None], X, W, H, out_key=key)
         self._mark('recon')
         y = h.istft_ola(est.reshape(2, self.F, Ts), self.window, self.N, self.hop,
-                        gain=np.float32(self.hop / float(self.N) * 2), center=False, conjugate=True)
+                        gain=np.float32(self.hop / float(self.N) * 2), center=False, conjugate=True, out_key=key)
         y = overlap_add_seams(comm, y, self.hop * Ts, self.N - self.hop)
         # global centre trim (librosaSTFT.py:283-284): N/2 samples off each end of the whole recording
         if comm.rank == 0:

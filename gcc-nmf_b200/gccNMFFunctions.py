@@ -202,9 +202,11 @@ def getGCCNMFArgMaxTDOA(spectralCoherenceV, frequenciesInHz, microphoneSeparatio
     cells 27+29, :444-467) -> (K, T) int32, without materialising the (K, D, T) float64 tensor."""
     E = getExpJOmegaTau(frequenciesInHz, getTDOAsInSeconds(microphoneSeparationInMetres, numTDOAs))
     h = default_handle()
-    _, argmax = h.tdoa_gccnmf(h.to_device(np.ascontiguousarray(spectralCoherenceV, dtype=np.complex64)),
-                              h.to_device(np.ascontiguousarray(E)), h.to_device(np.ascontiguousarray(W, dtype=np.float32)),
-                              want_values=False, want_argmax=True)
+    coh = h.to_device(np.ascontiguousarray(spectralCoherenceV, dtype=np.complex64))
+    Ed, Wd = h.to_device(np.ascontiguousarray(E)), h.to_device(np.ascontiguousarray(W, dtype=np.float32))
+    argmax, refined = h.tdoa_argmax(coh, Ed, Wd)
+    if int(refined.item()) > h.lib.gccnmf_tdoa_argmax_refine_capacity(Wd.shape[1], coh.shape[1]):
+        _, argmax = h.tdoa_gccnmf(coh, Ed, Wd, want_values=False, want_argmax=True)
     return argmax.cpu().numpy()
 
 

@@ -154,6 +154,21 @@ GCCNMF_API int gccnmf_phat_angspec(gccnmf_handle* h, const float* X, int F, int 
 GCCNMF_API int gccnmf_tdoa_gccnmf(gccnmf_handle* h, const float* coherence, int F, int T, const double* E,
                        int D, const float* W, int K, float* values, int32_t* argmax, void* stream);
 
+/*
+ * a10 / a11 fast path: argmax over ALL hypothesis TDOAs without materialising (K, D, T) float64.
+ * For D in {32, 64} and K % 4 == 0 the contraction runs as a 3xTF32 tcgen05 GEMM whose epilogue keeps the
+ * best / second-best value per (atom, frame); every decision whose margin is inside the GEMM's worst-case
+ * error is recomputed exactly in float64, so the result equals gccnmf_tdoa_gccnmf's argmax (the
+ * reference's numpy.argmax on float64) on every input.  Other shapes run the float64 kernel directly.
+ * *overflow_flag (device int32, may be NULL) receives the number of refined decisions; if it exceeds
+ * gccnmf_tdoa_argmax_refine_capacity(K, T) the caller must recompute with gccnmf_tdoa_gccnmf.
+ */
+GCCNMF_API size_t gccnmf_tdoa_argmax_workspace_bytes(int F, int T, int D, int K);
+GCCNMF_API int gccnmf_tdoa_argmax_refine_capacity(int K, int T);
+GCCNMF_API int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, const double* E, int D,
+                       const float* W, int K, int32_t* argmax, int32_t* overflow_flag, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* ---- a7: coefficient masks  (gccNMFFunctions.py:137-143; offlineSpeechEnhancement.ipynb:466-472) */
 /* nanargmax over S -> one-hot (S, K, T) f32.  *all_nan_flag (device int32, may be NULL) is set to 1
  * when some (k, t) is NaN for every target (numpy.nanargmax raises ValueError there). */

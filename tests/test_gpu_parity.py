@@ -301,7 +301,11 @@ def test_full_size_properties_config2(h, fn):
     f = fn.getFrequenciesInHz(16000, 513)
     E = fn.getExpJOmegaTau(f, fn.getTDOAsInSeconds(0.1, D))
     coh, ang, mean = h.phat_angspec(X, h.to_device(np.ascontiguousarray(E)))
-    _, argmax = h.tdoa_gccnmf(coh, h.to_device(np.ascontiguousarray(E)), W)
+    Ed = h.to_device(np.ascontiguousarray(E))
+    argmax, refined = h.tdoa_argmax(coh, Ed, W)              # tensor cores + float64 refinement of near-ties
+    _, argmax64 = h.tdoa_gccnmf(coh, Ed, W)                  # float64 kernel: all 1.9 M decisions must agree
+    assert torch.equal(argmax, argmax64)
+    print('config 2: %d of %d argmax decisions refined in float64' % (int(refined.item()), argmax.numel()))
     cohh = coh.cpu().numpy()
     ref = orc.getGCCNMFAllTDOAs(cohh[:, 500:532], E, W.cpu().numpy())
     assert np.array_equal(argmax.cpu().numpy()[:, 500:532], np.argmax(ref, axis=1))

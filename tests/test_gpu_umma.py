@@ -82,3 +82,29 @@ def test_klnmf_tensor_core_path_matches_oracle(h):
     for _ in range(5):
         Href *= np.dot(Wo.T, V / np.dot(Wo, Href)) / denom
     assert rel(Hi.cpu().numpy(), Href) < 2e-5
+
+
+@pytest.mark.parametrize('D', [32, 64])
+def test_tdoa_argmax_tensor_core_equals_float64_kernel(h, D):
+    """Every argmax decision of the tensor-core + refinement path equals the float64 kernel's (and the oracle's
+    on a slice), including planted exact ties and a NaN bin."""
+    import torch
+    from oracle import gccnmf_oracle as orc
+    import gcc_nmf_b200.gccNMFFunctions as fn
+    rng = np.random.default_rng(D)
+    F, T, K = 257, 300, 128
+    coh = np.exp(1j * rng.uniform(-np.pi, np.pi, (F, T))).astype(np.complex64)
+    coh[:, 5] = coh[:, 4]                       # two identical frames
+    coh[7, 9] = np.nan                          # one NaN bin (0/0 in the PHAT normalisation)
+    W = (rng.random((F, K)) ** 4).astype(np.float32)
+    W[:, 3] = W[:, 2]                           # two identical atoms
+    E = fn.getExpJOmegaTau(fn.getFrequenciesInHz(16000, F), fn.getTDOAsInSeconds(0.1, D))
+    cd, Ed, Wd = h.to_device(coh), h.to_device(np.ascontiguousarray(E)), h.to_device(W)
+    fast, refined = h.tdoa_argmax(cd, Ed, Wd)
+    _, exact = h.tdoa_gccnmf(cd, Ed, Wd, want_values=False, want_argmax=True)
+    assert int(refined.item()) <= h.lib.gccnmf_tdoa_argmax_refine_capacity(K, T)
+    assert torch.equal(fast, exact)
+    with np.errstate(all='ignore'):
+        ref = orc.getGCCNMFAllTDOAs(coh[:, :16], E, W)
+    assert np.array_equal(fast.cpu().numpy()[:, :16], np.argmax(ref, axis=1))
+    print('D=%d: %d of %d decisions refined in float64' % (D, int(refined.item()), K * T))
