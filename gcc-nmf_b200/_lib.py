@@ -62,6 +62,7 @@ SIGNATURES = {
     'gccnmf_argmax_mask': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, _S]),
     'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
     'gccnmf_gemm_tn_3xtf32': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _S]),
+    'gccnmf_gemm_tn_3xtf32_timed': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _S]),
 }
 
 _lib = None

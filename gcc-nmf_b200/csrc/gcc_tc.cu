@@ -227,7 +227,7 @@ int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, c
   GCCNMF_LAUNCH(h, transpose_w_kernel, dim3((K + 31) / 32, (int)((w.Fp + 31) / 32)), dim3(32, 8), 0, stream, W, F, K, w.WT, w.Fp, w.colsum);
   GCCNMF_LAUNCH(h, abs_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
   const int N = T * D;
-  GemmArgs args{w.WT, w.G, K, N, F, w.Fp, w.Fp, (F + umma::kBK - 1) / umma::kBK, (K + umma::kBM - 1) / umma::kBM, nullptr, 1};
+  GemmArgs args{w.WT, w.G, K, N, F, w.Fp, w.Fp, (F + umma::kBK - 1) / umma::kBK, (K + umma::kBM - 1) / umma::kBM, nullptr, nullptr, 1};
   EpiArgmaxTDOA epi{argmax, w.colsum, w.list, w.count, w.capacity, K, T, D, N};
   if (int st = launch_argmax_gemm(h, args, epi, stream)) return st;
   GCCNMF_LAUNCH(h, refine_argmax_kernel, h->sm_count * 4, 256, 0, stream, w.list, w.count, w.capacity,

@@ -425,7 +425,7 @@ int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, co
   (void)V;
   const float* pending = pending_norms ? w.norms : nullptr;
   {  // G1: RT = VT / (W.(n*H))
-    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, pending, 0};
+    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, pending, nullptr, 0};
     EpiRatioT e{w.VT, w.RT, w.Fp, F, T2};
     const int st = pending ? tc_gemm<true>(h, a, 1, e, stream) : tc_gemm<false>(h, a, 1, e, stream);
     if (st) return st;
@@ -433,7 +433,7 @@ int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, co
   if (colsum_state == 0) GCCNMF_LAUNCH(h, tc_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
   GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.rowsum_part, 0, (size_t)w.rowsum_slots * K * sizeof(float), (cudaStream_t)stream));
   {  // G2: H, HT = (n*H) * (WT.RT^T) / denom
-    GemmArgs a{w.WT, w.RT, K, T2, F, w.Fp, w.Fp, 0, 0, nullptr, 0};
+    GemmArgs a{w.WT, w.RT, K, T2, F, w.Fp, w.Fp, 0, 0, nullptr, nullptr, 0};
     EpiUpdateHBoth e{w.Hp, w.HT, w.colsum, pending, w.rowsum_part, alpha, eps, w.T2p, (int64_t)K, K, T2, colsum_state == 2 ? w.row_blocks : 1};
     (void)H;
     const int bn = tile_width(h, m_tiles_of(K), T2, 1);
@@ -447,7 +447,7 @@ int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, c
                               void* workspace, size_t workspace_bytes, bool have_rowsum, void* stream) {
   TC_CARVE_OR_FAIL(w);
   {  // G3: R = V / (W.H)
-    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, nullptr, 0};
+    GemmArgs a{W, w.HT, F, T2, K, (int64_t)K, (int64_t)K, 0, 0, nullptr, nullptr, 0};
     EpiRatioRow e{V, w.R, (int64_t)T2, w.T2p, F, T2};
     if (int st = tc_gemm<false>(h, a, 1, e, stream)) return st;
   }
@@ -457,7 +457,7 @@ int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, c
   }
   {  // G4: partial[z] = R.H^T
     (void)H;
-    GemmArgs a{w.R, w.Hp, F, K, T2, w.T2p, w.T2p, 0, 0, nullptr, 0};
+    GemmArgs a{w.R, w.Hp, F, K, T2, w.T2p, w.T2p, 0, 0, nullptr, nullptr, 0};
     EpiStoreRowMajor e{w.partial, (int64_t)K, F, K, (int64_t)F * K};
     if (int st = tc_gemm<false>(h, a, w.splits, e, stream)) return st;
   }
@@ -499,8 +499,18 @@ extern "C" {
 
 // D (M, N) row-major (ldd) = A (M, Kc; lda) . B (N, Kc; ldb)^T with 3xTF32 error compensation.
 // lda, ldb multiples of 4 with zero padding up to round_up(Kc, 4); tile_n in {128, 256}.
+int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd,
+                                int M, int N, int Kc, int tile_n, unsigned long long* timing, void* stream);
+
 int gccnmf_gemm_tn_3xtf32(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb, float* D,
                           int64_t ldd, int M, int N, int Kc, int tile_n, void* stream) {
+  return gccnmf_gemm_tn_3xtf32_timed(h, A, lda, B, ldb, D, ldd, M, N, Kc, tile_n, nullptr, stream);
+}
+
+// Diagnostics: same product; `timing` (device, 6 x number of CTAs uint64, or NULL) receives per-CTA clock64 stamps:
+// [0] kernel start, [1] first stage full, [2] last MMA issued, [3] loaders finished, [4] accumulator complete, [5] epilogue end.
+int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd,
+                                int M, int N, int Kc, int tile_n, unsigned long long* timing, void* stream) {
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   GCCNMF_REQUIRE(h, A && B && D && M > 0 && N > 0 && Kc > 0, "gemm_tn_3xtf32: bad arguments");
   GCCNMF_REQUIRE(h, lda % 4 == 0 && ldb % 4 == 0 && lda >= ((Kc + 3) & ~3) && ldb >= ((Kc + 3) & ~3),
@@ -508,7 +518,7 @@ int gccnmf_gemm_tn_3xtf32(gccnmf_handle* h, const float* A, int64_t lda, const f
   GCCNMF_REQUIRE(h, (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(B) % 16 == 0),
                  "gemm_tn_3xtf32: operands must be 16-byte aligned");
   if (tile_n != 128 && tile_n != 256) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "gemm_tn_3xtf32: tile_n must be 128 or 256");
-  GemmArgs args{A, B, M, N, Kc, lda, ldb, 0, 0, nullptr, 0};
+  GemmArgs args{A, B, M, N, Kc, lda, ldb, 0, 0, nullptr, timing, 0};
   EpiStoreRowMajor epi{D, ldd, M, N, 0};
   return tc_gemm<false>(h, args, 1, epi, stream, tile_n);
 }

@@ -130,6 +130,7 @@ struct GemmArgs {
   int kblocks_per_split;  // k-blocks of 32 handled by one blockIdx.z
   int m_tiles;            // 128-row tiles on the tensor cores; blockIdx.y == m_tiles -> SIMT tail rows [128 m_tiles, M)
   const float* b_scale;   // optional per-k scale of B (length >= round_up(Kc, 4)): B[n][k] * b_scale[k], or NULL
+  unsigned long long* timing;   // optional (diagnostics): 6 clock64 stamps per tensor-core CTA, or NULL
   int m_fastest;          // 0: grid (n tiles, m tiles + tail, splits); 1: grid (m tiles, n tiles, splits) -- CTAs sharing a B slab are co-scheduled
 };
 
@@ -145,35 +146,42 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
 };
 
-// One thread's share of a [ROWS x 32] float tile: chunk column c = tid % 8 (4 floats), rows tid / 8 + 32 i.
+// One thread's share of a [ROWS x 32] float tile loaded by NT threads: chunk column c = tid % 8 (4 floats),
+// rows tid / 8 + (NT / 8) i.
 // Rows past the end of the matrix are clamped to its last row (their products land in accumulator rows /
 // columns the epilogue never stores), so the only predicate left is the k tail, uniform per thread.
-template <int ROWS>
+template <int ROWS, int NT>
 struct TileLoader {
-  static constexpr int kChunks = ROWS * 8 / kLoaderThreads;
-  const float* ptr[kChunks];   // chunk i of this thread at the current k-block; advanced by 32 floats per fetch
+  static constexpr int kChunks = ROWS * 8 / NT;
+  static constexpr int kRowStep = NT / 8;                 // rows between consecutive chunks of one thread
+  static constexpr int kSmemStep = kRowStep * 128;         // bytes (kRowStep is a multiple of 8 rows = 1024 B groups)
+  const float* ptr;            // chunk 0 of this thread at the current k-block; advanced by 32 floats per fetch
+  int64_t stride;              // floats between consecutive chunks (kRowStep rows)
+  int imax;                    // last chunk index whose row is inside the matrix (chunks past it re-read that row)
   int kcol;                    // c * 4
-  uint32_t smem_off;           // swizzled byte offset of chunk 0 inside the tile; chunk i is + 4096 i
+  uint32_t smem_off;           // swizzled byte offset of chunk 0 inside the tile; chunk i is + kSmemStep i
 
   __device__ __forceinline__ void init(const float* src, int64_t ld, int row0, int rows_valid, int k0, int tid) {
     const int r = tid >> 3, c = tid & 7;
     kcol = c * 4;
-#pragma unroll
-    for (int i = 0; i < kChunks; ++i) ptr[i] = src + (int64_t)min(row0 + r + 32 * i, rows_valid - 1) * ld + k0 + kcol;
+    const int first = min(row0 + r, rows_valid - 1);
+    ptr = src + (int64_t)first * ld + k0 + kcol;
+    stride = (int64_t)kRowStep * ld;
+    imax = max(0, (rows_valid - 1 - first) / kRowStep);
     smem_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
   }
-  // loads the k-block starting at column k0 (the pointers already point there) and advances to the next one
+  // loads the k-block starting at column k0 (the pointer already points there) and advances to the next one
   __device__ __forceinline__ void fetch(float4 (&regs)[kChunks], int k0, int kc4) {
     if (k0 + kcol < kc4) {
 #pragma unroll
-      for (int i = 0; i < kChunks; ++i) regs[i] = __ldg(reinterpret_cast<const float4*>(ptr[i]));
+      for (int i = 0; i < kChunks; ++i) regs[i] = __ldg(reinterpret_cast<const float4*>(ptr + (int64_t)min(i, imax) * stride));
     } else {
 #pragma unroll
       for (int i = 0; i < kChunks; ++i) regs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll
-    for (int i = 0; i < kChunks; ++i) ptr[i] += kBK;
+    ptr += kBK;
   }
+  __device__ __forceinline__ void skip(int kblocks) { ptr += kblocks * kBK; }
   // hi = tf32(x) (round to nearest), lo = x - hi exactly (|lo| <= 2^-11 |x|; the tensor core drops its bits
   // below tf32 resolution: <= 2^-21 |x|, sign-symmetric)
   __device__ __forceinline__ void stash(const float4 (&regs)[kChunks], unsigned char* hi, unsigned char* lo) const {
@@ -183,8 +191,8 @@ struct TileLoader {
       float4 h, l;
       h.x = tf32_round(x.x); h.y = tf32_round(x.y); h.z = tf32_round(x.z); h.w = tf32_round(x.w);
       l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-      *reinterpret_cast<float4*>(hi + smem_off + i * 4096) = h;
-      *reinterpret_cast<float4*>(lo + smem_off + i * 4096) = l;
+      *reinterpret_cast<float4*>(hi + smem_off + i * kSmemStep) = h;
+      *reinterpret_cast<float4*>(lo + smem_off + i * kSmemStep) = l;
     }
   }
 };
@@ -261,9 +269,11 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
   const int m0 = tile_m * kBM;
 
+  const int cta_linear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (args.timing && tid == 0) args.timing[cta_linear * 6 + 0] = clock64();
   if (tid == 0) {
     for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(smem_u32(&full[s]), kLoaderThreads);
+      mbar_init(smem_u32(&full[s]), kLoaderThreads / ((BN <= 128) ? 2 : 1));   // one loader group fills a stage
       mbar_init(smem_u32(&empty[s]), 1);
     }
     mbar_init(smem_u32(accum_full), 1);
@@ -281,44 +291,54 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
 
   if (warp < kLoaderWarps) {
     // ------------------------------------------------------------------ loaders
-    TileLoader<kBM> la;
-    TileLoader<BN> lb;
-    la.init(args.A, args.lda, m0, min(args.M, args.m_tiles * kBM), kb_begin * kBK, tid);
-    lb.init(args.B, args.ldb, n0, args.N, kb_begin * kBK, tid);
-    // two register sets: the global loads of k-block i+2 are in flight while k-block i+1 is split and stored
-    float4 a0[TileLoader<kBM>::kChunks], b0[TileLoader<BN>::kChunks], a1[TileLoader<kBM>::kChunks], b1[TileLoader<BN>::kChunks];
-    float4 s0, s1;
-    auto fetch = [&](float4 (&ar)[TileLoader<kBM>::kChunks], float4 (&br)[TileLoader<BN>::kChunks], float4& sc, int kb) {
+    // The 8 loader warps form kGroups groups of 128 threads; group g produces k-blocks g, g + kGroups, ...  Each
+    // thread keeps ONE register set: the loads of its next k-block are issued right after it has stored the
+    // current one, and while it waits for them the other group's warps (same SM sub-partitions) work -- the
+    // overlap comes from warp scheduling.  (A two-register-set software pipeline inside one thread does not
+    // overlap: ptxas tracks all the LDGs of both sets on one scoreboard slot, so waiting for the older set waits
+    // for the newer one as well -- seen in the SASS control codes, and as 38 % long-scoreboard stalls in ncu.)
+    // BN = 256: one group (a k-block there is 1536 MMA cycles, so a prefetch distance of one k-block is enough and the
+    // 12 chunks per thread fit the register budget; two groups would need 24).
+    constexpr int kGroups = (BN <= 128) ? 2 : 1;
+    constexpr int kGroupThreads = kLoaderThreads / kGroups;
+    const int group = tid / kGroupThreads, gtid = tid % kGroupThreads;
+    TileLoader<kBM, kGroupThreads> la;
+    TileLoader<BN, kGroupThreads> lb;
+    const int kb_first = kb_begin + group;
+    la.init(args.A, args.lda, m0, min(args.M, args.m_tiles * kBM), kb_first * kBK, gtid);
+    lb.init(args.B, args.ldb, n0, args.N, kb_first * kBK, gtid);
+    float4 ar[TileLoader<kBM, kGroupThreads>::kChunks], br[TileLoader<BN, kGroupThreads>::kChunks];
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    auto fetch = [&](int kb) {
       la.fetch(ar, kb * kBK, kc4);
       lb.fetch(br, kb * kBK, kc4);
       if (SCALE_B) sc = (kb * kBK + lb.kcol < kc4) ? __ldg(reinterpret_cast<const float4*>(args.b_scale + kb * kBK + lb.kcol))
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      la.skip(kGroups - 1);            // the pointers advance by one k-block per fetch; jump over the other groups' k-blocks
+      lb.skip(kGroups - 1);
     };
-    auto produce = [&](float4 (&ar)[TileLoader<kBM>::kChunks], float4 (&br)[TileLoader<BN>::kChunks], float4& sc, int i) {
+    if (group < num_kb) fetch(kb_first);
+    for (int i = group; i < num_kb; i += kGroups) {
       const int s = i % S::kStages;
       const uint32_t use = i / S::kStages;
       if (SCALE_B) {
 #pragma unroll
-        for (int j = 0; j < TileLoader<BN>::kChunks; ++j) { br[j].x *= sc.x; br[j].y *= sc.y; br[j].z *= sc.z; br[j].w *= sc.w; }
+        for (int j = 0; j < TileLoader<BN, kGroupThreads>::kChunks; ++j) { br[j].x *= sc.x; br[j].y *= sc.y; br[j].z *= sc.z; br[j].w *= sc.w; }
       }
       if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // MMAs that read this stage have retired
       unsigned char* st = stage_ptr(s);
       la.stash(ar, st, st + kATile);
       lb.stash(br, st + 2 * kATile, st + 2 * kATile + kBTile);
-      if (i + 2 < num_kb) fetch(ar, br, sc, kb_begin + i + 2);
+      if (i + kGroups < num_kb) fetch(kb_begin + i + kGroups);
       fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&full[s]));
-    };
-    if (num_kb > 0) fetch(a0, b0, s0, kb_begin);
-    if (num_kb > 1) fetch(a1, b1, s1, kb_begin + 1);
-    for (int i = 0; i < num_kb; i += 2) {
-      produce(a0, b0, s0, i);
-      if (i + 1 < num_kb) produce(a1, b1, s1, i + 1);
     }
     // ------------------------------------------------------------------ epilogue
     if (num_kb > 0) {
+      if (args.timing && tid == 0) args.timing[cta_linear * 6 + 3] = clock64();   // loaders done producing
       mbar_wait(smem_u32(accum_full), 0);   // every MMA has retired: accumulator complete, pipeline stages free
       tc_fence_after_sync();
+      if (args.timing && tid == 0) args.timing[cta_linear * 6 + 4] = clock64();
     }
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
     constexpr int kColsPerWarp = BN / 2;                  // warps w and w + 4 split the columns of a lane quarter
@@ -338,6 +358,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
       }
       epi.tile(m0 + quarter * 32, lane, n0 + col0 + c, v, (int)blockIdx.z, tile_n * 2 + slot, scratch, epi_state);
     }
+    if (args.timing && tid == 0) args.timing[cta_linear * 6 + 5] = clock64();
     tc_fence_before_sync();
   } else {
     // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -347,6 +368,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
         const int s = i % S::kStages;
         mbar_wait(smem_u32(&full[s]), (i / S::kStages) & 1);
         tc_fence_after_sync();
+        if (args.timing && i == 0) args.timing[cta_linear * 6 + 1] = clock64();
         const uint32_t base = smem_u32(stage_ptr(s));
         const uint64_t a_hi = make_desc_kmajor_sw128(base), a_lo = make_desc_kmajor_sw128(base + kATile);
         const uint64_t b_hi = make_desc_kmajor_sw128(base + 2 * kATile), b_lo = make_desc_kmajor_sw128(base + 2 * kATile + kBTile);
@@ -360,6 +382,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
         mma_commit(smem_u32(&empty[s]));      // stage reusable once these MMAs retire
       }
       if (num_kb > 0) mma_commit(smem_u32(accum_full));
+      if (args.timing) args.timing[cta_linear * 6 + 2] = clock64();
     }
     __syncwarp();
   }

@@ -194,6 +194,11 @@ GCCNMF_API int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, c
  */
 GCCNMF_API int gccnmf_gemm_tn_3xtf32(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb,
                           float* D, int64_t ldd, int M, int N, int Kc, int tile_n, void* stream);
+/* Diagnostics: the same product; `timing` (device uint64[6 x CTAs] or NULL) receives per-CTA clock64 stamps:
+ * kernel start, first stage full, last MMA issued, loaders finished, accumulator complete, epilogue end. */
+GCCNMF_API int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb,
+                                float* D, int64_t ldd, int M, int N, int Kc, int tile_n,
+                                unsigned long long* timing, void* stream);
 
 #ifdef __cplusplus
 }
