@@ -60,6 +60,10 @@ SIGNATURES = {
     'gccnmf_tdoa_argmax': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_size_t, _S]),
     'gccnmf_coeff_mask': (c_int, [_H, _P, c_int, c_int, c_int, _P, _P, _S]),
     'gccnmf_argmax_mask': (c_int, [_H, _P, c_int, c_int, _P, c_int, _P, _S]),
+    'gccnmf_online_targets': (c_int, [_H, _P, c_int, c_int, _P, _P, _S]),
+    'gccnmf_atom_mask': (c_int, [_H, _P, c_int, c_int, _P, c_float, c_float, c_int, c_float, c_float, _P, _S]),
+    'gccnmf_wiener_apply_workspace_bytes': (c_size_t, [c_int]),
+    'gccnmf_wiener_apply': (c_int, [_H, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _S]),
     'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
     'gccnmf_gemm_tn_3xtf32': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _S]),
     'gccnmf_gemm_tn_3xtf32_timed': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _S]),
@@ -299,6 +303,35 @@ class Handle(object):
         mask = self._out(out_key, 'mask', (K, T), torch.float32)
         self.check(self.lib.gccnmf_argmax_mask(self.h, _ptr(argmax), K, T, _ptr(lut), lut.numel(), _ptr(mask), self.stream))
         return mask
+
+    def online_targets(self, angular):
+        """angular (D, T) f64 -> (accumulated max (D, T) f64, targets (T) i32)."""
+        torch = self.torch
+        D, T = angular.shape
+        acc = self.empty((D, T), torch.float64)
+        targets = self.empty((T,), torch.int32)
+        self.check(self.lib.gccnmf_online_targets(self.h, _ptr(angular), D, T, _ptr(acc), _ptr(targets), self.stream))
+        return acc, targets
+
+    def atom_mask(self, argmax, targets=None, target_scalar=0.0, epsilon=1.0, mode=0, beta=1.0, noise_floor=0.0):
+        torch = self.torch
+        K, T = argmax.shape
+        mask = self.empty((K, T), torch.float32)
+        self.check(self.lib.gccnmf_atom_mask(self.h, _ptr(argmax), K, T, _ptr(targets), float(target_scalar), float(epsilon),
+                                             int(mode), float(beta), float(noise_floor), _ptr(mask), self.stream))
+        return mask
+
+    def wiener_apply(self, mask, W, X, want_filter=False):
+        """mask (K, T) f32, W (F, K) f32, X (2, F, T) c64 -> Y (2, F, T) c64 [, wiener (F, T) f32]."""
+        torch = self.torch
+        K, T = mask.shape
+        F = W.shape[0]
+        Y = self.empty((2, F, T), torch.complex64)
+        wiener = self.empty((F, T), torch.float32) if want_filter else None
+        ws = self.workspace('wiener', self.lib.gccnmf_wiener_apply_workspace_bytes(F))
+        self.check(self.lib.gccnmf_wiener_apply(self.h, _ptr(mask), _ptr(W), _ptr(X), F, T, K, _ptr(Y), _ptr(wiener), _ptr(ws),
+                                                ws.numel(), self.stream))
+        return (Y, wiener) if want_filter else Y
 
     def masked_recon_phase(self, masks, X, W, H, out_key=None):
         """masks (S,K,T) f32, X (2,F,T) c64, W (F,K), H (K,2T) -> (S,2,F,T) c64."""

@@ -263,6 +263,96 @@ masked_recon_kernel(const float* __restrict__ masks, const float2* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ a11 / a13: online localisation, atom masks, Wiener-like filter
+// acc[tau] = max over frames <= t of A[tau, t'] (onlineSpeechEnhancement.ipynb:416); one thread per TDOA scans time.
+__global__ void cummax_time_kernel(const double* __restrict__ A, int D, int T, double* __restrict__ acc) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double m = -INFINITY;
+  for (int t = 0; t < T; ++t) {
+    const double v = A[(int64_t)d * T + t];
+    if (v > m || v != v) m = v;          // numpy.max: NaN propagates (and then sticks: comparisons with NaN are false)
+    acc[(int64_t)d * T + t] = m;
+  }
+}
+// target[t] = argmax over TDOA of acc[:, t] (:417), numpy.argmax semantics.
+__global__ void argmax_tdoa_kernel(const double* __restrict__ acc, int D, int T, int32_t* __restrict__ target) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double bv = acc[t];
+  int bi = 0;
+  for (int d = 1; d < D; ++d) {
+    const double v = acc[(int64_t)d * T + t];
+    if (argmax_better(v, d, bv, bi)) { bv = v; bi = d; }
+  }
+  target[t] = bi;
+}
+
+// mode 0 (boxcar): |argmax - target| < eps -> 1 else 0      (onlineSpeechEnhancement.ipynb:423-425; gccNMFProcessor.py:263)
+// mode 1 (window): exp(-(|argmax - target| / eps)^beta) / (1 + floor) + floor     (gccNMFProcessor.py:265)
+__global__ void atom_mask_kernel(const int32_t* __restrict__ argmax, int K, int T, const int32_t* __restrict__ target, int target_stride,
+                                 float target_scalar, float eps, int mode, float beta, float noise_floor, float* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)K * T) return;
+  const int t = (int)(i % T);
+  const float mu = target ? (float)target[(int64_t)t * target_stride] : target_scalar;
+  const float dist = fabsf((float)argmax[i] - mu);
+  float m;
+  if (mode == 0) m = dist < eps ? 1.f : 0.f;
+  else m = expf(-powf(dist / eps, beta)) / (1.f + noise_floor) + noise_floor;
+  mask[i] = m;
+}
+
+__global__ void rowsum_w_kernel(const float* __restrict__ W, int F, int K, float* __restrict__ rowsum) {
+  const int f = blockIdx.x;
+  __shared__ float ws[32];
+  float s = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s += W[(int64_t)f * K + k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) rowsum[f] = s;
+  }
+}
+
+struct LoadMaskT {  // B(n = t, k = atom) = mask[atom][t]
+  static constexpr bool kContigK = false;
+  const float* mask; int K, T;
+  __device__ float operator()(int n, int k) const { return (n < T && k < K) ? __ldg(mask + (int64_t)k * T + n) : 0.f; }
+};
+
+// Y[c] = ((W . mask) / rowsum(W)) * X[c]     (onlineSpeechEnhancement.ipynb:429-431,440; gccNMFProcessor.py:267-269,209)
+__global__ void __launch_bounds__(kReconThreads, 2)
+wiener_apply_kernel(const float* __restrict__ mask, const float* __restrict__ W, const float* __restrict__ rowsumW,
+                    const float2* __restrict__ X, int F, int T, int K, float2* __restrict__ Y, float* __restrict__ wiener) {
+  float acc[RTM][RTN];
+  const int m0 = blockIdx.y * RM, n0 = blockIdx.x * RN;
+  LoadWRows a{W, F, K};
+  LoadMaskT b{mask, K, T};
+  gemm_simt_mainloop<float, RM, RN, RK, RTM, RTN>(acc, m0, n0, K, a, b);
+#pragma unroll
+  for (int i = 0; i < RTM; ++i) {
+    const int m = gemm_row<RM, RTM, RN / RTN>(m0, i);
+    if (m >= F) continue;
+    const float rs = rowsumW[m];
+#pragma unroll
+    for (int j = 0; j < RTN; ++j) {
+      const int n = gemm_col<RN, RTN, RN / RTN>(n0, j);
+      if (n >= T) continue;
+      const float w = acc[i][j] / rs;
+      if (wiener) wiener[(int64_t)m * T + n] = w;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float2 x = X[((int64_t)c * F + m) * T + n];
+        Y[((int64_t)c * F + m) * T + n] = float2{w * x.x, w * x.y};
+      }
+    }
+  }
+}
+
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 }  // namespace
@@ -345,6 +435,39 @@ int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float*
   dim3 grid((T + RN - 1) / RN, (F + RM - 1) / RM, S * 2);
   GCCNMF_LAUNCH(h, masked_recon_kernel, grid, kReconThreads, 0, stream, masks, reinterpret_cast<const float2*>(X), W, H, F, T, K,
                 reinterpret_cast<float2*>(out));
+  return GCCNMF_OK;
+}
+
+int gccnmf_online_targets(gccnmf_handle* h, const double* angular, int D, int T, double* accumulated_max, int32_t* targets, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, angular && accumulated_max && targets && D > 0 && T > 0, "online_targets: bad arguments");
+  GCCNMF_LAUNCH(h, cummax_time_kernel, (D + 63) / 64, 64, 0, stream, angular, D, T, accumulated_max);
+  GCCNMF_LAUNCH(h, argmax_tdoa_kernel, (T + 127) / 128, 128, 0, stream, accumulated_max, D, T, targets);
+  return GCCNMF_OK;
+}
+
+int gccnmf_atom_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, const int32_t* targets, float target_scalar, float epsilon,
+                     int mode, float beta, float noise_floor, float* mask, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, argmax && mask && K > 0 && T > 0 && (mode == 0 || mode == 1), "atom_mask: bad arguments");
+  const int64_t n = (int64_t)K * T;
+  GCCNMF_LAUNCH(h, atom_mask_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, argmax, K, T, targets, 1, target_scalar, epsilon, mode,
+                beta, noise_floor, mask);
+  return GCCNMF_OK;
+}
+
+size_t gccnmf_wiener_apply_workspace_bytes(int F) { return F > 0 ? align_up((size_t)F * sizeof(float), 256) : 0; }
+
+int gccnmf_wiener_apply(gccnmf_handle* h, const float* mask, const float* W, const float* X, int F, int T, int K, float* Y,
+                        float* wiener, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, mask && W && X && Y && F > 0 && T > 0 && K > 0, "wiener_apply: bad arguments");
+  if (!workspace || workspace_bytes < gccnmf_wiener_apply_workspace_bytes(F)) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "wiener_apply workspace too small");
+  float* rowsum = static_cast<float*>(workspace);
+  GCCNMF_LAUNCH(h, rowsum_w_kernel, F, 128, 0, stream, W, F, K, rowsum);
+  dim3 grid((T + RN - 1) / RN, (F + RM - 1) / RM);
+  GCCNMF_LAUNCH(h, wiener_apply_kernel, grid, kReconThreads, 0, stream, mask, W, rowsum, reinterpret_cast<const float2*>(X), F, T, K,
+                reinterpret_cast<float2*>(Y), wiener);
   return GCCNMF_OK;
 }
 

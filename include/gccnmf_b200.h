@@ -179,6 +179,27 @@ GCCNMF_API int gccnmf_coeff_mask(gccnmf_handle* h, const float* gccnmfs, int S, 
 GCCNMF_API int gccnmf_argmax_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, const uint8_t* lut,
                        int D, float* mask, void* stream);
 
+/* ---- a11 / a13: online localisation, atom masks, Wiener-like filter ------------------------------
+ * (notebooks/onlineSpeechEnhancement.ipynb:406-447, lowLatencySpeechEnhancement.ipynb:511-584,
+ *  realtime/gccNMFProcessor.py:201-231,259-269).  The notebooks' frame loop carries one piece of state, the
+ * accumulated maximum of the GCC-PHAT angular spectrum; it is a prefix maximum over time, so all frames are
+ * processed in one batch. */
+/* accumulated_max (D, T) f64 = running max over frames of angular (D, T); targets (T) i32 = its argmax over TDOA (:416-417). */
+GCCNMF_API int gccnmf_online_targets(gccnmf_handle* h, const double* angular, int D, int T, double* accumulated_max,
+                          int32_t* targets, void* stream);
+/* mask (K, T) f32 from argmax (K, T) and the target TDOA index (per frame: targets (T) i32; or targets == NULL and
+ * one float target_scalar, the Theano shared scalar of gccNMFProcessor.py:196).
+ * mode 0 boxcar |argmax - target| < epsilon (ipynb:423-425; gccNMFProcessor.py:263);
+ * mode 1 window exp(-(|argmax - target| / epsilon)^beta) / (1 + noise_floor) + noise_floor (gccNMFProcessor.py:265). */
+GCCNMF_API int gccnmf_atom_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, const int32_t* targets,
+                     float target_scalar, float epsilon, int mode, float beta, float noise_floor, float* mask,
+                     void* stream);
+/* Y (2, F, T) c64 = wiener * X with wiener (F, T) f32 = (W . mask) / rowsum(W) (ipynb:429-431,440;
+ * gccNMFProcessor.py:267-269,209); wiener may be NULL when only Y is wanted. */
+GCCNMF_API size_t gccnmf_wiener_apply_workspace_bytes(int F);
+GCCNMF_API int gccnmf_wiener_apply(gccnmf_handle* h, const float* mask, const float* W, const float* X, int F, int T,
+                        int K, float* Y, float* wiener, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a8: masked reconstruction with mixture phase  (gccNMFFunctions.py:145-151) -------------- */
 /* out[s, c] = (W . (H[:, c*T:(c+1)*T] * masks[s])) * exp(i angle(X[c])) ; out (S, 2, F, T) c64. */
 GCCNMF_API int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W,
