@@ -205,8 +205,13 @@ tc_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, int
       const int f = blockIdx.y * kApplyTile + g + 8 * r;
       if (f < F) {
         const int64_t i = (int64_t)f * K + k;
-        float numer = partial[i];
-        for (int z = 1; z < splits; ++z) numer += partial[(int64_t)z * slab + i];
+        float p[kMaxSplits];                         // all split partials in flight at once, then summed in split order
+#pragma unroll
+        for (int z = 0; z < kMaxSplits; ++z) p[z] = z < splits ? __ldg(partial + (int64_t)z * slab + i) : 0.f;
+        float numer = p[0];
+#pragma unroll
+        for (int z = 1; z < kMaxSplits; ++z)
+          if (z < splits) numer += p[z];
         const float w = W[i] * (numer / rs);
         W[i] = w;
         sumsq += w * w;
