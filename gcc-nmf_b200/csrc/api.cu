@@ -43,6 +43,8 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   h->last_error = "no error";
   const char* path = getenv("GCCNMF_NMF_PATH");
   h->force_simt_nmf = path && strcmp(path, "simt") == 0;
+  const char* split = getenv("GCCNMF_NMF_SPLIT");
+  h->nmf_split_bf16 = !(split && strcmp(split, "tf32") == 0);   // default: 3xBF16 (same measured parity, 12 % faster)
   *out = h;
   return GCCNMF_OK;
 }
@@ -76,6 +78,7 @@ int64_t gccnmf_launch_count(const gccnmf_handle* h) { return h ? h->launches : 0
 int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
   if (!h || !name) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (strcmp(name, "force_simt_nmf") == 0) { h->force_simt_nmf = value != 0; return GCCNMF_OK; }
+  if (strcmp(name, "nmf_split_bf16") == 0) { h->nmf_split_bf16 = value != 0; return GCCNMF_OK; }
   return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
 }
 

@@ -13,6 +13,7 @@ struct gccnmf_handle {
   int device = 0;
   int sm_count = 148;
   int64_t launches = 0;
+  bool nmf_split_bf16 = true;    // KL-NMF contractions: 0 = 3xTF32 (hi/lo tf32), 1 = 3xBF16 (hi/lo bf16)
   bool force_simt_nmf = false;   // GCCNMF_NMF_PATH=simt: float32 SIMT contractions instead of tcgen05 3xTF32
   std::string last_error;
   // twiddle tables e^{-2 pi i j / n}, j < n/2, float64 and float32, cached per FFT size

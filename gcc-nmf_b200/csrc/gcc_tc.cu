@@ -181,7 +181,7 @@ ArgmaxWorkspace carve_argmax(void* ws, size_t bytes, int F, int T, int D, int K)
 template <class Epi>
 int launch_argmax_gemm(gccnmf_handle* h, const GemmArgs& args, const Epi& epi, void* stream) {
   using S = umma::GemmSmem<128>;
-  auto kernel = umma::gemm_tn_3xtf32_kernel<128, false, Epi>;
+  auto kernel = umma::gemm_tn_3xtf32_kernel<128, false, umma::kSplitTF32, umma::kLoaderWarps, Epi>;
   static bool configured = false;
   if (!configured) {
     GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));

@@ -32,6 +32,7 @@ using umma::warp_transpose_32x32;
 
 constexpr int kTailRowsMax = 8;
 constexpr int kMaxSplits = 8;
+constexpr int kNmfWorkerWarps = 8;    // 2 loader groups of 128 threads (16 warps / 4 groups measured no faster: the loop is L2 / shared-memory bound)
 
 // ------------------------------------------------------------------------------------------------ epilogues
 struct EpiStoreRowMajor {  // D[z][m][n] = acc   (test entry, G4 partials)
@@ -307,18 +308,25 @@ __global__ void tc_pack_numer_kernel(const float* partial, int splits, int64_t n
 }
 
 // ------------------------------------------------------------------------------------------------ launch helpers
-template <int BN, bool SCALE_B, class Epi>
-int launch_gemm(gccnmf_handle* h, const GemmArgs& args, int tail_rows, int splits, const Epi& epi, void* stream) {
-  using S = umma::GemmSmem<BN>;
-  auto kernel = umma::gemm_tn_3xtf32_kernel<BN, SCALE_B, Epi>;
+template <int BN, bool SCALE_B, int SPLIT, class Epi>
+int launch_gemm_split(gccnmf_handle* h, const GemmArgs& args, int tail_rows, int splits, const Epi& epi, void* stream) {
+  using S = umma::GemmSmem<BN, SPLIT>;
+  constexpr int LW = kNmfWorkerWarps;
+  auto kernel = umma::gemm_tn_3xtf32_kernel<BN, SCALE_B, SPLIT, LW, Epi>;
   static bool configured = false;
   if (!configured) {
     GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
   dim3 grid((args.N + BN - 1) / BN, args.m_tiles + (tail_rows > 0 ? 1 : 0), splits);
-  GCCNMF_LAUNCH(h, kernel, grid, umma::kThreads, S::kTotal, stream, args, epi);
+  GCCNMF_LAUNCH(h, kernel, grid, LW * 32 + 32, S::kTotal, stream, args, epi);
   return 0;
+}
+
+template <int BN, bool SCALE_B, class Epi>
+int launch_gemm(gccnmf_handle* h, const GemmArgs& args, int tail_rows, int splits, const Epi& epi, void* stream) {
+  if (h->nmf_split_bf16) return launch_gemm_split<BN, SCALE_B, umma::kSplitBF16>(h, args, tail_rows, splits, epi, stream);
+  return launch_gemm_split<BN, SCALE_B, umma::kSplitTF32>(h, args, tail_rows, splits, epi, stream);
 }
 
 int tile_width(const gccnmf_handle* h, int m_tiles, int N, int splits) {
@@ -365,7 +373,7 @@ TcWorkspace tc_carve(const gccnmf_handle* h, void* ws, size_t bytes, int F, int 
   w.T2p = (T2 + 3) & ~3;
   w.splits = tc_pick_splits(m_tiles_of(F) * ((K + 127) / 128), (T2 + umma::kBK - 1) / umma::kBK, h->sm_count);
   const int bn = tile_width(h, m_tiles_of(K), T2, 1);          // G2's tile width decides the number of row-sum slots
-  w.rowsum_slots = ((T2 + bn - 1) / bn) * 2;
+  w.rowsum_slots = ((T2 + bn - 1) / bn) * (kNmfWorkerWarps / 4);
   w.HT = c.take<float>((size_t)T2 * K);
   w.WT = c.take<float>((size_t)K * w.Fp);
   w.VT = c.take<float>((size_t)T2 * w.Fp);
@@ -376,7 +384,7 @@ TcWorkspace tc_carve(const gccnmf_handle* h, void* ws, size_t bytes, int F, int 
   w.row_blocks = (F + kApplyTile - 1) / kApplyTile;
   w.colsum = c.take<float>((size_t)w.row_blocks * K);
   w.sumsq_part = c.take<float>((size_t)w.row_blocks * K);
-  w.rowsum_part = c.take<float>((size_t)(2 * ((T2 + 127) / 128)) * K);
+  w.rowsum_part = c.take<float>((size_t)((kNmfWorkerWarps / 4) * ((T2 + 127) / 128)) * K);
   w.norms = c.take<float>(K);
   w.ok = c.ok();
   return w;
@@ -388,7 +396,7 @@ size_t tc_workspace_bytes(int F, int T2, int K) {
   auto add = [&](size_t count) { n = align_up(n, 256) + count * sizeof(float); };
   add((size_t)T2 * K); add((size_t)K * Fp); add((size_t)T2 * Fp); add((size_t)F * T2p); add((size_t)T2 * Fp); add((size_t)K * T2p);
   add((size_t)kMaxSplits * F * K); add((size_t)((F + 31) / 32) * K); add((size_t)((F + 31) / 32) * K);
-  add((size_t)(2 * ((T2 + 127) / 128)) * K); add(K);
+  add((size_t)((kNmfWorkerWarps / 4) * ((T2 + 127) / 128)) * K); add(K);
   return align_up(n, 256);
 }
 

@@ -110,6 +110,35 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// K-major SWIZZLE_64B (rows of 64 bytes = 32 bf16, 8-row groups of 512 B, 16-byte chunk index XOR (row / 2) % 4): layout = 4.
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// D = f32, A = B = bf16 (kind::f16, format 1), both K-major, M x N; K = 16 per instruction.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// two floats -> packed bf16x2 (round to nearest even); low half = first argument
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M x N.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -134,14 +163,21 @@ struct GemmArgs {
   int m_fastest;          // 0: grid (n tiles, m tiles + tail, splits); 1: grid (m tiles, n tiles, splits) -- CTAs sharing a B slab are co-scheduled
 };
 
-constexpr int kLoaderWarps = 8;
-constexpr int kLoaderThreads = kLoaderWarps * 32;
-constexpr int kThreads = kLoaderThreads + 32;
+// Operand split modes (both: three tensor-core products hi.hi + hi.lo + lo.hi into a float32 accumulator):
+//   kSplitTF32  hi = tf32(x), lo = x - hi            kind::tf32, K = 8,  128-byte shared rows   error ~2^-21 per product
+//   kSplitBF16  hi = bf16(x), lo = bf16(x - hi)      kind::f16,  K = 16, 64-byte shared rows    error ~2^-17 per product
+// BF16 halves the shared-memory bytes per k-block (the measured limiter of the TF32 main loop) and runs at twice the
+// tensor rate; whether 2^-17 is enough is a parity question answered by the tests (KL-NMF, 100 iterations, 1e-4 bar).
+constexpr int kSplitTF32 = 0, kSplitBF16 = 1;
+constexpr int kLoaderWarps = 8;                 // default worker-warp count (loaders + epilogue); the KL-NMF GEMMs use 16
+constexpr int kThreads = kLoaderWarps * 32 + 32;
 
-template <int BN>
+template <int BN, int SPLIT = kSplitTF32>
 struct GemmSmem {
-  static constexpr int kStageBytes = (kBM + BN) * kBK * 4 * 2;  // A and B tiles, hi and lo
-  static constexpr int kStages = (BN <= 128) ? 3 : 2;
+  static constexpr int kElemBytes = (SPLIT == kSplitBF16) ? 2 : 4;
+  static constexpr int kRowBytes = kBK * kElemBytes;              // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  static constexpr int kStageBytes = (kBM + BN) * kRowBytes * 2;  // A and B tiles, hi and lo
+  static constexpr int kStages = (SPLIT == kSplitBF16) ? ((BN <= 128) ? 4 : 3) : ((BN <= 128) ? 3 : 2);
   static constexpr int kBarrierBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
 };
@@ -150,11 +186,12 @@ struct GemmSmem {
 // rows tid / 8 + (NT / 8) i.
 // Rows past the end of the matrix are clamped to its last row (their products land in accumulator rows /
 // columns the epilogue never stores), so the only predicate left is the k tail, uniform per thread.
-template <int ROWS, int NT>
+template <int ROWS, int NT, int SPLIT = kSplitTF32>
 struct TileLoader {
   static constexpr int kChunks = ROWS * 8 / NT;
   static constexpr int kRowStep = NT / 8;                 // rows between consecutive chunks of one thread
-  static constexpr int kSmemStep = kRowStep * 128;         // bytes (kRowStep is a multiple of 8 rows = 1024 B groups)
+  static constexpr int kRowBytes = (SPLIT == kSplitBF16) ? 64 : 128;
+  static constexpr int kSmemStep = kRowStep * kRowBytes;   // bytes (kRowStep is a multiple of the 8-row swizzle groups)
   const float* ptr;            // chunk 0 of this thread at the current k-block; advanced by 32 floats per fetch
   int64_t stride;              // floats between consecutive chunks (kRowStep rows)
   int imax;                    // last chunk index whose row is inside the matrix (chunks past it re-read that row)
@@ -168,7 +205,10 @@ struct TileLoader {
     ptr = src + (int64_t)first * ld + k0 + kcol;
     stride = (int64_t)kRowStep * ld;
     imax = max(0, (rows_valid - 1 - first) / kRowStep);
-    smem_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    if (SPLIT == kSplitBF16)   // 4 floats -> 8 bytes: half of 16-byte chunk c/2, swizzled with (row / 2) % 4
+      smem_off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (uint32_t)(((c >> 1) ^ ((r >> 1) & 3)) << 4) + (uint32_t)(c & 1) * 8u;
+    else
+      smem_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
   }
   // loads the k-block starting at column k0 (the pointer already points there) and advances to the next one
   __device__ __forceinline__ void fetch(float4 (&regs)[kChunks], int k0, int kc4) {
@@ -188,6 +228,14 @@ struct TileLoader {
 #pragma unroll
     for (int i = 0; i < kChunks; ++i) {
       const float4 x = regs[i];
+      if (SPLIT == kSplitBF16) {
+        const uint32_t h01 = pack_bf16x2(x.x, x.y), h23 = pack_bf16x2(x.z, x.w);
+        const float l0 = x.x - __uint_as_float(h01 << 16), l1 = x.y - __uint_as_float(h01 & 0xFFFF0000u);
+        const float l2 = x.z - __uint_as_float(h23 << 16), l3 = x.w - __uint_as_float(h23 & 0xFFFF0000u);
+        *reinterpret_cast<uint2*>(hi + smem_off + i * kSmemStep) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(lo + smem_off + i * kSmemStep) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+        continue;
+      }
       float4 h, l;
       h.x = tf32_round(x.x); h.y = tf32_round(x.y); h.z = tf32_round(x.z); h.w = tf32_round(x.w);
       l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
@@ -221,10 +269,12 @@ __device__ __forceinline__ void warp_transpose_32x32(float (&v)[32], float* scra
 //       warp owns (for per-CTA partial outputs); scratch = 32 x 33 floats of shared memory private to the
 //       warp (for warp_transpose_32x32); State = per-thread registers carried across the chunks.
 //   __device__ void elem(int m, int n, float acc, int z) const;      // SIMT tail rows
-template <int BN, bool SCALE_B, class Epilogue>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, bool SCALE_B, int SPLIT, int LW, class Epilogue>
+__global__ void __launch_bounds__(LW * 32 + 32, 1)
 gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, SPLIT>;
+  constexpr int kLoaderWarps = LW, kLoaderThreads = LW * 32, kThreads = LW * 32 + 32;
+  static_assert(LW == 8 || LW == 16, "worker warps");
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
 
@@ -273,7 +323,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
   if (args.timing && tid == 0) args.timing[cta_linear * 6 + 0] = clock64();
   if (tid == 0) {
     for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(smem_u32(&full[s]), kLoaderThreads / ((BN <= 128) ? 2 : 1));   // one loader group fills a stage
+      mbar_init(smem_u32(&full[s]), (BN <= 128) ? 128 : 256);   // one loader group fills a stage
       mbar_init(smem_u32(&empty[s]), 1);
     }
     mbar_init(smem_u32(accum_full), 1);
@@ -287,7 +337,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
 
   auto stage_ptr = [&](int s) { return smem + (size_t)s * S::kStageBytes; };
   // stage layout: A_hi | A_lo | B_hi | B_lo
-  constexpr int kATile = kBM * kBK * 4, kBTile = BN * kBK * 4;
+  constexpr int kATile = kBM * S::kRowBytes, kBTile = BN * S::kRowBytes;
 
   if (warp < kLoaderWarps) {
     // ------------------------------------------------------------------ loaders
@@ -299,15 +349,15 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
     // for the newer one as well -- seen in the SASS control codes, and as 38 % long-scoreboard stalls in ncu.)
     // BN = 256: one group (a k-block there is 1536 MMA cycles, so a prefetch distance of one k-block is enough and the
     // 12 chunks per thread fit the register budget; two groups would need 24).
-    constexpr int kGroups = (BN <= 128) ? 2 : 1;
+    constexpr int kGroups = (BN <= 128) ? LW / 4 : LW / 8;      // groups of 128 (BN = 128) / 256 (BN = 256) threads
     constexpr int kGroupThreads = kLoaderThreads / kGroups;
     const int group = tid / kGroupThreads, gtid = tid % kGroupThreads;
-    TileLoader<kBM, kGroupThreads> la;
-    TileLoader<BN, kGroupThreads> lb;
+    TileLoader<kBM, kGroupThreads, SPLIT> la;
+    TileLoader<BN, kGroupThreads, SPLIT> lb;
     const int kb_first = kb_begin + group;
     la.init(args.A, args.lda, m0, min(args.M, args.m_tiles * kBM), kb_first * kBK, gtid);
     lb.init(args.B, args.ldb, n0, args.N, kb_first * kBK, gtid);
-    float4 ar[TileLoader<kBM, kGroupThreads>::kChunks], br[TileLoader<BN, kGroupThreads>::kChunks];
+    float4 ar[TileLoader<kBM, kGroupThreads, SPLIT>::kChunks], br[TileLoader<BN, kGroupThreads, SPLIT>::kChunks];
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
     auto fetch = [&](int kb) {
       la.fetch(ar, kb * kBK, kc4);
@@ -323,7 +373,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
       const uint32_t use = i / S::kStages;
       if (SCALE_B) {
 #pragma unroll
-        for (int j = 0; j < TileLoader<BN, kGroupThreads>::kChunks; ++j) { br[j].x *= sc.x; br[j].y *= sc.y; br[j].z *= sc.z; br[j].w *= sc.w; }
+        for (int j = 0; j < TileLoader<BN, kGroupThreads, SPLIT>::kChunks; ++j) { br[j].x *= sc.x; br[j].y *= sc.y; br[j].z *= sc.z; br[j].w *= sc.w; }
       }
       if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // MMAs that read this stage have retired
       unsigned char* st = stage_ptr(s);
@@ -341,7 +391,7 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
       if (args.timing && tid == 0) args.timing[cta_linear * 6 + 4] = clock64();
     }
     const int quarter = warp & 3;                         // TMEM lane quarter this warp may read
-    constexpr int kColsPerWarp = BN / 2;                  // warps w and w + 4 split the columns of a lane quarter
+    constexpr int kColsPerWarp = BN / (LW / 4);           // the LW / 4 warps of a lane quarter split the columns
     const int slot = warp >> 2;
     const int col0 = slot * kColsPerWarp;
     float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // aliases stage 0 (idle now)
@@ -356,28 +406,40 @@ gemm_tn_3xtf32_kernel(GemmArgs args, Epilogue epi) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      epi.tile(m0 + quarter * 32, lane, n0 + col0 + c, v, (int)blockIdx.z, tile_n * 2 + slot, scratch, epi_state);
+      epi.tile(m0 + quarter * 32, lane, n0 + col0 + c, v, (int)blockIdx.z, tile_n * (LW / 4) + slot, scratch, epi_state);
     }
     if (args.timing && tid == 0) args.timing[cta_linear * 6 + 5] = clock64();
     tc_fence_before_sync();
   } else {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
+      constexpr uint32_t idesc = (SPLIT == kSplitBF16) ? make_idesc_bf16(kBM, BN) : make_idesc_tf32(kBM, BN);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % S::kStages;
         mbar_wait(smem_u32(&full[s]), (i / S::kStages) & 1);
         tc_fence_after_sync();
         if (args.timing && i == 0) args.timing[cta_linear * 6 + 1] = clock64();
         const uint32_t base = smem_u32(stage_ptr(s));
-        const uint64_t a_hi = make_desc_kmajor_sw128(base), a_lo = make_desc_kmajor_sw128(base + kATile);
-        const uint64_t b_hi = make_desc_kmajor_sw128(base + 2 * kATile), b_lo = make_desc_kmajor_sw128(base + 2 * kATile + kBTile);
+        if (SPLIT == kSplitBF16) {
+          const uint64_t a_hi = make_desc_kmajor_sw64(base), a_lo = make_desc_kmajor_sw64(base + kATile);
+          const uint64_t b_hi = make_desc_kmajor_sw64(base + 2 * kATile), b_lo = make_desc_kmajor_sw64(base + 2 * kATile + kBTile);
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);   // +32 bytes per k-step inside the 128-byte swizzle row
-          mma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (i | k) != 0);
-          mma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
-          mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);       // +32 bytes per 16-element k-step inside the 64-byte swizzle row
+            mma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, (i | k) != 0);
+            mma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+            mma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+        } else {
+          const uint64_t a_hi = make_desc_kmajor_sw128(base), a_lo = make_desc_kmajor_sw128(base + kATile);
+          const uint64_t b_hi = make_desc_kmajor_sw128(base + 2 * kATile), b_lo = make_desc_kmajor_sw128(base + 2 * kATile + kBTile);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);   // +32 bytes per k-step inside the 128-byte swizzle row
+            mma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (i | k) != 0);
+            mma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+            mma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+          }
         }
         mma_commit(smem_u32(&empty[s]));      // stage reusable once these MMAs retire
       }

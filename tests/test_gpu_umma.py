@@ -12,7 +12,8 @@ def h():
     return default_handle()
 
 
-def _check(h, M, N, Kc, tile_n, positive):
+def _check(h, M, N, Kc, tile_n, positive, bf16=False):
+    h.set_option('nmf_split_bf16', 1 if bf16 else 0)
     import torch
     g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + Kc)
     ld = (Kc + 3) // 4 * 4
@@ -26,21 +27,24 @@ def _check(h, M, N, Kc, tile_n, positive):
     ref = (Ad[:, :Kc].double() @ Bd[:, :Kc].double().T)
     scale = (Ad[:, :Kc].abs().double() @ Bd[:, :Kc].abs().double().T)     # |a|.|b| bound for the error
     err = ((D.double() - ref).abs() / scale).max().item()
+    h.set_option('nmf_split_bf16', 1)      # library default
     return err
 
 
 @pytest.mark.parametrize('tile_n', [128, 256])
 @pytest.mark.parametrize('shape', [(128, 128, 32), (128, 256, 64), (256, 384, 1024), (100, 70, 40), (513, 3744, 1024),
                                    (1024, 3744, 513), (513, 1024, 3744)])
-def test_gemm_3xtf32_matches_float64(h, shape, tile_n):
+@pytest.mark.parametrize('bf16', [False, True])
+def test_gemm_3xtf32_matches_float64(h, shape, tile_n, bf16):
     M, N, Kc = shape
     for positive in (True, False):
-        err = _check(h, M, N, Kc, tile_n, positive)
+        err = _check(h, M, N, Kc, tile_n, positive, bf16)
         # The operand split recovers float32 products (plain TF32 would give ~5e-4); what remains is the tensor
         # core's float32 accumulator, which truncates on every accumulation: a bias of up to ~2^-24 per MMA
         # into the same accumulator (3 Kc / 8 of them), fully coherent for all-positive data.
-        bound = 2e-6 + 4e-8 * (3 * Kc / 8)
-        assert err < bound, (shape, tile_n, positive, err, bound)
+        # 3xBF16 (hi/lo bf16): operand split error 2^-17 per product (sign-symmetric) and half as many accumulations.
+        bound = (8e-6 + 4e-8 * (3 * Kc / 16)) if bf16 else (2e-6 + 4e-8 * (3 * Kc / 8))
+        assert err < bound, (shape, tile_n, positive, bf16, err, bound)
 
 
 def test_klnmf_tensor_core_path_matches_oracle(h):
@@ -55,13 +59,15 @@ def test_klnmf_tensor_core_path_matches_oracle(h):
 
     def rel(a, b):
         return float(np.linalg.norm(a - b) / np.linalg.norm(b))
-    for iters, tol in ((1, 5e-6), (30, 1e-4)):
-        W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
-        h.klnmf(h.to_device(V), W, H, iters)
-        Wo, Ho = orc.performKLNMF(V, K, iters, 0, W0=W0, H0=H0)
-        eW, eH = rel(W.cpu().numpy(), Wo), rel(H.cpu().numpy(), Ho)
-        print('tensor-core KL-NMF %d iterations: rel W %.2e  rel H %.2e' % (iters, eW, eH))
-        assert eW < tol and eH < tol, (iters, eW, eH)
+    for split, name in ((0, '3xTF32'), (1, '3xBF16')):
+        h.set_option('nmf_split_bf16', split)
+        for iters, tol in ((1, 2e-5), (30, 1e-4)):
+            W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
+            h.klnmf(h.to_device(V), W, H, iters)
+            Wo, Ho = orc.performKLNMF(V, K, iters, 0, W0=W0, H0=H0)
+            eW, eH = rel(W.cpu().numpy(), Wo), rel(H.cpu().numpy(), Ho)
+            print('tensor-core KL-NMF %s %d iterations: rel W %.2e  rel H %.2e' % (name, iters, eW, eH))
+            assert eW < tol and eH < tol, (name, iters, eW, eH)
     # step protocol (multi-GPU) against the fused loop
     V_d = h.to_device(V)
     W1, H1 = h.to_device(W0.copy()), h.to_device(H0.copy())

@@ -5,6 +5,8 @@ import torch
 sys.path.insert(0, '.')
 from gcc_nmf_b200._lib import default_handle, _ptr
 h = default_handle()
+import os
+h.set_option("nmf_split_bf16", 1 if os.environ.get("SPLIT") == "bf16" else 0)
 shapes = {'G1/G3 (F x T2 over K)': (512, 3744, 1024, 128), 'G2 (K x T2 over F)': (1024, 3744, 513, 256), 'G4-like (F x K over T2/4)': (512, 1024, 936, 128)}
 for name, (M, N, Kc, bn) in shapes.items():
     ld = (Kc + 3) // 4 * 4
