@@ -21,9 +21,10 @@ namespace {
 
 using umma::GemmArgs;
 
-// Error budget of step 2 relative to sum_f |W| (|G| <= 1): operand split 2^-21, float32 rounding of G 2^-24,
-// accumulator truncation <= 2^-24 per accumulation x (3 F / 8) accumulations (measured 1.2e-5 at 384, tests/test_gpu_umma.py).
-// Margin = 2 x (1.5e-5 + slack): two values each off by the bound.
+// Error budget of step 2 relative to sum_f |W| (|G| <= 1): 3xBF16 operand split <= 2^-17 per product (worst case, all
+// coherent), float32 rounding of G 2^-24, accumulator truncation <= 2^-24 per accumulation x (3 F / 16) accumulations
+// (measured 1.2e-5 at 384 accumulations, tests/test_gpu_umma.py): < 2e-5 per value.  Margin = 2 x that + slack: two
+// values each off by the bound.
 constexpr float kMarginFactor = 6e-5f;
 
 // ------------------------------------------------------------------ step 1: G[(t, tau)][f]
@@ -180,8 +181,8 @@ ArgmaxWorkspace carve_argmax(void* ws, size_t bytes, int F, int T, int D, int K)
 
 template <class Epi>
 int launch_argmax_gemm(gccnmf_handle* h, const GemmArgs& args, const Epi& epi, void* stream) {
-  using S = umma::GemmSmem<128>;
-  auto kernel = umma::gemm_tn_3xtf32_kernel<128, false, umma::kSplitTF32, umma::kLoaderWarps, Epi>;
+  using S = umma::GemmSmem<128, umma::kSplitBF16>;
+  auto kernel = umma::gemm_tn_3xtf32_kernel<128, false, umma::kSplitBF16, umma::kLoaderWarps, Epi>;
   static bool configured = false;
   if (!configured) {
     GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
