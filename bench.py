@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(sampleRate=16000, windowSize=1024, hopSize=256, dictionarySize=1024, numTDOAs=64,
            numIterations=100, microphoneSeparationInMetres=0.1, duration_s=30.0)
+# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one KL-NMF iteration (profiles/r01c_ncu_full_nmf_kernels.csv)
+NMF_ITERATION_DRAM_BYTES = 111.9e6
 METRIC = 'STFT frames/sec (1024-FFT, K=1024) full GCC-NMF pipeline'
 UNIT = 'frames/s'
 
@@ -50,7 +52,7 @@ class ClockSampler(object):
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -210,7 +212,6 @@ def run_gpu(args):
     barrier()
     wall = time.perf_counter() - wall0
     launches = h.launches - launches0
-    clocks = sampler.stop() if sampler else None
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=h.device)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -238,6 +239,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_value = total_frames * args.steps / (float(e2e_total.item()) * 1e-3)
+    clocks = sampler.stop() if sampler else None      # sampled over the device-resident AND the end-to-end timed regions
 
     if rank == 0:
         F, K, I = CFG['windowSize'] // 2 + 1, CFG['dictionarySize'], CFG['numIterations']
@@ -254,11 +256,15 @@ def run_gpu(args):
             'wall_s_timed_region': wall, 'gpu_launches': int(launches), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(x_host.numel() * 4),
                     'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': float(e2e_total.item()) / args.steps},
-            'roofline': {'kernel': 'KL-NMF iteration (W.H with fused V/(W.H), W^T.R, R.H^T GEMMs + updates), per rank',
+            'roofline': {'kernel': 'KL-NMF iteration: umma::gemm_tn_3xtf32_kernel x4 (tcgen05, 3xBF16 operand split) + W update, per rank',
                          'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                         'frac': achieved / peak_tf, 'traffic': NMF_ITERATION_DRAM_BYTES, 'peak_source': peak_src,
                          'algorithmic_flops_per_launch_group': flops_per_iter, 'ms_per_iteration': nmf_ms / I,
-                         'note': 'algorithmic flops 16 F K T per iteration / CUDA-event time of the NMF stage inside the step'},
+                         'executed_tensor_tflops': 3 * achieved, 'frac_executed': 3 * achieved / peak_tf,
+                         'note': 'achieved = algorithmic flops (16 F K T per iteration, SURVEY.md 8d) / CUDA-event time of the NMF stage '
+                                 'inside the step; float32-level parity needs 3 tensor-core products per algorithmic product (hi.hi + hi.lo '
+                                 '+ lo.hi of a bf16 hi/lo split), so executed tensor flops are 3x: frac_executed is the tensor-pipe view; '
+                                 'traffic = DRAM bytes per iteration from the ncu --set full capture in profiles/ (cold-cache replay)'},
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(3.0)
