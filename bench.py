@@ -253,6 +253,7 @@ def run_gpu(args):
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world),
             'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
+            'collective': getattr(pipe, 'collective', None),
             'wall_s_timed_region': wall, 'gpu_launches': int(launches), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(x_host.numel() * 4),
                     'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': float(e2e_total.item()) / args.steps},

@@ -51,6 +51,7 @@ SIGNATURES = {
     'gccnmf_klnmf_begin': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, _P, c_size_t, _S]),
     'gccnmf_klnmf_step_numer': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, c_int, _P, _P, c_size_t, _S]),
     'gccnmf_klnmf_step_apply': (c_int, [_H, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
+    'gccnmf_klnmf_step_apply_multimem': (c_int, [_H, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
     'gccnmf_klnmf_end': (c_int, [_H, c_int, c_int, _P, _P, c_int, c_int, _P, c_size_t, _S]),
     'gccnmf_phat_angspec_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_phat_angspec': (c_int, [_H, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _S]),
@@ -242,6 +243,14 @@ class Handle(object):
         T2 = H.shape[1]
         ws = self._klnmf_ws(F, T2, K)
         self.check(self.lib.gccnmf_klnmf_step_apply(self.h, F, T2, _ptr(W), _ptr(H), K, _ptr(numer), _ptr(ws), ws.numel(), self.stream))
+
+    def klnmf_step_apply_multimem(self, W, H, numer_multicast_ptr):
+        """W update reading the cross-rank numerator sum through the NVSwitch multicast address (an int)."""
+        F, K = W.shape
+        T2 = H.shape[1]
+        ws = self._klnmf_ws(F, T2, K)
+        self.check(self.lib.gccnmf_klnmf_step_apply_multimem(self.h, F, T2, _ptr(W), _ptr(H), K, int(numer_multicast_ptr), _ptr(ws),
+                                                             ws.numel(), self.stream))
 
     def klnmf_end(self, W, H, iterations_done):
         F, K = W.shape

@@ -239,8 +239,8 @@ int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, co
                              void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream);
 int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
                               size_t workspace_bytes, bool have_rowsum, void* stream);
-int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, void* workspace,
-                            size_t workspace_bytes, void* stream);
+int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
+                            void* workspace, size_t workspace_bytes, void* stream);
 int gccnmf_klnmf_tc_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
                            size_t workspace_bytes, void* stream);
 int gccnmf_klnmf_tc_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
@@ -301,9 +301,21 @@ int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H,
   GCCNMF_REQUIRE(h, numer != nullptr, "klnmf_step_apply: NULL numerator");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, numer, workspace, workspace_bytes, stream);
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, numer, false, workspace, workspace_bytes, stream);
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   return apply_W_impl(h, F, T2, W, H, K, numer, w, stream);
+}
+
+int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer_multicast,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (int st = check_dims(h, F, T2, K)) return st;
+  (void)H;
+  GCCNMF_REQUIRE(h, numer_multicast != nullptr, "klnmf_step_apply_multimem: NULL multicast address");
+  if (!use_tc(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_apply_multimem: only the tensor-core path reads the numerator through multimem");
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  return gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, numer_multicast, true, workspace, workspace_bytes, stream);
 }
 
 int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,
@@ -332,7 +344,7 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
                                             it == 0 ? 0 : (update_W ? 2 : 1), update_W && it > 0, stream)) return st;
       if (!update_W) continue;
       if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
-      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, nullptr, workspace, workspace_bytes, stream)) return st;
+      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, nullptr, false, workspace, workspace_bytes, stream)) return st;
     }
     return gccnmf_klnmf_tc_finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream);
   }

@@ -182,7 +182,16 @@ __global__ void tc_rowsum_kernel(const float* H, int T2, int64_t ld, float* rows
 //   pass 2  norm = sqrt(sum of the row-block partials) (:79); W = W' / norm (:80); W^T through a shared-memory transpose;
 //           per-tile column sums -> colsum_part[row block][atom] (the next H update's colsum(W)); norms[atom].
 // rowsum(H) = sum of `rowsum_slots` partial vectors (G2's epilogue) or one all-reduced vector.
+// Cross-rank sum read straight from the NVSwitch: `p` is the MULTICAST address of a symmetric buffer; the switch
+// returns the float32 sum of the word at that offset over all GPUs of the multicast group (NVLS in-switch reduction).
+__device__ __forceinline__ float multimem_sum_f32(const float* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
 constexpr int kApplyTile = 32;
+template <bool MULTIMEM>
 __global__ void __launch_bounds__(kApplyTile * 8)
 tc_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, int splits, const float* __restrict__ rowsum,
                    int rowsum_slots, int F, int K, float* __restrict__ sumsq_part) {
@@ -193,8 +202,11 @@ tc_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, int
   const int64_t slab = (int64_t)F * K;
   if (g == 0) {
     float rs = 0.f;
-    if (k < K)
-      for (int s = 0; s < rowsum_slots; ++s) rs += rowsum[(int64_t)s * K + k];
+    if (k < K) {
+      if (MULTIMEM) rs = multimem_sum_f32(rowsum + k);
+      else
+        for (int s = 0; s < rowsum_slots; ++s) rs += rowsum[(int64_t)s * K + k];
+    }
     rs_s[c] = rs;
   }
   __syncthreads();
@@ -206,13 +218,18 @@ tc_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, int
       const int f = blockIdx.y * kApplyTile + g + 8 * r;
       if (f < F) {
         const int64_t i = (int64_t)f * K + k;
-        float p[kMaxSplits];                         // all split partials in flight at once, then summed in split order
+        float numer;
+        if (MULTIMEM) {
+          numer = multimem_sum_f32(partial + i);      // sum over ranks, reduced inside the NVSwitch
+        } else {
+          float p[kMaxSplits];                       // all split partials in flight at once, then summed in split order
 #pragma unroll
-        for (int z = 0; z < kMaxSplits; ++z) p[z] = z < splits ? __ldg(partial + (int64_t)z * slab + i) : 0.f;
-        float numer = p[0];
+          for (int z = 0; z < kMaxSplits; ++z) p[z] = z < splits ? __ldg(partial + (int64_t)z * slab + i) : 0.f;
+          numer = p[0];
 #pragma unroll
-        for (int z = 1; z < kMaxSplits; ++z)
-          if (z < splits) numer += p[z];
+          for (int z = 1; z < kMaxSplits; ++z)
+            if (z < splits) numer += p[z];
+        }
         const float w = W[i] * (numer / rs);
         W[i] = w;
         sumsq += w * w;
@@ -479,14 +496,18 @@ int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, c
 
 // :77-:80; the H rescale of :81 stays pending (applied by the next update_H, or by finish).  Numerator and row
 // sums come from `numer` (F*K + K floats, all-reduced across ranks) when given, else from this rank's partials.
-int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer,
+int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
                             void* workspace, size_t workspace_bytes, void* stream) {
   TC_CARVE_OR_FAIL(w);
   const float* partial = numer ? numer : w.partial;
   const float* rowsum = numer ? numer + (int64_t)F * K : w.rowsum_part;
   const dim3 grid((K + kApplyTile - 1) / kApplyTile, w.row_blocks), block(kApplyTile, 8);
-  GCCNMF_LAUNCH(h, tc_apply_w1_kernel, grid, block, 0, stream, W, partial, numer ? 1 : w.splits, rowsum, numer ? 1 : w.rowsum_slots,
-                F, K, w.sumsq_part);
+  if (numer_is_multicast) {
+    GCCNMF_LAUNCH(h, tc_apply_w1_kernel<true>, grid, block, 0, stream, W, partial, 1, rowsum, 1, F, K, w.sumsq_part);
+  } else {
+    GCCNMF_LAUNCH(h, tc_apply_w1_kernel<false>, grid, block, 0, stream, W, partial, numer ? 1 : w.splits, rowsum,
+                  numer ? 1 : w.rowsum_slots, F, K, w.sumsq_part);
+  }
   GCCNMF_LAUNCH(h, tc_apply_w2_kernel, grid, block, 0, stream, W, w.WT, w.Fp, w.sumsq_part, w.row_blocks, F, K, w.norms, w.colsum);
   return 0;
 }

@@ -16,6 +16,8 @@ float32 reduction order.
 
 `ShardComm` abstracts the three exchanges so the host logic is testable on CPU with gloo.
 """
+import os
+
 import numpy as np
 
 from . import gccNMFFunctions as fn
@@ -85,6 +87,60 @@ def klnmf_sharded(ops, comm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon,
     return W, H_s
 
 
+class MultimemNumerator(object):
+    """Two symmetric (F*K + K)-float buffers bound to an NVLink multicast object (torch symmetric memory) for the
+    fused W update: step_numer writes the local partial, a device-side cross-rank barrier follows, and the W-update
+    kernel reads the cross-rank SUM with multimem.ld_reduce (reduction inside the NVSwitch).  Double-buffered so one
+    barrier per iteration is enough.  `create` returns None when the platform has no multicast support (the caller
+    then uses the NCCL all-reduce)."""
+
+    def __init__(self, buffers, handles):
+        self.buffers, self.handles = buffers, handles
+
+    @classmethod
+    def create(cls, numel, device, group):
+        try:
+            import torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group if group is not None else dist.group.WORLD
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+            buffers, handles = [], []
+            for _ in range(2):
+                t = symm_mem.empty(numel, dtype=torch.float32, device=device)
+                hdl = symm_mem.rendezvous(t, group)
+                if not getattr(hdl, 'has_multicast_support', False) or not int(hdl.multicast_ptr):
+                    return None
+                buffers.append(t)
+                handles.append(hdl)
+            return cls(buffers, handles)
+        except Exception:
+            return None
+
+    def buffer(self, it):
+        return self.buffers[it & 1]
+
+    def barrier(self, it):
+        self.handles[it & 1].barrier(channel=0, timeout_ms=20000)
+
+    def multicast_ptr(self, it):
+        return int(self.handles[it & 1].multicast_ptr)
+
+
+def klnmf_sharded_multimem(ops, mm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon):
+    """klnmf_sharded with the all-reduce folded into the W-update kernel (gccnmf_klnmf_step_apply_multimem)."""
+    ops.klnmf_begin(V_s, W, H_s)
+    for it in range(numIterations):
+        ops.klnmf_step_numer(V_s, W, H_s, it, mm.buffer(it), sparsityAlpha, epsilon)
+        mm.barrier(it)                 # every rank's partial is written (and every rank is done reading buffer it-2)
+        ops.klnmf_step_apply_multimem(W, H_s, mm.multicast_ptr(it))
+    ops.klnmf_end(W, H_s, numIterations)
+    return W, H_s
+
+
 def overlap_add_seams(comm, y_local, owned, halo):
     """y_local: (B, owned + halo) un-trimmed local overlap-add.  Adds the left neighbour's tail onto
     this rank's head and returns the owned part (the last rank keeps its tail)."""
@@ -128,6 +184,8 @@ class ShardedGCCNMFPipeline(object):
         W0, H0s = sharded_nmf_init(self.F, self.total_frames, self.K, self.eps, self.seed, self.t0, self.t1)
         self.W0, self.H0s = self.h.to_device(W0), self.h.to_device(H0s)
         self.numer = self.h.empty((self.F * self.K + self.K,), torch.float32)
+        self.multimem = None            # decided on the first call (needs the agreed NMF path)
+        self.collective = 'nccl-all-reduce'
         self.stage_events = None
 
     def local_samples(self):
@@ -159,6 +217,13 @@ class ShardedGCCNMFPipeline(object):
             self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
         if int(flag.item()) == 0:
             self.h.set_option('force_simt_nmf', 1)
+        elif self.comm.world > 1 and os.environ.get('GCCNMF_COLLECTIVE', 'multimem') == 'multimem':
+            # fused W update over the NVSwitch multicast (all ranks must agree that it is available)
+            mm = MultimemNumerator.create(self.F * self.K + self.K, self.h.device, self.comm.group)
+            ok = self.torch.tensor([1 if mm is not None else 0], dtype=self.torch.int32, device=self.h.device)
+            self.comm.dist.all_reduce(ok, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+            if int(ok.item()) == 1:
+                self.multimem, self.collective = mm, 'multimem.ld_reduce in the W-update kernel (NVLS)'
         self._path_agreed = True
 
     def enhance(self, samples, collect_stage_times=False):
@@ -179,7 +244,10 @@ class ShardedGCCNMFPipeline(object):
         W.copy_(self.W0)
         H.copy_(self.H0s)
         self._agree_on_nmf_path(V.shape[1])
-        klnmf_sharded(h, comm, V, W, H, self.I, self.alpha, self.eps, self.numer)
+        if self.multimem is not None:
+            klnmf_sharded_multimem(h, self.multimem, V, W, H, self.I, self.alpha, self.eps)
+        else:
+            klnmf_sharded(h, comm, V, W, H, self.I, self.alpha, self.eps, self.numer)
         self._mark('nmf')
         argmax, refined = h.tdoa_argmax(coh, self.E, W, out_key=key)
         self._mark('gccnmf')

@@ -126,6 +126,17 @@ GCCNMF_API int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, 
                             void* workspace, size_t workspace_bytes, void* stream);
 GCCNMF_API int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
                             const float* numer, void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * Fused collective variant of step_apply for NVSwitch systems: every rank's step_numer wrote its partial into the
+ * SAME offset of a symmetric buffer bound to an NVLink multicast object; `numer_multicast` is the multicast address
+ * of that buffer.  After a cross-rank barrier the W update reads each numerator / row-sum word with
+ * multimem.ld_reduce.add.f32 -- the sum over ranks is formed inside the switch (NVLS) while the kernel streams it,
+ * so there is no separate all-reduce kernel and no second pass over the 2 MB.  Every rank receives the same
+ * switch-reduced value, hence a bit-identical W.  Tensor-core path only (GCCNMF_ERR_UNSUPPORTED otherwise).
+ */
+GCCNMF_API int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
+                                     const float* numer_multicast, void* workspace, size_t workspace_bytes,
+                                     void* stream);
 GCCNMF_API int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done,
                      void* workspace, size_t workspace_bytes, void* stream);
 

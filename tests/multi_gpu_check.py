@@ -45,6 +45,7 @@ def main():
 
         def rel(a, b):
             return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+        print('collective:', sp.collective)
         print('world', world, 'frames', sp.total_frames, 'target', r['targetTDOAIndexes'], r1['targetTDOAIndexes'])
         print('W identical across ranks:', all(np.array_equal(Ws[0], w) for w in Ws))
         print('rel W sharded vs single: %.3e' % rel(Ws[0], W1))
