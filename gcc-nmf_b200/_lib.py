@@ -67,6 +67,8 @@ SIGNATURES = {
     'gccnmf_wiener_apply': (c_int, [_H, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _S]),
     'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
     'gccnmf_gemm_tn_3xtf32': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _S]),
+    'gccnmf_gemm_planes_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'gccnmf_gemm_planes': (c_int, [_H, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _S]),
     'gccnmf_gemm_tn_3xtf32_timed': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _S]),
 }
 
@@ -362,6 +364,18 @@ class Handle(object):
         self.check(self.lib.gccnmf_gemm_tn_3xtf32(self.h, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(D), D.stride(0),
                                                   M, N, Kc, tile_n, self.stream))
         return D
+
+    def gemm_planes(self, A, B, a_mn_major=False, b_mn_major=False, tile_n=128, splits=1, timing=None):
+        """(A . B^T)^T on the TMA-fed plane GEMM.  A: (M, Kc) or, MN-major, (Kc, M); B likewise with N.
+        Returns DT (splits, N, M) f32 (partial slabs over k ranges when splits > 1)."""
+        torch = self.torch
+        M, Kc = (A.shape[1], A.shape[0]) if a_mn_major else A.shape
+        N = B.shape[1] if b_mn_major else B.shape[0]
+        DT = self.empty((splits, N, M), torch.float32)
+        ws = self.workspace('gemm_planes', self.lib.gccnmf_gemm_planes_workspace_bytes(M, N, Kc))
+        self.check(self.lib.gccnmf_gemm_planes(self.h, _ptr(A), 1 if a_mn_major else 0, _ptr(B), 1 if b_mn_major else 0, _ptr(DT),
+                                               M, N, Kc, tile_n, splits, _ptr(ws), ws.numel(), _ptr(timing), self.stream))
+        return DT
 
 
 _default_handles = {}

@@ -45,6 +45,10 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   h->force_simt_nmf = path && strcmp(path, "simt") == 0;
   const char* split = getenv("GCCNMF_NMF_SPLIT");
   h->nmf_split_bf16 = !(split && strcmp(split, "tf32") == 0);   // default: 3xBF16 (same measured parity, 12 % faster)
+  const char* tma = getenv("GCCNMF_NMF_TMA");
+  h->nmf_tma = !(tma && strcmp(tma, "0") == 0);
+  const char* pdl = getenv("GCCNMF_NMF_PDL");
+  h->nmf_pdl = pdl && strcmp(pdl, "1") == 0;
   *out = h;
   return GCCNMF_OK;
 }
@@ -55,6 +59,7 @@ int gccnmf_destroy(gccnmf_handle* h) {
     if (h->plan_tw64[i]) cudaFree(h->plan_tw64[i]);
     if (h->plan_tw32[i]) cudaFree(h->plan_tw32[i]);
   }
+  gccnmf_tmap_cache_free(h);
   delete h;
   return GCCNMF_OK;
 }
@@ -79,6 +84,8 @@ int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
   if (!h || !name) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (strcmp(name, "force_simt_nmf") == 0) { h->force_simt_nmf = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "nmf_split_bf16") == 0) { h->nmf_split_bf16 = value != 0; return GCCNMF_OK; }
+  if (strcmp(name, "nmf_tma") == 0) { h->nmf_tma = value != 0; return GCCNMF_OK; }
+  if (strcmp(name, "nmf_pdl") == 0) { h->nmf_pdl = value != 0; return GCCNMF_OK; }
   return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
 }
 

@@ -15,6 +15,9 @@ struct gccnmf_handle {
   int64_t launches = 0;
   bool nmf_split_bf16 = true;    // KL-NMF contractions: 0 = 3xTF32 (hi/lo tf32), 1 = 3xBF16 (hi/lo bf16)
   bool force_simt_nmf = false;   // GCCNMF_NMF_PATH=simt: float32 SIMT contractions instead of tcgen05 3xTF32
+  bool nmf_tma = true;           // KL-NMF contractions on the TMA-fed plane GEMM (klnmf_tma.cu); 0 = loader-based kernel (klnmf_tc.cu)
+  bool nmf_pdl = false;          // programmatic dependent launch between the kernels of a KL-NMF iteration
+  struct gccnmf_tmap_cache* tmaps = nullptr;   // TMA tensor maps, keyed by (buffer, shape, box)
   std::string last_error;
   // twiddle tables e^{-2 pi i j / n}, j < n/2, float64 and float32, cached per FFT size
   static constexpr int kMaxPlans = 8;
@@ -76,4 +79,5 @@ struct WorkspaceCarver {
   bool ok() const { return base != nullptr && used <= size; }
 };
 
+void gccnmf_tmap_cache_free(gccnmf_handle* h);
 int gccnmf_get_twiddles(gccnmf_handle* h, int n, const double** tw64, const float** tw32);

@@ -245,7 +245,32 @@ int gccnmf_klnmf_tc_finish(gccnmf_handle* h, int F, int T2, float* H, int K, boo
                            size_t workspace_bytes, void* stream);
 int gccnmf_klnmf_tc_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
 
+// TMA-fed plane GEMM path (klnmf_tma.cu): same protocol
+bool gccnmf_klnmf_tma_supported(int F, int T2, int K);
+size_t gccnmf_klnmf_tma_workspace_bytes(int F, int T2, int K);
+int gccnmf_klnmf_tma_prepare(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
+                             size_t workspace_bytes, bool need_vt, bool need_w, bool need_ht, void* stream);
+int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
+                              void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream);
+int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
+                               size_t workspace_bytes, bool have_rowsum, void* stream);
+int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int gccnmf_klnmf_tma_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
+
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tc_supported(F, T2, K); }
+// The TMA path is the 3xBF16 split over pre-split planes; the 3xTF32 option and shapes it does not cover use the loader-based kernel.
+static bool use_tma(const gccnmf_handle* h, int F, int T2, int K) {
+  return use_tc(h, F, T2, K) && h->nmf_tma && h->nmf_split_bf16 && gccnmf_klnmf_tma_supported(F, T2, K);
+}
+#define gccnmf_klnmf_tc_prepare(h, V, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_prepare(h, V, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_prepare(h, V, F, T2, __VA_ARGS__))
+#define gccnmf_klnmf_tc_update_H(h, V, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_update_H(h, V, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_update_H(h, V, F, T2, __VA_ARGS__))
+#define gccnmf_klnmf_tc_partial_W(h, V, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_partial_W(h, V, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_partial_W(h, V, F, T2, __VA_ARGS__))
+#define gccnmf_klnmf_tc_apply_W(h, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_apply_W(h, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_apply_W(h, F, T2, __VA_ARGS__))
+#define gccnmf_klnmf_tc_finish(h, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_finish(h, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_finish(h, F, T2, __VA_ARGS__))
+#define gccnmf_klnmf_tc_pack_numer(h, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_pack_numer(h, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_pack_numer(h, F, T2, __VA_ARGS__))
 
 extern "C" {
 
@@ -262,6 +287,7 @@ size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K) {
   add(K);
   n = align_up(n, 256);
   if (gccnmf_klnmf_tc_supported(F, T2, K)) n = std::max(n, gccnmf_klnmf_tc_workspace_bytes(F, T2, K));
+  if (gccnmf_klnmf_tma_supported(F, T2, K)) n = std::max(n, gccnmf_klnmf_tma_workspace_bytes(F, T2, K));
   return n;
 }
 

@@ -1,0 +1,723 @@
+// KL-NMF (reference: gccNMF/gccNMFFunctions.py:69-83) on the TMA-fed tcgen05 GEMM over pre-split bf16 planes (tma_gemm.cuh).
+//
+// Every matrix lives in ONE orientation; the four contractions of an iteration pick the UMMA operand layout
+// (K-major / MN-major) that matches it, so nothing is transposed or re-split inside the loop:
+//   W    (F, K)   float32 master (the caller's buffer) + bf16 hi/lo planes Wp (F, K); Wnp = planes of W * pending norms
+//   H^T  (T2, K)  float32 master HT32 + planes HTp          (the caller's H (K, T2) is read once and written once)
+//   V^T  (T2, Fp) float32 (epilogue operand only)
+//   R^T  (T2, Fp) planes RTp only, R = V / (W H)            Fp = F rounded up to 8 (16-byte plane rows)
+//
+// One iteration, reference order (:76-:81); M = accumulator rows (TMEM lanes = the coalesced store direction):
+//   G1  RTp = split(VT / (Wn . H^T))      M = f,    N = t,    over atoms   A = Wnp K-major, B = HTp K-major  (Wn = W * n, see below)
+//   G2  HT32, HTp = (n*H) * (W^T . R) / (colsum(W) + alpha + eps); row-sum partials
+//                                          M = atom, N = t,    over f       A = Wp MN-major,  B = RTp K-major
+//   G3  RTp = split(VT / (W . H^T))       M = f,    N = t,    over atoms   A = Wp K-major,   B = HTp K-major
+//   G4  partial[z] = (R . H^T)^T          M = atom, N = f,    over frames  A = HTp MN-major, B = RTp MN-major, split over z
+//   A   W *= sum_z partial / rowsum(H); unit-L2 atoms; Wp, Wnp, colsum(W), n = norms
+// The rescaling H *= n (:81) is applied lazily: G1 contracts (W * n) with the unscaled H^T -- the W update writes the
+// planes of fl(W * n) next to those of W -- and G2's epilogue multiplies the old H by n (the reference's own float32
+// product), so the 30 MB of H^T are not rewritten every iteration; the last rescale happens in finish().
+// F = 513 = 4 x 128 + 1: the row past the last full 128-row tile of G1 / G3 is computed by SIMT CTAs of the same launch.
+// Tile widths are chosen per contraction so that one wave fills the 148 SMs (G2: 8 x 18 tiles of 128 x 208 = 144 CTAs;
+// G4: 8 x 3 tiles of 128 x 176 x 6 k-splits = 144 CTAs at the headline shape).
+#include <algorithm>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "tma_gemm.cuh"
+
+namespace {
+
+using tgemm::PlaneGemmArgs;
+using tgemm::split_bf16;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kKB = 32;              // k-block: 64-byte K-major rows (SWIZZLE_64B), 32 k-rows per MN-major atom
+constexpr int kTailRowsMax = 8;
+constexpr int kMaxSplits = 8;
+constexpr int kApplyTile = 32;
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t inner, rows, pitch_bytes, plane_bytes;
+  uint32_t box_inner, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && rows == o.rows && pitch_bytes == o.pitch_bytes && plane_bytes == o.plane_bytes &&
+           box_inner == o.box_inner && box_rows == o.box_rows;
+  }
+};
+
+}  // namespace
+
+struct gccnmf_tmap_cache {
+  std::vector<std::pair<TmapKey, CUtensorMap>> entries;
+};
+
+void gccnmf_tmap_cache_free(gccnmf_handle* h) {
+  delete h->tmaps;
+  h->tmaps = nullptr;
+}
+
+namespace {
+
+// Tensor map over a plane pair [2][rows][pitch] of bf16: dims (inner, rows, 2), box (box_inner, box_rows, 2).
+// box_inner * 2 bytes = 64 -> SWIZZLE_64B (K-major k-blocks of 32), 128 -> SWIZZLE_128B (MN-major atoms of 64).
+int get_tmap(gccnmf_handle* h, const bf16* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint64_t plane_elems,
+             uint32_t box_inner, uint32_t box_rows, CUtensorMap* out) {
+  if (!h->tmaps) h->tmaps = new gccnmf_tmap_cache();
+  const TmapKey key{base, inner, rows, pitch_elems * 2, plane_elems * 2, box_inner, box_rows};
+  for (auto& e : h->tmaps->entries)
+    if (e.first == key) { *out = e.second; return 0; }
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) return gccnmf_fail(h, GCCNMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (key.pitch_bytes & 15) || (key.plane_bytes & 15))
+    return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "tensor map: base / pitch / plane stride must be 16-byte aligned");
+  const cuuint64_t dims[3] = {inner, rows, 2};
+  const cuuint64_t strides[2] = {key.pitch_bytes, key.plane_bytes};
+  const cuuint32_t box[3] = {box_inner, box_rows, 2};
+  const cuuint32_t elem_strides[3] = {1, 1, 1};
+  const CUtensorMapSwizzle swz = (box_inner * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap m;
+  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), dims, strides, box, elem_strides,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return gccnmf_fail(h, GCCNMF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  if (h->tmaps->entries.size() > 256) h->tmaps->entries.clear();
+  h->tmaps->entries.emplace_back(key, m);
+  *out = m;
+  return 0;
+}
+
+// K-major operand: rows x kc, k contiguous.
+int tmap_kmajor(gccnmf_handle* h, const bf16* planes, int rows, int kc, int64_t pitch, int64_t plane, int box_rows, CUtensorMap* out) {
+  return get_tmap(h, planes, (uint64_t)kc, (uint64_t)rows, (uint64_t)pitch, (uint64_t)plane, kKB, (uint32_t)box_rows, out);
+}
+// MN-major operand: stored as kc rows x mn contiguous.
+int tmap_mnmajor(gccnmf_handle* h, const bf16* planes, int mn, int kc, int64_t pitch, int64_t plane, CUtensorMap* out) {
+  return get_tmap(h, planes, (uint64_t)mn, (uint64_t)kc, (uint64_t)pitch, (uint64_t)plane, 64, kKB, out);
+}
+
+// ------------------------------------------------------------------------------------------------ launch helper
+template <class... KArgs, class... Args>
+int launch_ex(gccnmf_handle* h, const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, bool pdl,
+              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (err != cudaSuccess) return gccnmf_fail(h, GCCNMF_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(err));
+  h->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+struct EpiStoreT {   // DT[z][n][m] = acc  (lanes run along m: coalesced).  G4 partials (m = atom, n = f) and the test entry.
+  struct State {};
+  float* __restrict__ DT; int64_t ld, slab; int M, N;
+  __device__ void init(State&, int) const {}
+  __device__ void finish(int, int, int, State&) const {}
+  __device__ void elem(int m, int n, float acc, int z) const { DT[(int64_t)z * slab + (int64_t)n * ld + m] = acc; }
+  template <int NC>
+  __device__ void tile(int m, int n0, float (&v)[32], int z, int, State&) const {
+    if (m >= M) return;
+    float* out = DT + (int64_t)z * slab + m;
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (n0 + j < N) out[(int64_t)(n0 + j) * ld] = v[j];
+  }
+};
+
+struct EpiRatioPlanes {   // RT[n][m] = split(VT[n][m] / acc)     G1 / G3 (m = f, n = t)
+  struct State {};
+  const float* __restrict__ VT; bf16* __restrict__ RT; int64_t ld, plane; int M, N;
+  __device__ void init(State&, int) const {}
+  __device__ void finish(int, int, int, State&) const {}
+  __device__ void elem(int m, int n, float acc, int) const {
+    bf16 hi, lo;
+    split_bf16(VT[(int64_t)n * ld + m] / acc, hi, lo);
+    RT[(int64_t)n * ld + m] = hi;
+    RT[plane + (int64_t)n * ld + m] = lo;
+  }
+  template <int NC>
+  __device__ void tile(int m, int n0, float (&v)[32], int, int, State&) const {
+    if (m >= M) return;
+    float vt[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) vt[j] = (n0 + j < N) ? __ldg(VT + (int64_t)(n0 + j) * ld + m) : 1.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if (n0 + j < N) {
+        bf16 hi, lo;
+        split_bf16(vt[j] / v[j], hi, lo);
+        RT[(int64_t)(n0 + j) * ld + m] = hi;
+        RT[plane + (int64_t)(n0 + j) * ld + m] = lo;
+      }
+    }
+  }
+};
+
+// G2 (m = atom, n = frame): new = (old * pending_norm[m]) * (acc / (colsum[m] + alpha + eps))  (:81 then :76).
+// H^T is updated in place (float32 master + planes); the per-row sums of the new H go to rowsum_part[slot][m]
+// (one writer per (slot, m): plain stores, fixed order, no atomics).
+struct EpiUpdateH {
+  struct State { float denom, pn, rsum; };
+  float* __restrict__ HT; bf16* __restrict__ HTp; const float* __restrict__ colsumW; const float* __restrict__ pending;
+  float* __restrict__ rowsum_part; float alpha, eps; int64_t ld, plane; int M, N; int colsum_slots;
+  __device__ void init(State& s, int m) const {
+    s.rsum = 0.f; s.denom = 1.f; s.pn = 1.f;
+    if (m >= M) return;
+    float c = colsumW[m];
+    for (int b = 1; b < colsum_slots; ++b) c += colsumW[(int64_t)b * M + m];   // colsum(W): the W update's per-row-block partials
+    s.denom = (c + alpha) + eps;
+    s.pn = pending ? pending[m] : 1.f;
+  }
+  __device__ void finish(int m, int, int slot, State& s) const {
+    if (m < M) rowsum_part[(int64_t)slot * M + m] = s.rsum;
+  }
+  __device__ void elem(int, int, float, int) const {}   // M = atoms is tiled without SIMT tail rows
+  template <int NC>
+  __device__ void tile(int m, int n0, float (&v)[32], int, int, State& s) const {
+    if (m >= M) return;
+#pragma unroll
+    for (int b = 0; b < NC; b += 16) {     // 16 loads in flight per batch (32 spill)
+      float old[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) old[j] = (n0 + b + j < N) ? HT[(int64_t)(n0 + b + j) * ld + m] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (n0 + b + j < N) {
+          float o = old[j];
+          if (pending) o = o * s.pn;
+          const float hv = o * (v[b + j] / s.denom);
+          bf16 hi, lo;
+          split_bf16(hv, hi, lo);
+          const int64_t i = (int64_t)(n0 + b + j) * ld + m;
+          HT[i] = hv;
+          HTp[i] = hi;
+          HTp[plane + i] = lo;
+          s.rsum += hv;
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// dst32 (cols, ld32) = src (rows, cols; ld_src)^T, zero in the pad columns [rows, ld32); optional hi/lo planes (cols, ldp).
+__global__ void tma_transpose_split_kernel(const float* __restrict__ src, int rows, int cols, int64_t ld_src, float* __restrict__ dst32,
+                                           int64_t ld32, bf16* __restrict__ planes, int64_t ldp, int64_t plane) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(int64_t)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c >= cols) continue;
+    const float x = tile[threadIdx.x][i];
+    if (dst32 && r < ld32) dst32[(int64_t)c * ld32 + r] = x;
+    if (planes && r < ldp) {
+      bf16 hi, lo;
+      split_bf16(x, hi, lo);
+      planes[(int64_t)c * ldp + r] = hi;
+      planes[plane + (int64_t)c * ldp + r] = lo;
+    }
+  }
+}
+
+__global__ void tma_split_kernel(const float* __restrict__ src, int64_t n, bf16* __restrict__ planes, int64_t plane) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bf16 hi, lo;
+  split_bf16(src[i], hi, lo);
+  planes[i] = hi;
+  planes[plane + i] = lo;
+}
+
+// planes (rows, pitch) = split(src (rows, inner)) row by row (pitch >= inner; pad columns are left as they are).
+__global__ void tma_split_rows_kernel(const float* src, int rows, int inner, bf16* planes, int64_t pitch, int64_t plane) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * inner) return;
+  const int r = (int)(i / inner), col = (int)(i - (int64_t)r * inner);
+  bf16 hi, lo;
+  split_bf16(src[i], hi, lo);
+  planes[(int64_t)r * pitch + col] = hi;
+  planes[plane + (int64_t)r * pitch + col] = lo;
+}
+
+__global__ void tma_colsum_kernel(const float* W, int F, int K, float* colsum) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int f = 0; f < F; ++f) s += W[(int64_t)f * K + k];   // row order like numpy.sum(W, axis=0)
+  colsum[k] = s;
+}
+
+// Cross-rank sum read straight from the NVSwitch (see klnmf_tc.cu).
+__device__ __forceinline__ float multimem_sum_f32(const float* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// W update, two fully parallel passes over 32 x 32 tiles (grid: atoms / 32 x rows / 32):
+//   pass 1  W' = W * (sum_z partial[z]) / rowsum(H)  (:77); per-tile column sums of squares -> sumsq_part[row block][atom]
+//   pass 2  norm = sqrt(sum of the row-block partials) (:79); W = W' / norm (:80); planes of W and of W * norm (the lazily
+//           applied H rescale of :81, see the header); per-tile column sums -> colsum_part[row block][atom]; norms[atom]
+template <bool MULTIMEM>
+__global__ void __launch_bounds__(kApplyTile * 8)
+tma_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, int splits, const float* __restrict__ rowsum,
+                    int rowsum_slots, int F, int K, float* __restrict__ sumsq_part) {
+  __shared__ float rs_s[kApplyTile];
+  __shared__ float part[8][kApplyTile + 1];
+  tgemm::pdl_launch_dependents();
+  tgemm::pdl_wait_prior_grids();
+  const int c = threadIdx.x, g = threadIdx.y;
+  const int k = blockIdx.x * kApplyTile + c;
+  const int64_t slab = (int64_t)F * K;
+  if (g == 0) {
+    float rs = 0.f;
+    if (k < K) {
+      if (MULTIMEM) rs = multimem_sum_f32(rowsum + k);
+      else
+        for (int s = 0; s < rowsum_slots; ++s) rs += rowsum[(int64_t)s * K + k];
+    }
+    rs_s[c] = rs;
+  }
+  __syncthreads();
+  float sumsq = 0.f;
+  if (k < K) {
+    const float rs = rs_s[c];
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {
+      const int f = blockIdx.y * kApplyTile + g + 8 * r;
+      if (f < F) {
+        const int64_t i = (int64_t)f * K + k;
+        float numer;
+        if (MULTIMEM) {
+          numer = multimem_sum_f32(partial + i);      // sum over ranks, reduced inside the NVSwitch
+        } else {
+          float p[kMaxSplits];                       // all split partials in flight at once, then summed in split order
+#pragma unroll
+          for (int z = 0; z < kMaxSplits; ++z) p[z] = z < splits ? __ldg(partial + (int64_t)z * slab + i) : 0.f;
+          numer = p[0];
+#pragma unroll
+          for (int z = 1; z < kMaxSplits; ++z)
+            if (z < splits) numer += p[z];
+        }
+        const float w = W[i] * (numer / rs);
+        W[i] = w;
+        sumsq += w * w;
+      }
+    }
+  }
+  part[g][c] = sumsq;
+  __syncthreads();
+  if (g == 0 && k < K) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][c];
+    sumsq_part[(int64_t)blockIdx.y * K + k] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kApplyTile * 8)
+tma_apply_w2_kernel(float* __restrict__ W, bf16* __restrict__ Wp, bf16* __restrict__ Wnp, int64_t plane, const float* __restrict__ sumsq_part,
+                    int row_blocks, int F, int K, float* __restrict__ norms, float* __restrict__ colsum_part) {
+  __shared__ float norm_s[kApplyTile];
+  __shared__ float part[8][kApplyTile + 1];
+  tgemm::pdl_launch_dependents();
+  tgemm::pdl_wait_prior_grids();
+  const int c = threadIdx.x, g = threadIdx.y;
+  const int k = blockIdx.x * kApplyTile + c;
+  if (g == 0) {
+    float s = 0.f;
+    if (k < K)
+      for (int b = 0; b < row_blocks; ++b) s += sumsq_part[(int64_t)b * K + k];
+    const float nrm = sqrtf(s);
+    norm_s[c] = nrm;
+    if (k < K && blockIdx.y == 0) norms[k] = nrm;
+  }
+  __syncthreads();
+  const float nrm = norm_s[c];
+  float csum = 0.f;
+#pragma unroll
+  for (int r = 0; r < kApplyTile / 8; ++r) {
+    const int f = blockIdx.y * kApplyTile + g + 8 * r;
+    if (k < K && f < F) {
+      const int64_t i = (int64_t)f * K + k;
+      const float w = W[i] / nrm;
+      W[i] = w;
+      csum += w;
+      bf16 hi, lo;
+      split_bf16(w, hi, lo);
+      Wp[i] = hi;
+      Wp[plane + i] = lo;
+      split_bf16(w * nrm, hi, lo);
+      Wnp[i] = hi;
+      Wnp[plane + i] = lo;
+    }
+  }
+  part[g][c] = csum;
+  __syncthreads();
+  if (g == 0 && k < K) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][c];
+    colsum_part[(int64_t)blockIdx.y * K + k] = s;
+  }
+}
+
+// H (K, T2; caller) = HT32 (T2, K)^T * norms (pending :81) or a plain transpose.
+__global__ void tma_finish_h_kernel(const float* __restrict__ HT, int T2, int K, const float* __restrict__ norms, float* __restrict__ H) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T2 && k < K) ? HT[(int64_t)t * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, t = t0 + threadIdx.x;
+    if (k < K && t < T2) {
+      const float v = tile[threadIdx.x][i];
+      H[(int64_t)k * T2 + t] = norms ? v * norms[k] : v;
+    }
+  }
+}
+
+// numer = [sum_z partial[z] (F*K) | sum_s rowsum_part[s] (K)] for the cross-rank all-reduce.
+__global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t n, const float* rowsum, int rowsum_slots, int K, float* numer) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float s = partial[i];
+    for (int z = 1; z < splits; ++z) s += partial[(int64_t)z * n + i];
+    numer[i] = s;
+  } else if (i < n + K) {
+    float s = 0.f;
+    for (int j = 0; j < rowsum_slots; ++j) s += rowsum[(int64_t)j * K + (i - n)];
+    numer[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+struct Operand {
+  const bf16* planes;      // hi plane; lo at + plane
+  int64_t pitch, plane;    // elements
+  bool mn_major;           // false: (rows, kc) k contiguous; true: (kc, rows) rows contiguous
+};
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, bool simt_tail,
+                      const Epi& epi, unsigned long long* timing, void* stream) {
+  using C = tgemm::Config<BN, kKB, A_MN, B_MN>;
+  auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, Epi>;
+  static bool configured = false;
+  if (!configured) {
+    GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+    configured = true;
+  }
+  CUtensorMap map_a, map_b;
+  if (int st = A_MN ? tmap_mnmajor(h, A.planes, M, Kc, A.pitch, A.plane, &map_a) : tmap_kmajor(h, A.planes, M, Kc, A.pitch, A.plane, tgemm::kBM, &map_a)) return st;
+  if (int st = B_MN ? tmap_mnmajor(h, B.planes, N, Kc, B.pitch, B.plane, &map_b) : tmap_kmajor(h, B.planes, N, Kc, B.pitch, B.plane, BN, &map_b)) return st;
+  PlaneGemmArgs args{};
+  args.M = M; args.N = N; args.Kc = Kc;
+  const int tail = M % tgemm::kBM;
+  const bool use_tail = simt_tail && !A_MN && !B_MN && tail != 0 && tail <= kTailRowsMax && M > tgemm::kBM;
+  args.m_tiles = use_tail ? M / tgemm::kBM : (M + tgemm::kBM - 1) / tgemm::kBM;
+  const int total_kb = (Kc + kKB - 1) / kKB;
+  args.kblocks_per_split = (total_kb + splits - 1) / splits;
+  args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
+  args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
+  args.timing = timing;
+  const dim3 grid((N + BN - 1) / BN, args.m_tiles + (use_tail ? 1 : 0), splits);
+  return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl, map_a, map_b, args, epi);
+}
+
+template <bool A_MN, bool B_MN, class Epi>
+int plane_gemm(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, bool simt_tail, const Epi& epi,
+               unsigned long long* timing, void* stream) {
+  switch (bn) {
+    case 128: return launch_plane_gemm<128, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream);
+    case 176: return launch_plane_gemm<176, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream);
+    case 208: return launch_plane_gemm<208, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream);
+    case 256: return launch_plane_gemm<256, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream);
+  }
+  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: tile width %d (supported: 128, 176, 208, 256)", bn);
+}
+
+// ------------------------------------------------------------------------------------------------ tile plan
+// Cycles per 16-deep k-step of one CTA: the three UMMAs read 3 x 32 (128 + BN) bytes of shared memory and TMA writes
+// 2 x 32 (128 + BN) through the same 128 B/clk port; the tensor pipe needs 3 BN / 2.
+double kstep_cycles(int bn) { return std::max(160.0 * (128 + bn) / 128.0, 1.5 * bn); }
+double epilogue_cycles(int bn) { return 1500.0 + 20.0 * bn; }
+
+int m_tiles_of(int M, bool simt_tail) {
+  const int tail = M % tgemm::kBM;
+  return (simt_tail && tail != 0 && tail <= kTailRowsMax && M > tgemm::kBM) ? M / tgemm::kBM : (M + tgemm::kBM - 1) / tgemm::kBM;
+}
+
+struct TilePlan { int bn, splits; };
+
+// Picks the tile width (and k-split count when `allow_split`) with the smallest estimated time.
+TilePlan plan_tiles(int sm_count, int m_tiles, int N, int Kc, bool allow_split, const int* widths, int n_widths) {
+  TilePlan best{128, 1};
+  double best_cost = 1e300;
+  const int total_kb = (Kc + kKB - 1) / kKB;
+  for (int i = 0; i < n_widths; ++i) {
+    const int bn = widths[i];
+    const int tiles = m_tiles * ((N + bn - 1) / bn);
+    int splits = 1;
+    if (allow_split) splits = std::max(1, std::min(std::min(kMaxSplits, sm_count / std::max(1, tiles)), total_kb / 4));
+    const int kb = (total_kb + splits - 1) / splits;
+    const int waves = (tiles * splits + sm_count - 1) / sm_count;
+    const double cost = waves * (kb * (kKB / 16) * kstep_cycles(bn) + epilogue_cycles(bn) + 3000.0);
+    if (cost < best_cost) { best_cost = cost; best = TilePlan{bn, splits}; }
+  }
+  return best;
+}
+
+const int kWidthsWH[] = {128, 256};
+const int kWidthsAll[] = {128, 176, 208, 256};
+
+struct Plan {
+  int bn_wh;            // G1 / G3
+  int bn_h;             // G2
+  TilePlan w;           // G4
+  int rowsum_slots;     // 2 x n-tiles of G2
+};
+
+Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
+  Plan p;
+  p.bn_wh = plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 2).bn;
+  p.bn_h = plan_tiles(h->sm_count, m_tiles_of(K, false), T2, F, false, kWidthsAll, 4).bn;
+  p.w = plan_tiles(h->sm_count, m_tiles_of(K, false), F, T2, true, kWidthsAll, 4);
+  p.rowsum_slots = 2 * ((T2 + p.bn_h - 1) / p.bn_h);
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct TmaWorkspace {
+  float *HT, *VT, *partial, *colsum, *sumsq_part, *rowsum_part, *norms;
+  bf16 *HTp, *Wp, *Wnp, *RTp;
+  int64_t Fp, plane_w, plane_ht, plane_rt;
+  int row_blocks;
+  bool ok;
+};
+
+int max_rowsum_slots(int T2) { return 2 * ((T2 + 127) / 128); }
+
+TmaWorkspace tma_carve(void* ws, size_t bytes, int F, int T2, int K) {
+  WorkspaceCarver c(ws, bytes);
+  TmaWorkspace w;
+  w.Fp = (F + 7) & ~7;
+  w.plane_w = (int64_t)F * K;
+  w.plane_ht = (int64_t)T2 * K;
+  w.plane_rt = (int64_t)T2 * w.Fp;
+  w.row_blocks = (F + kApplyTile - 1) / kApplyTile;
+  w.HT = c.take<float>((size_t)T2 * K);
+  w.VT = c.take<float>((size_t)T2 * w.Fp);
+  w.partial = c.take<float>((size_t)kMaxSplits * F * K);
+  w.colsum = c.take<float>((size_t)w.row_blocks * K);
+  w.sumsq_part = c.take<float>((size_t)w.row_blocks * K);
+  w.rowsum_part = c.take<float>((size_t)max_rowsum_slots(T2) * K);
+  w.norms = c.take<float>(K);
+  w.HTp = c.take<bf16>((size_t)2 * w.plane_ht);
+  w.Wp = c.take<bf16>((size_t)2 * w.plane_w);
+  w.Wnp = c.take<bf16>((size_t)2 * w.plane_w);
+  w.RTp = c.take<bf16>((size_t)2 * w.plane_rt);
+  w.ok = c.ok();
+  return w;
+}
+
+size_t tma_workspace_bytes(int F, int T2, int K) {
+  const size_t Fp = (F + 7) & ~7;
+  size_t n = 0;
+  auto add = [&](size_t bytes) { n = align_up(n, 256) + bytes; };
+  add((size_t)T2 * K * 4); add((size_t)T2 * Fp * 4); add((size_t)kMaxSplits * F * K * 4);
+  add((size_t)((F + 31) / 32) * K * 4); add((size_t)((F + 31) / 32) * K * 4);
+  add((size_t)max_rowsum_slots(T2) * K * 4); add((size_t)K * 4);
+  add((size_t)2 * T2 * K * 2); add((size_t)2 * F * K * 2); add((size_t)2 * F * K * 2); add((size_t)2 * T2 * Fp * 2);
+  return align_up(n, 256);
+}
+
+#define TMA_CARVE_OR_FAIL(w)                                                                                        \
+  TmaWorkspace w = tma_carve(workspace, workspace_bytes, F, T2, K);                                                 \
+  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf (TMA tensor-core path) workspace too small: need %zu bytes", tma_workspace_bytes(F, T2, K))
+
+}  // namespace
+
+// Whether the TMA path supports this problem (else the loader-based path in klnmf_tc.cu / the SIMT path is used).
+bool gccnmf_klnmf_tma_supported(int F, int T2, int K) { return K % 8 == 0 && F >= 128 && T2 >= 128 && K >= 32; }
+size_t gccnmf_klnmf_tma_workspace_bytes(int F, int T2, int K) { return tma_workspace_bytes(F, T2, K); }
+
+// Builds the operand set from the caller's V, W, H: V^T, planes of W, H^T (float32 + planes).
+int gccnmf_klnmf_tma_prepare(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
+                             void* workspace, size_t workspace_bytes, bool need_vt, bool need_w, bool need_ht, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  const dim3 block(32, 8);
+  if (need_vt)
+    GCCNMF_LAUNCH(h, tma_transpose_split_kernel, dim3((T2 + 31) / 32, (int)((w.Fp + 31) / 32)), block, 0, stream, V, F, T2, (int64_t)T2, w.VT, w.Fp,
+                  (bf16*)nullptr, (int64_t)0, (int64_t)0);
+  if (need_w) {
+    const int64_t n = (int64_t)F * K;
+    GCCNMF_LAUNCH(h, tma_split_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, W, n, w.Wp, w.plane_w);
+  }
+  if (need_ht)
+    GCCNMF_LAUNCH(h, tma_transpose_split_kernel, dim3((T2 + 31) / 32, (K + 31) / 32), block, 0, stream, H, K, T2, (int64_t)T2, w.HT, (int64_t)K,
+                  w.HTp, (int64_t)K, w.plane_ht);
+  return 0;
+}
+
+// :76 (preceded by the pending :81 when pending_norms): H = (n*H) * (W^T (V / (W (n*H)))) / (colsum(W) + alpha + eps).
+int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
+                              void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream) {
+  // colsum_state: 0 = compute colsum(W) now; 1 = reuse the one computed before (fixed dictionary); 2 = per-row-block partials left by the W update
+  TMA_CARVE_OR_FAIL(w);
+  (void)V; (void)H;
+  const Plan p = make_plan(h, F, T2, K);
+  const Operand Wk{pending_norms ? w.Wnp : w.Wp, (int64_t)K, w.plane_w, false};
+  const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
+  {  // G1: RT = split(VT / (Wn . H^T))
+    EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2};
+    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream)) return st;
+  }
+  if (colsum_state == 0) GCCNMF_LAUNCH(h, tma_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
+  {  // G2: HT32, HTp = (n*H) * (W^T . R) / denom
+    const Operand Wmn{w.Wp, (int64_t)K, w.plane_w, true};
+    const Operand RTk{w.RTp, w.Fp, w.plane_rt, false};
+    EpiUpdateH e{w.HT, w.HTp, w.colsum, pending_norms ? w.norms : nullptr, w.rowsum_part, alpha, eps, (int64_t)K, w.plane_ht, K, T2,
+                 colsum_state == 2 ? w.row_blocks : 1};
+    if (int st = plane_gemm<true, false>(h, p.bn_h, Wmn, RTk, K, T2, F, 1, false, e, nullptr, stream)) return st;
+  }
+  return 0;
+}
+
+// :77 numerator: partial[z] = (V / (W H)) . H^T over the frame range of split z (row sums of H come from update_H).
+int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
+                               void* workspace, size_t workspace_bytes, bool have_rowsum, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  (void)V; (void)W; (void)H;
+  if (!have_rowsum) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf (TMA path): partial_W needs the row sums left by update_H");
+  const Plan p = make_plan(h, F, T2, K);
+  {  // G3: RT = split(VT / (W . H^T))
+    const Operand Wk{w.Wp, (int64_t)K, w.plane_w, false};
+    const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
+    EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2};
+    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream)) return st;
+  }
+  {  // G4: partial[z][f][atom] = sum_t H^T[t][atom] R^T[t][f]
+    const Operand HTmn{w.HTp, (int64_t)K, w.plane_ht, true};
+    const Operand RTmn{w.RTp, w.Fp, w.plane_rt, true};
+    EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F};
+    if (int st = plane_gemm<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, false, e, nullptr, stream)) return st;
+  }
+  return 0;
+}
+
+// :77-:80; the H rescale of :81 stays pending (applied by the next update_H, or by finish).  Numerator and row
+// sums come from `numer` (F*K + K floats, all-reduced across ranks) when given, else from this rank's partials.
+int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  const Plan p = make_plan(h, F, T2, K);
+  const float* partial = numer ? numer : w.partial;
+  const float* rowsum = numer ? numer + (int64_t)F * K : w.rowsum_part;
+  const dim3 grid((K + kApplyTile - 1) / kApplyTile, w.row_blocks), block(kApplyTile, 8);
+  if (numer_is_multicast) {
+    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<true>, grid, block, 0, stream, h->nmf_pdl, W, partial, 1, rowsum, 1, F, K,
+                           w.sumsq_part)) return st;
+  } else {
+    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<false>, grid, block, 0, stream, h->nmf_pdl, W, partial,
+                           numer ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part)) return st;
+  }
+  return launch_ex(h, "tma_apply_w2_kernel", tma_apply_w2_kernel, grid, block, 0, stream, h->nmf_pdl, W, w.Wp, w.Wnp, w.plane_w,
+                   (const float*)w.sumsq_part, w.row_blocks, F, K, w.norms, w.colsum);
+}
+
+// Writes the caller's H from H^T, applying a pending H *= norms (:81) when there is one.
+int gccnmf_klnmf_tma_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  GCCNMF_LAUNCH(h, tma_finish_h_kernel, dim3((K + 31) / 32, (T2 + 31) / 32), dim3(32, 8), 0, stream, w.HT, T2, K,
+                pending_norms ? w.norms : (const float*)nullptr, H);
+  return 0;
+}
+
+int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  const Plan p = make_plan(h, F, T2, K);
+  const int64_t n = (int64_t)F * K;
+  GCCNMF_LAUNCH(h, tma_pack_numer_kernel, (unsigned)((n + K + 255) / 256), 256, 0, stream, w.partial, p.w.splits, n, w.rowsum_part,
+                p.rowsum_slots, K, numer);
+  return 0;
+}
+
+extern "C" {
+
+size_t gccnmf_gemm_planes_workspace_bytes(int M, int N, int Kc) {
+  auto pad8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+  const size_t a = std::max((size_t)M * pad8(Kc), (size_t)Kc * pad8(M)), b = std::max((size_t)N * pad8(Kc), (size_t)Kc * pad8(N));
+  return align_up(2 * a * 2, 256) + align_up(2 * b * 2, 256) + 512;
+}
+
+// Test / diagnostics entry of the TMA plane GEMM: DT (N, M) row-major = (A . B^T)^T.
+//   a_mn_major = 0: A is (M, Kc) row-major;  1: A is (Kc, M) row-major (m contiguous).  Same for B with N.
+// The float32 operands are split into bf16 hi/lo planes in the workspace first.  tile_n in {128, 176, 208, 256};
+// splits > 1 writes `splits` partial slabs DT[z] (N * M floats each).  timing: 6 clock64 stamps per CTA, or NULL.
+int gccnmf_gemm_planes(gccnmf_handle* h, const float* A, int a_mn_major, const float* B, int b_mn_major, float* DT, int M, int N, int Kc,
+                       int tile_n, int splits, void* workspace, size_t workspace_bytes, unsigned long long* timing, void* stream) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_REQUIRE(h, A && B && DT && M > 0 && N > 0 && Kc > 0 && splits >= 1 && splits <= kMaxSplits, "gemm_planes: bad arguments");
+  if (!workspace || workspace_bytes < gccnmf_gemm_planes_workspace_bytes(M, N, Kc))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "gemm_planes workspace too small: need %zu bytes", gccnmf_gemm_planes_workspace_bytes(M, N, Kc));
+  WorkspaceCarver c(workspace, workspace_bytes);
+  // planes keep the operand's own orientation: rows x pitch with pitch = inner extent rounded up to 8
+  const int a_rows = a_mn_major ? Kc : M, a_inner = a_mn_major ? M : Kc;
+  const int b_rows = b_mn_major ? Kc : N, b_inner = b_mn_major ? N : Kc;
+  const int64_t a_pitch = (a_inner + 7) & ~7, b_pitch = (b_inner + 7) & ~7;
+  bf16* Ap = c.take<bf16>((size_t)2 * a_rows * a_pitch);
+  bf16* Bp = c.take<bf16>((size_t)2 * b_rows * b_pitch);
+  if (!c.ok()) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "gemm_planes workspace too small");
+  GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(Ap, 0, (size_t)2 * a_rows * a_pitch * 2, (cudaStream_t)stream));
+  GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(Bp, 0, (size_t)2 * b_rows * b_pitch * 2, (cudaStream_t)stream));
+  const int64_t na = (int64_t)a_rows * a_inner, nb = (int64_t)b_rows * b_inner;
+  GCCNMF_LAUNCH(h, tma_split_rows_kernel, (unsigned)((na + 255) / 256), 256, 0, stream, A, a_rows, a_inner, Ap, a_pitch, (int64_t)a_rows * a_pitch);
+  GCCNMF_LAUNCH(h, tma_split_rows_kernel, (unsigned)((nb + 255) / 256), 256, 0, stream, B, b_rows, b_inner, Bp, b_pitch, (int64_t)b_rows * b_pitch);
+  const Operand Ao{Ap, a_pitch, (int64_t)a_rows * a_pitch, a_mn_major != 0};
+  const Operand Bo{Bp, b_pitch, (int64_t)b_rows * b_pitch, b_mn_major != 0};
+  EpiStoreT e{DT, (int64_t)M, (int64_t)N * M, M, N};
+  if (!a_mn_major && !b_mn_major) return plane_gemm<false, false>(h, tile_n, Ao, Bo, M, N, Kc, splits, true, e, timing, stream);
+  if (a_mn_major && !b_mn_major) return plane_gemm<true, false>(h, tile_n, Ao, Bo, M, N, Kc, splits, false, e, timing, stream);
+  if (a_mn_major && b_mn_major) return plane_gemm<true, true>(h, tile_n, Ao, Bo, M, N, Kc, splits, false, e, timing, stream);
+  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "gemm_planes: A K-major with B MN-major is not instantiated");
+}
+
+}  // extern "C"

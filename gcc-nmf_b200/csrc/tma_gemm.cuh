@@ -1,0 +1,318 @@
+// TMA-fed 3xBF16 GEMM over pre-split operand planes on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+//   D[m, n] = sum_k A(m, k) * B(n, k)        A = A_hi + A_lo, B = B_hi + B_lo   (bf16 planes, hi = bf16(x), lo = bf16(x - hi))
+//
+// Each operand lives in global memory as TWO bf16 planes [2][rows][pitch] written by the kernel that produced it
+// (the KL-NMF epilogues / the W update), in ONE orientation; the contraction picks the matching shared-memory layout:
+//   K-major  : element (r, k) at rows r, k contiguous        TMA box {KB, rows, 2}   UMMA descriptor K-major
+//   MN-major : element (r, k) at rows k, r contiguous        TMA boxes {64, KB, 2}   UMMA descriptor MN-major, SWIZZLE_128B
+// so no matrix is ever transposed or re-split inside the loop (the loader-based kernel in umma_gemm.cuh converted
+// float32 operands on the fly: 32 KB of L2->SM traffic and 32 KB of shared-memory stores per k-block per CTA, its limiter).
+// Three tcgen05.mma.kind::f16 products per 16-deep k-step (lo.hi + hi.lo + hi.hi) accumulate in float32 TMEM.
+//
+// CTA = one 128 x BN accumulator tile, 10 warps:
+//   warp 0     lane 0 is the TMA producer: waits empty[s], arms full[s] with the stage's byte count, issues the boxes
+//   warp 1     allocates TMEM; lane 0 issues every tcgen05.mma and tcgen05.commit (-> empty[s], accum_full)
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> functor; warp w reads TMEM lane quarter w % 4
+// Rows past the last full 128-row tile (F = 513 = 4 x 128 + 1) are computed by extra SIMT CTAs of the same launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "umma_gemm.cuh"
+
+namespace tgemm {
+
+using umma::mbar_init;
+using umma::mbar_wait;
+using umma::smem_u32;
+
+constexpr int kBM = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kSmemBudget = 225 * 1024;   // stages; + barriers + alignment slack stays under the 227 KB per-CTA limit
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// One 3-D box (inner, rows, planes) -> shared memory; completion is signalled on `bar` as transaction bytes.
+// Coordinates outside the tensor are zero-filled (and still counted in the transaction bytes).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// Programmatic dependent launch: both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 at bit 16 | SBO >> 4 at bit 32 |
+// version 1 at bit 46 | layout type at bit 61 (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// hi = bf16(x) (round to nearest even), lo = bf16(x - hi): x = hi + lo up to 2^-17 |x|.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+struct PlaneGemmArgs {
+  int M, N, Kc;
+  int m_tiles;             // 128-row tiles on the tensor cores; blockIdx.y == m_tiles -> SIMT tail rows [128 m_tiles, M)
+  int kblocks_per_split;   // k-blocks of KB handled by one blockIdx.z
+  // SIMT tail rows (both operands K-major only): element (r, k) of plane p at ptr[p * plane + r * ld + k]
+  const __nv_bfloat16* A; int64_t a_plane, lda;
+  const __nv_bfloat16* B; int64_t b_plane, ldb;
+  unsigned long long* timing;   // optional diagnostics: 6 clock64 stamps per tensor-core CTA, or NULL
+};
+
+template <int BN, int KB, bool A_MN, bool B_MN>
+struct Config {
+  static_assert(KB == 32 || KB == 64, "k-block of 32 (SWIZZLE_64B K-major rows) or 64 (SWIZZLE_128B)");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
+  static constexpr int kAAtoms = kBM / 64;
+  static constexpr int kBAtoms = (BN + 63) / 64;
+  static constexpr int kAtomBytes = 2 * KB * 128;                 // one MN-major atom: 64 elements x KB k-rows x 2 planes
+  static constexpr int kABytes = 2 * kBM * KB * 2;                // both layouts: 512 KB
+  static constexpr int kBBytes = B_MN ? kBAtoms * kAtomBytes : 2 * BN * KB * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "operand blocks must keep 1024-byte alignment");
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static_assert(kStages >= 2, "tile too large for a 2-stage pipeline");
+  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;   // + alignment slack
+  // K-major rows: KB bf16 = 64 B (SWIZZLE_64B, 8-row groups of 512 B) or 128 B (SWIZZLE_128B, groups of 1024 B)
+  static constexpr uint32_t kKRowBytes = KB * 2;
+  static constexpr uint32_t kKLayout = (KB == 32) ? 4u : 2u;
+  static constexpr uint32_t kKSbo = 8 * kKRowBytes;
+  // epilogue: the two warps of a TMEM lane quarter split the BN columns at a multiple of 16
+  static constexpr int kCols0 = ((BN / 2 + 15) / 16) * 16;
+};
+
+// D = f32, A = B = bf16 (kind::f16), M = 128; bit 15 / 16: A / B is MN-major.
+__host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(kBM >> 4) << 24);
+}
+
+// Epilogue concept (functors in klnmf_tma.cu):
+//   struct State;  __device__ void init(State&, int m) const;          m = the thread's accumulator row
+//   template <int NC> __device__ void tile(int m, int n0, float (&v)[32], int z, int slot, State&) const;
+//       the thread holds D[m][n0 .. n0 + NC), NC = 32 or 16; called in increasing n0 over the warp's column range;
+//       slot = 2 * tile_n + column half (for per-CTA partial outputs)
+//   __device__ void finish(int m, int z, int slot, State&) const;      after the warp's last chunk
+//   __device__ void elem(int m, int n, float acc, int z) const;        SIMT tail rows
+template <int BN, int KB, bool A_MN, bool B_MN, class Epilogue>
+__global__ void __launch_bounds__(kThreads, 1)
+plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, PlaneGemmArgs args, Epilogue epi) {
+  using C = Config<BN, KB, A_MN, B_MN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y, z = blockIdx.z;
+  const int n0 = tile_n * BN;
+  const int total_kblocks = (args.Kc + KB - 1) / KB;
+  const int kb_begin = z * args.kblocks_per_split;
+  const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
+  const int num_kb = max(0, kb_end - kb_begin);
+
+  if (tile_m >= args.m_tiles) {
+    // ---------------------------------------------------------------- SIMT tail rows (K-major planes; runs on SMs the tile grid leaves idle)
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();
+    const int k_begin = kb_begin * KB, k_end = min(args.Kc, kb_end * KB);
+    for (int m = args.m_tiles * kBM; m < args.M; ++m) {
+      const __nv_bfloat16* a_hi = args.A + (int64_t)m * args.lda;
+      const __nv_bfloat16* a_lo = a_hi + args.a_plane;
+      for (int n = n0 + warp; n < min(args.N, n0 + BN); n += kThreads / 32) {
+        const __nv_bfloat16* b_hi = args.B + (int64_t)n * args.ldb;
+        const __nv_bfloat16* b_lo = b_hi + args.b_plane;
+        float acc = 0.f;
+        for (int k = k_begin + 2 * lane; k < k_end; k += 64) {     // pitches are multiples of 8 and pad columns hold zeros
+          const float2 ah = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a_hi + k));
+          const float2 al = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a_lo + k));
+          const float2 bh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b_hi + k));
+          const float2 bl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b_lo + k));
+          acc = fmaf(ah.x + al.x, bh.x + bl.x, acc);
+          if (k + 1 < k_end) acc = fmaf(ah.y + al.y, bh.y + bl.y, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) epi.elem(m, n, acc, z);
+      }
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + C::kStages;      // [kStages]  tcgen05.commit -> TMA
+  uint64_t* accum_full = bars + 2 * C::kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
+  const int m0 = tile_m * kBM;
+
+  const int cta_linear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (args.timing && tid == 0) args.timing[cta_linear * 6 + 0] = clock64();
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    umma::fence_barrier_init();
+    tma_prefetch_descriptor(&map_a);
+    tma_prefetch_descriptor(&map_b);
+  }
+  if (warp == 1) umma::tmem_alloc(smem_u32(tmem_base_slot), C::kTmemCols);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_slot;
+  // Everything above overlaps the previous kernel's tail under programmatic dependent launch; nothing below may
+  // touch global memory before the prior grids have completed.
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::kStages;
+        const uint32_t use = i / C::kStages;
+        if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // the MMAs that read this stage have retired
+        const uint32_t bar = smem_u32(&full[s]);
+        mbar_arrive_expect_tx(bar, C::kStageBytes);
+        const uint32_t a_dst = smem_u32(smem + (size_t)s * C::kStageBytes), b_dst = a_dst + C::kABytes;
+        const int k0 = (kb_begin + i) * KB;
+        if (A_MN) {
+#pragma unroll
+          for (int a = 0; a < C::kAAtoms; ++a) tma_load_3d(a_dst + a * C::kAtomBytes, &map_a, bar, m0 + 64 * a, k0, 0);
+        } else {
+          tma_load_3d(a_dst, &map_a, bar, k0, m0, 0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int a = 0; a < C::kBAtoms; ++a) tma_load_3d(b_dst + a * C::kAtomBytes, &map_b, bar, n0 + 64 * a, k0, 0);
+        } else {
+          tma_load_3d(b_dst, &map_b, bar, k0, n0, 0);
+        }
+      }
+      if (args.timing) args.timing[cta_linear * 6 + 3] = clock64();   // producer done issuing
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+      // plane offsets inside an operand block and the per-k16 start-address advance
+      constexpr uint32_t a_lo_off = A_MN ? KB * 128 : kBM * KB * 2;
+      constexpr uint32_t b_lo_off = B_MN ? KB * 128 : BN * KB * 2;
+      constexpr uint32_t a_step = A_MN ? 2048u : 32u, b_step = B_MN ? 2048u : 32u;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::kStages;
+        mbar_wait(smem_u32(&full[s]), (i / C::kStages) & 1);
+        umma::tc_fence_after_sync();
+        if (args.timing && i == 0) args.timing[cta_linear * 6 + 1] = clock64();
+        const uint32_t a_base = smem_u32(smem + (size_t)s * C::kStageBytes), b_base = a_base + C::kABytes;
+        const int k_left = args.Kc - (kb_begin + i) * KB;
+        const int steps = min(KB / 16, (k_left + 15) / 16);              // the k tail issues only the 16-deep steps that hold data
+#pragma unroll
+        for (int kk = 0; kk < KB / 16; ++kk) {
+          if (kk < steps) {
+            const uint32_t a_addr = a_base + kk * a_step, b_addr = b_base + kk * b_step;
+            const uint64_t a_hi = A_MN ? make_desc(a_addr, C::kAtomBytes, 1024, 2) : make_desc(a_addr, 16, C::kKSbo, C::kKLayout);
+            const uint64_t a_lo = A_MN ? make_desc(a_addr + a_lo_off, C::kAtomBytes, 1024, 2) : make_desc(a_addr + a_lo_off, 16, C::kKSbo, C::kKLayout);
+            const uint64_t b_hi = B_MN ? make_desc(b_addr, C::kAtomBytes, 1024, 2) : make_desc(b_addr, 16, C::kKSbo, C::kKLayout);
+            const uint64_t b_lo = B_MN ? make_desc(b_addr + b_lo_off, C::kAtomBytes, 1024, 2) : make_desc(b_addr + b_lo_off, 16, C::kKSbo, C::kKLayout);
+            umma::mma_bf16(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
+            umma::mma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+            umma::mma_bf16(tmem_base, a_hi, b_hi, idesc, 1);
+          }
+        }
+        umma::mma_commit(smem_u32(&empty[s]));      // stage reusable once these MMAs retire
+      }
+      if (num_kb > 0) umma::mma_commit(smem_u32(accum_full));
+      if (args.timing) args.timing[cta_linear * 6 + 2] = clock64();
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int e = warp - 2;
+    const int quarter = warp & 3;                        // TMEM lanes 32 (warp % 4) .. + 31 are the ones this warp may read
+    const int half = e >> 2;
+    const int col0 = half ? C::kCols0 : 0;
+    const int ncols = half ? BN - C::kCols0 : C::kCols0;
+    const int m = m0 + quarter * 32 + lane;
+    const int slot = tile_n * 2 + half;
+    typename Epilogue::State st;
+    epi.init(st, m);
+    if (num_kb > 0) {
+      mbar_wait(smem_u32(accum_full), 0);   // every MMA has retired: accumulator complete
+      umma::tc_fence_after_sync();
+      if (args.timing && tid == 64) args.timing[cta_linear * 6 + 4] = clock64();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+    float v[32];
+    int c = 0;
+#pragma unroll 1
+    for (; c + 32 <= ncols; c += 32) {
+      if (num_kb > 0) {
+        umma::tmem_ld_32x32(taddr + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      epi.template tile<32>(m, n0 + col0 + c, v, z, slot, st);
+    }
+    if (c < ncols) {   // 16-column remainder (BN = 176, 208)
+      if (num_kb > 0) {
+        tmem_ld_32x16(taddr + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      epi.template tile<16>(m, n0 + col0 + c, v, z, slot, st);
+    }
+    epi.finish(m, z, slot, st);
+    if (args.timing && tid == 64) args.timing[cta_linear * 6 + 5] = clock64();
+    umma::tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    umma::tc_fence_after_sync();
+    umma::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace tgemm

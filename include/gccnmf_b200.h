@@ -232,6 +232,21 @@ GCCNMF_API int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int
                                 float* D, int64_t ldd, int M, int N, int Kc, int tile_n,
                                 unsigned long long* timing, void* stream);
 
+/*
+ * The building block the KL-NMF loop runs on (klnmf_tma.cu): the same 3-product contraction, TMA-fed, over operands
+ * that are pre-split into bf16 hi/lo planes and kept in ONE orientation each; an operand contracted over its
+ * non-contiguous dimension is consumed MN-major.  Test / diagnostics entry: splits the float32 operands into planes
+ * in the workspace, then DT (N, M) row-major = (A . B^T)^T.
+ *   a_mn_major = 0: A is (M, Kc) row-major;  1: A is (Kc, M) row-major.   b_mn_major likewise with N.
+ *   tile_n in {128, 176, 208, 256};  splits > 1: `splits` partial slabs DT[z] over k ranges (N * M floats each).
+ *   timing: device uint64[6 x CTAs] clock64 stamps (start, first stage full, last MMA issued, producer done,
+ *   accumulator complete, epilogue end) or NULL.
+ */
+GCCNMF_API size_t gccnmf_gemm_planes_workspace_bytes(int M, int N, int Kc);
+GCCNMF_API int gccnmf_gemm_planes(gccnmf_handle* h, const float* A, int a_mn_major, const float* B, int b_mn_major, float* DT,
+                       int M, int N, int Kc, int tile_n, int splits, void* workspace, size_t workspace_bytes,
+                       unsigned long long* timing, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
