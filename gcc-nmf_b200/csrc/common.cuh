@@ -17,6 +17,9 @@ struct gccnmf_handle {
   bool force_simt_nmf = false;   // GCCNMF_NMF_PATH=simt: float32 SIMT contractions instead of tcgen05 3xTF32
   bool nmf_tma = true;           // KL-NMF contractions on the TMA-fed plane GEMM (klnmf_tma.cu); 0 = loader-based kernel (klnmf_tc.cu)
   bool nmf_pdl = false;          // programmatic dependent launch between the kernels of a KL-NMF iteration
+  bool gemm_m_fastest = false;   // plane GEMM grid order (diagnostics): m tiles vary fastest
+  unsigned long long* debug_timing = nullptr;   // diagnostics (gccnmf_debug_timing): CTA stamps of every plane GEMM
+  size_t debug_timing_cursor = 0;
   struct gccnmf_tmap_cache* tmaps = nullptr;   // TMA tensor maps, keyed by (buffer, shape, box)
   std::string last_error;
   // twiddle tables e^{-2 pi i j / n}, j < n/2, float64 and float32, cached per FFT size

@@ -457,7 +457,13 @@ int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int 
   args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
   args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
   args.timing = timing;
-  const dim3 grid((N + BN - 1) / BN, args.m_tiles + (use_tail ? 1 : 0), splits);
+  if (!timing && h->debug_timing) {   // diagnostics: every plane GEMM of the KL-NMF loop appends its CTA stamps (8 per CTA)
+    args.timing = h->debug_timing + h->debug_timing_cursor;
+  }
+  args.m_fastest = h->gemm_m_fastest ? 1 : 0;
+  const int n_tiles = (N + BN - 1) / BN, m_rows = args.m_tiles + (use_tail ? 1 : 0);
+  const dim3 grid(args.m_fastest ? m_rows : n_tiles, args.m_fastest ? n_tiles : m_rows, splits);
+  if (!timing && h->debug_timing) h->debug_timing_cursor += (size_t)grid.x * grid.y * grid.z * 8;
   return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl, map_a, map_b, args, epi);
 }
 
@@ -681,6 +687,16 @@ int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* n
 }
 
 extern "C" {
+
+// Diagnostics: while `stamps` is non-NULL every plane GEMM launched through this handle appends 8 uint64 per CTA
+// (see tma_gemm.cuh) at a running offset; returns the offset (in uint64) reached so far and resets it when asked.
+int64_t gccnmf_debug_timing(gccnmf_handle* h, unsigned long long* stamps, int reset) {
+  if (!h) return -1;
+  const int64_t reached = (int64_t)h->debug_timing_cursor;
+  h->debug_timing = stamps;
+  if (reset) h->debug_timing_cursor = 0;
+  return reached;
+}
 
 size_t gccnmf_gemm_planes_workspace_bytes(int M, int N, int Kc) {
   auto pad8 = [](size_t x) { return (x + 7) & ~(size_t)7; };

@@ -49,6 +49,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 // Programmatic dependent launch: both are no-ops for a kernel launched without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -85,6 +90,17 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// 8 consecutive elements of a plane pair (one 16-byte load per plane) as floats hi + lo.
+__device__ __forceinline__ void load_planes8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float (&out)[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi)), l = __ldg(reinterpret_cast<const uint4*>(lo));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    out[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+  }
+}
+
 struct PlaneGemmArgs {
   int M, N, Kc;
   int m_tiles;             // 128-row tiles on the tensor cores; blockIdx.y == m_tiles -> SIMT tail rows [128 m_tiles, M)
@@ -92,7 +108,9 @@ struct PlaneGemmArgs {
   // SIMT tail rows (both operands K-major only): element (r, k) of plane p at ptr[p * plane + r * ld + k]
   const __nv_bfloat16* A; int64_t a_plane, lda;
   const __nv_bfloat16* B; int64_t b_plane, ldb;
-  unsigned long long* timing;   // optional diagnostics: 6 clock64 stamps per tensor-core CTA, or NULL
+  unsigned long long* timing;   // optional diagnostics, 8 slots per CTA: [0] / [7] globaltimer (ns) at CTA start / end (tail CTAs too),
+                                // [1..6] clock64: start, first stage full, last MMA issued, producer done, accumulator complete, epilogue end
+  int m_fastest;           // 0: grid (n tiles, m tiles + tail, splits); 1: grid (m tiles + tail, n tiles, splits) -- the CTAs sharing a B block are co-scheduled
 };
 
 template <int BN, int KB, bool A_MN, bool B_MN>
@@ -141,7 +159,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y, z = blockIdx.z;
+  const int tile_n = args.m_fastest ? blockIdx.y : blockIdx.x, tile_m = args.m_fastest ? blockIdx.x : blockIdx.y, z = blockIdx.z;
   const int n0 = tile_n * BN;
   const int total_kblocks = (args.Kc + KB - 1) / KB;
   const int kb_begin = z * args.kblocks_per_split;
@@ -150,27 +168,43 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (tile_m >= args.m_tiles) {
     // ---------------------------------------------------------------- SIMT tail rows (K-major planes; runs on SMs the tile grid leaves idle)
+    const int cta_tail = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (args.timing && tid == 0) args.timing[cta_tail * 8 + 0] = globaltimer_ns();
     pdl_launch_dependents();
     pdl_wait_prior_grids();
+    // One accumulator row x BN columns x the split's k range: each warp takes two columns at a time, each lane 8 consecutive
+    // k per 16-byte load (hi and lo plane), four k-chunks in flight -- 24 independent loads per thread, so the whole tail
+    // costs a few L2 round trips (a scalar version of this loop took 3 x as long as the tensor-core tiles it runs beside).
     const int k_begin = kb_begin * KB, k_end = min(args.Kc, kb_end * KB);
+    const int n_end = min(args.N, n0 + BN);
     for (int m = args.m_tiles * kBM; m < args.M; ++m) {
       const __nv_bfloat16* a_hi = args.A + (int64_t)m * args.lda;
       const __nv_bfloat16* a_lo = a_hi + args.a_plane;
-      for (int n = n0 + warp; n < min(args.N, n0 + BN); n += kThreads / 32) {
+      for (int n = n0 + 2 * warp; n < n_end; n += 2 * (kThreads / 32)) {
+        const bool two = n + 1 < n_end;
         const __nv_bfloat16* b_hi = args.B + (int64_t)n * args.ldb;
         const __nv_bfloat16* b_lo = b_hi + args.b_plane;
-        float acc = 0.f;
-        for (int k = k_begin + 2 * lane; k < k_end; k += 64) {     // pitches are multiples of 8 and pad columns hold zeros
-          const float2 ah = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a_hi + k));
-          const float2 al = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a_lo + k));
-          const float2 bh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b_hi + k));
-          const float2 bl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b_lo + k));
-          acc = fmaf(ah.x + al.x, bh.x + bl.x, acc);
-          if (k + 1 < k_end) acc = fmaf(ah.y + al.y, bh.y + bl.y, acc);
+        const int64_t next = two ? args.ldb : 0;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+        for (int k = k_begin + 8 * lane; k < k_end; k += 256) {     // pitches are multiples of 8; pad columns hold zeros
+          float a[8], b0[8], b1[8];
+          load_planes8(a_hi + k, a_lo + k, a);
+          load_planes8(b_hi + k, b_lo + k, b0);
+          load_planes8(b_hi + next + k, b_lo + next + k, b1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc0 = fmaf(a[j], b0[j], acc0); acc1 = fmaf(a[j], b1[j], acc1); }
         }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) epi.elem(m, n, acc, z);
+        for (int o = 16; o > 0; o >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
+        if (lane == 0) {
+          epi.elem(m, n, acc0, z);
+          if (two) epi.elem(m, n + 1, acc1, z);
+        }
       }
+    }
+    if (args.timing) {
+      __syncthreads();
+      if (tid == 0) args.timing[cta_tail * 8 + 7] = globaltimer_ns();
     }
     return;
   }
@@ -183,7 +217,10 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int m0 = tile_m * kBM;
 
   const int cta_linear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  if (args.timing && tid == 0) args.timing[cta_linear * 6 + 0] = clock64();
+  if (args.timing && tid == 0) {
+    args.timing[cta_linear * 8 + 0] = globaltimer_ns();
+    args.timing[cta_linear * 8 + 1] = clock64();
+  }
   if (tid == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
@@ -228,7 +265,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           tma_load_3d(b_dst, &map_b, bar, k0, n0, 0);
         }
       }
-      if (args.timing) args.timing[cta_linear * 6 + 3] = clock64();   // producer done issuing
+      if (args.timing) args.timing[cta_linear * 8 + 4] = clock64();   // producer done issuing
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -243,7 +280,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int s = i % C::kStages;
         mbar_wait(smem_u32(&full[s]), (i / C::kStages) & 1);
         umma::tc_fence_after_sync();
-        if (args.timing && i == 0) args.timing[cta_linear * 6 + 1] = clock64();
+        if (args.timing && i == 0) args.timing[cta_linear * 8 + 2] = clock64();
         const uint32_t a_base = smem_u32(smem + (size_t)s * C::kStageBytes), b_base = a_base + C::kABytes;
         const int k_left = args.Kc - (kb_begin + i) * KB;
         const int steps = min(KB / 16, (k_left + 15) / 16);              // the k tail issues only the 16-deep steps that hold data
@@ -263,7 +300,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         umma::mma_commit(smem_u32(&empty[s]));      // stage reusable once these MMAs retire
       }
       if (num_kb > 0) umma::mma_commit(smem_u32(accum_full));
-      if (args.timing) args.timing[cta_linear * 6 + 2] = clock64();
+      if (args.timing) args.timing[cta_linear * 8 + 3] = clock64();
     }
     __syncwarp();
   } else {
@@ -280,7 +317,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (num_kb > 0) {
       mbar_wait(smem_u32(accum_full), 0);   // every MMA has retired: accumulator complete
       umma::tc_fence_after_sync();
-      if (args.timing && tid == 64) args.timing[cta_linear * 6 + 4] = clock64();
+      if (args.timing && tid == 64) args.timing[cta_linear * 8 + 5] = clock64();
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
     float v[32];
@@ -305,10 +342,11 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       epi.template tile<16>(m, n0 + col0 + c, v, z, slot, st);
     }
     epi.finish(m, z, slot, st);
-    if (args.timing && tid == 64) args.timing[cta_linear * 6 + 5] = clock64();
+    if (args.timing && tid == 64) args.timing[cta_linear * 8 + 6] = clock64();
     umma::tc_fence_before_sync();
   }
   __syncthreads();
+  if (args.timing && tid == 0) args.timing[cta_linear * 8 + 7] = globaltimer_ns();
   if (warp == 1) {
     umma::tc_fence_after_sync();
     umma::tmem_dealloc(tmem_base, C::kTmemCols);

@@ -239,10 +239,13 @@ GCCNMF_API int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int
  * in the workspace, then DT (N, M) row-major = (A . B^T)^T.
  *   a_mn_major = 0: A is (M, Kc) row-major;  1: A is (Kc, M) row-major.   b_mn_major likewise with N.
  *   tile_n in {128, 176, 208, 256};  splits > 1: `splits` partial slabs DT[z] over k ranges (N * M floats each).
- *   timing: device uint64[6 x CTAs] clock64 stamps (start, first stage full, last MMA issued, producer done,
- *   accumulator complete, epilogue end) or NULL.
+ *   timing: device uint64[8 x CTAs] stamps (layout: gccnmf_debug_timing) or NULL.
  */
 GCCNMF_API size_t gccnmf_gemm_planes_workspace_bytes(int M, int N, int Kc);
+/* Diagnostics: while `stamps` (device uint64) is non-NULL every plane GEMM launched through the handle appends 8 values
+ * per CTA at a running offset: [0] / [7] %globaltimer ns at CTA start / end, [1..6] clock64 at start, first stage full,
+ * last MMA issued, producer done, accumulator complete, epilogue end.  Returns the offset reached; reset != 0 rewinds. */
+GCCNMF_API int64_t gccnmf_debug_timing(gccnmf_handle* h, unsigned long long* stamps, int reset);
 GCCNMF_API int gccnmf_gemm_planes(gccnmf_handle* h, const float* A, int a_mn_major, const float* B, int b_mn_major, float* DT,
                        int M, int N, int Kc, int tile_n, int splits, void* workspace, size_t workspace_bytes,
                        unsigned long long* timing, void* stream);

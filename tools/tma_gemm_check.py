@@ -119,9 +119,10 @@ def timing():
     V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
     W0, H0 = orc.initKLNMF(F, T2, K)
     W0d, H0d = h.to_device(W0), h.to_device(H0)
-    for name, tma, pdl in (('loader', 0, 0), ('tma', 1, 0), ('tma+pdl', 1, 1)):
+    for name, tma, pdl, mf in (('loader', 0, 0, 0), ('tma', 1, 0, 0), ('tma+pdl', 1, 1, 0), ('tma+pdl+m_fastest', 1, 1, 1)):
         h.set_option('nmf_tma', tma)
         h.set_option('nmf_pdl', pdl)
+        h.set_option('gemm_m_fastest', mf)
         ms = []
         for rep in range(4):
             W, H = W0d.clone(), H0d.clone()
@@ -133,6 +134,7 @@ def timing():
             ms.append(e0.elapsed_time(e1))
         print('KL-NMF config 2 (%s): %s ms per 100 iterations; W finite %s' % (name, ['%.2f' % m for m in ms], bool(torch.isfinite(W).all())), flush=True)
     h.set_option('nmf_pdl', 0)
+    h.set_option('gemm_m_fastest', 0)
     # per-GEMM CTA phase stamps
     g = torch.Generator(device='cpu').manual_seed(1)
     for (a_mn, b_mn, M, N, Kc, tile, splits, label) in ((0, 0, 513, 3744, 1024, 128, 1, 'G1/G3'), (1, 0, 1024, 3744, 513, 208, 1, 'G2'),
@@ -142,7 +144,7 @@ def timing():
         Ain = A.T.contiguous() if a_mn else A
         Bin = B.T.contiguous() if b_mn else B
         ctas = ((N + tile - 1) // tile) * ((M + 127) // 128 + 1) * splits
-        stamps = torch.zeros(ctas * 6, dtype=torch.int64, device=h.device)
+        stamps = torch.zeros(ctas * 8, dtype=torch.int64, device=h.device)
         for _ in range(3):
             h.gemm_planes(Ain, Bin, bool(a_mn), bool(b_mn), tile_n=tile, splits=splits, timing=stamps)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -152,13 +154,77 @@ def timing():
             h.gemm_planes(Ain, Bin, bool(a_mn), bool(b_mn), tile_n=tile, splits=splits)
         e1.record()
         e1.synchronize()
-        s = stamps.cpu().numpy().reshape(-1, 6)
+        s = stamps.cpu().numpy().reshape(-1, 8)[:, 1:7]
         s = s[s[:, 0] > 0]
         s = s[s[:, 5] > 0]
         d = lambda a, b: float(np.median(s[:, b] - s[:, a]))   # noqa: E731
         print('%s M=%d N=%d K=%d tile %d splits %d: %.1f us per call incl. operand split; CTA medians: start->first full %.0f, '
               'mma issue loop %.0f, last issue->accum done %.0f, epilogue %.0f, total %.0f cycles (%d CTAs)' % (
                   label, M, N, Kc, tile, splits, e0.elapsed_time(e1) / 20 * 1e3, d(0, 1), d(1, 2), d(2, 4), d(4, 5), d(0, 5), len(s)), flush=True)
+    return 0
+
+
+def stamps():
+    """%globaltimer / clock64 stamps of every CTA of the plane GEMMs inside the live KL-NMF loop (config 2)."""
+    import ctypes
+    import torch
+    from oracle import gccnmf_oracle as orc
+    h = handle()
+    F, T2, K = 513, 3744, 1024
+    rng = np.random.default_rng(5)
+    V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
+    W0, H0 = orc.initKLNMF(F, T2, K)
+    h.set_option('nmf_tma', 1)
+    for pdl in (0, 1):
+        h.set_option('nmf_pdl', pdl)
+        W, H = h.to_device(W0), h.to_device(H0)
+        h.klnmf(V, W, H, 5)
+        buf = torch.zeros(4 << 20, dtype=torch.int64, device=h.device)
+        torch.cuda.synchronize()
+        h.lib.gccnmf_debug_timing(h.h, buf.data_ptr(), 1)
+        h.klnmf(V, W, H, 3)
+        torch.cuda.synchronize()
+        used = h.lib.gccnmf_debug_timing(h.h, None, 1)
+        s = buf.cpu().numpy()[:used].reshape(-1, 8)
+        grids = [('G1', 30 * 5, 120), ('G2', 18 * 8, 144), ('G3', 30 * 5, 120), ('G4', 3 * 8 * 6, 144)] * 3
+        off, prev_end = 0, None
+        print('pdl=%d: %d CTA records' % (pdl, len(s)))
+        for name, ctas, tc in grids:
+            k = s[off:off + ctas]
+            off += ctas
+            k = k[k[:, 0] > 0]
+            t0 = k[:, 0].min()
+            st, en = k[:, 0] - t0, k[:, 7] - t0
+            is_tc = k[:, 1] > 0
+            dur = (k[:, 7] - k[:, 0])
+            cyc = lambda a, b: np.median((k[is_tc, b] - k[is_tc, a]))   # noqa: E731
+            msg = '%s: span %.1f us | CTA start offset p50 %.1f max %.1f us | tc CTA dur p50 %.1f max %.1f us' % (
+                name, en.max() / 1e3, np.median(st) / 1e3, st.max() / 1e3, np.median(dur[is_tc]) / 1e3, dur[is_tc].max() / 1e3)
+            if (~is_tc).any():
+                msg += ' | tail CTA dur p50 %.1f max %.1f, last tail end %.1f us' % (np.median(dur[~is_tc]) / 1e3, dur[~is_tc].max() / 1e3, en[~is_tc].max() / 1e3)
+            msg += ' | cycles: prologue %.0f, main %.0f, drain %.0f, epilogue %.0f' % (cyc(1, 2), cyc(2, 3), cyc(3, 5), cyc(5, 6))
+            if prev_end is not None:
+                msg += ' | gap after previous GEMM %.1f us' % ((t0 - prev_end) / 1e3)
+            prev_end = k[:, 7].max()
+            print(msg, flush=True)
+    h.set_option('nmf_pdl', 0)
+    return 0
+
+
+def prof():
+    """A short KL-NMF run on the TMA path for an ncu launch list (--cache-control none: warm L2 like the live loop)."""
+    import torch
+    from oracle import gccnmf_oracle as orc
+    h = handle()
+    F, T2, K = 513, 3744, 1024
+    rng = np.random.default_rng(5)
+    V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
+    W0, H0 = orc.initKLNMF(F, T2, K)
+    h.set_option('nmf_tma', 1)
+    h.set_option('nmf_pdl', int(os.environ.get('PROF_PDL', '0')))
+    W, H = h.to_device(W0), h.to_device(H0)
+    h.klnmf(V, W, H, int(os.environ.get('PROF_ITERS', '6')))
+    torch.cuda.synchronize()
     return 0
 
 
@@ -175,4 +241,4 @@ if __name__ == '__main__':
                 print('TIMEOUT in %s' % part)
                 rc |= 1
         sys.exit(rc)
-    sys.exit({'gemm': gemm, 'nmf': nmf, 'time': timing}[what]())
+    sys.exit({'gemm': gemm, 'nmf': nmf, 'time': timing, 'prof': prof, 'stamps': stamps}[what]())
