@@ -48,7 +48,7 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   const char* tma = getenv("GCCNMF_NMF_TMA");
   h->nmf_tma = !(tma && strcmp(tma, "0") == 0);
   const char* pdl = getenv("GCCNMF_NMF_PDL");
-  h->nmf_pdl = pdl && strcmp(pdl, "1") == 0;
+  h->nmf_pdl = !(pdl && strcmp(pdl, "0") == 0);
   *out = h;
   return GCCNMF_OK;
 }

@@ -16,7 +16,7 @@ struct gccnmf_handle {
   bool nmf_split_bf16 = true;    // KL-NMF contractions: 0 = 3xTF32 (hi/lo tf32), 1 = 3xBF16 (hi/lo bf16)
   bool force_simt_nmf = false;   // GCCNMF_NMF_PATH=simt: float32 SIMT contractions instead of tcgen05 3xTF32
   bool nmf_tma = true;           // KL-NMF contractions on the TMA-fed plane GEMM (klnmf_tma.cu); 0 = loader-based kernel (klnmf_tc.cu)
-  bool nmf_pdl = false;          // programmatic dependent launch between the kernels of a KL-NMF iteration
+  bool nmf_pdl = true;           // programmatic dependent launch between the kernels of a KL-NMF iteration
   bool gemm_m_fastest = false;   // plane GEMM grid order (diagnostics): m tiles vary fastest
   unsigned long long* debug_timing = nullptr;   // diagnostics (gccnmf_debug_timing): CTA stamps of every plane GEMM
   size_t debug_timing_cursor = 0;

@@ -136,94 +136,145 @@ int launch_ex(gccnmf_handle* h, const char* name, void (*kernel)(KArgs...), dim3
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
-struct EpiStoreT {   // DT[z][n][m] = acc  (lanes run along m: coalesced).  G4 partials (m = atom, n = f) and the test entry.
-  struct State {};
-  float* __restrict__ DT; int64_t ld, slab; int M, N;
-  __device__ void init(State&, int) const {}
-  __device__ void finish(int, int, int, State&) const {}
-  __device__ void elem(int m, int n, float acc, int z) const { DT[(int64_t)z * slab + (int64_t)n * ld + m] = acc; }
-  template <int NC>
-  __device__ void tile(int m, int n0, float (&v)[32], int z, int, State&) const {
-    if (m >= M) return;
-    float* out = DT + (int64_t)z * slab + m;
+// (concept: tma_gemm.cuh)  A warp owns column n; the lane holds rows m .. m + 3, contiguous in every output below.
+__device__ __forceinline__ uint32_t bf162_bits(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+// four consecutive values -> 4 hi + 4 lo bf16, packed in element order
+__device__ __forceinline__ void split4(const float4& x, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  hi = make_uint2(bf162_bits(h01), bf162_bits(h23));
+  lo = make_uint2(bf162_bits(__floats2bfloat162_rn(x.x - f01.x, x.y - f01.y)), bf162_bits(__floats2bfloat162_rn(x.z - f23.x, x.w - f23.y)));
+}
+__device__ __forceinline__ void store_planes4(bf16* hi_ptr, int64_t plane, const float4& x, int valid, bool vec) {
+  uint2 hi, lo;
+  split4(x, hi, lo);
+  if (vec && valid == 4) {
+    *reinterpret_cast<uint2*>(hi_ptr) = hi;
+    *reinterpret_cast<uint2*>(hi_ptr + plane) = lo;
+  } else {
+    const uint32_t hw[2] = {hi.x, hi.y}, lw[2] = {lo.x, lo.y};
 #pragma unroll
-    for (int j = 0; j < NC; ++j)
-      if (n0 + j < N) out[(int64_t)(n0 + j) * ld] = v[j];
+    for (int i = 0; i < 4; ++i)
+      if (i < valid) {
+        reinterpret_cast<uint16_t*>(hi_ptr)[i] = (uint16_t)(hw[i >> 1] >> (16 * (i & 1)));
+        reinterpret_cast<uint16_t*>(hi_ptr + plane)[i] = (uint16_t)(lw[i >> 1] >> (16 * (i & 1)));
+      }
+  }
+}
+__device__ __forceinline__ float4 load4(const float* p, int valid, bool vec, float fill) {
+  if (vec && valid == 4) return *reinterpret_cast<const float4*>(p);
+  float4 r = make_float4(fill, fill, fill, fill);
+  if (valid > 0) r.x = p[0];
+  if (valid > 1) r.y = p[1];
+  if (valid > 2) r.z = p[2];
+  if (valid > 3) r.w = p[3];
+  return r;
+}
+__device__ __forceinline__ void store4(float* p, const float4& v, int valid, bool vec) {
+  if (vec && valid == 4) { *reinterpret_cast<float4*>(p) = v; return; }
+  if (valid > 0) p[0] = v.x;
+  if (valid > 1) p[1] = v.y;
+  if (valid > 2) p[2] = v.z;
+  if (valid > 3) p[3] = v.w;
+}
+
+struct EpiStoreT {   // DT[z][n][m] = acc.  G4 partials (m = atom, n = f) and the test entry.
+  struct State {};
+  struct Loaded {};
+  static constexpr bool kRowReduce = false;
+  static constexpr int kRowValues = 0;
+  float* __restrict__ DT; int64_t ld, slab; int M, N; bool vec;
+  __device__ void row_values(int, float*) const {}
+  __device__ void init(State&, int, const float*) const {}
+  __device__ float4 row_partial(const State&) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ void row_total(int, int, float) const {}
+  __device__ void elem(int m, int n, float acc, int z) const { DT[(int64_t)z * slab + (int64_t)n * ld + m] = acc; }
+  __device__ Loaded load(int, int) const { return Loaded{}; }
+  __device__ void store(int m, int n, const float4& acc, const Loaded&, int z, State&) const {
+    const int valid = min(4, M - m);
+    if (valid <= 0) return;
+    store4(DT + (int64_t)z * slab + (int64_t)n * ld + m, acc, valid, vec);
   }
 };
 
 struct EpiRatioPlanes {   // RT[n][m] = split(VT[n][m] / acc)     G1 / G3 (m = f, n = t)
   struct State {};
-  const float* __restrict__ VT; bf16* __restrict__ RT; int64_t ld, plane; int M, N;
-  __device__ void init(State&, int) const {}
-  __device__ void finish(int, int, int, State&) const {}
+  struct Loaded { float4 vt; };
+  static constexpr bool kRowReduce = false;
+  static constexpr int kRowValues = 0;
+  const float* __restrict__ VT; bf16* __restrict__ RT; int64_t ld, plane; int M, N; bool vec;
+  __device__ void row_values(int, float*) const {}
+  __device__ void init(State&, int, const float*) const {}
+  __device__ float4 row_partial(const State&) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ void row_total(int, int, float) const {}
   __device__ void elem(int m, int n, float acc, int) const {
     bf16 hi, lo;
     split_bf16(VT[(int64_t)n * ld + m] / acc, hi, lo);
     RT[(int64_t)n * ld + m] = hi;
     RT[plane + (int64_t)n * ld + m] = lo;
   }
-  template <int NC>
-  __device__ void tile(int m, int n0, float (&v)[32], int, int, State&) const {
-    if (m >= M) return;
-    float vt[NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) vt[j] = (n0 + j < N) ? __ldg(VT + (int64_t)(n0 + j) * ld + m) : 1.f;
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      if (n0 + j < N) {
-        bf16 hi, lo;
-        split_bf16(vt[j] / v[j], hi, lo);
-        RT[(int64_t)(n0 + j) * ld + m] = hi;
-        RT[plane + (int64_t)(n0 + j) * ld + m] = lo;
-      }
-    }
+  __device__ Loaded load(int m, int n) const { return Loaded{load4(VT + (int64_t)n * ld + m, min(4, M - m), vec, 1.f)}; }
+  __device__ void store(int m, int n, const float4& acc, const Loaded& l, int, State&) const {
+    const int valid = min(4, M - m);
+    if (valid <= 0) return;
+    // V / (W H) with the hardware reciprocal (<= 2 ulp; the IEEE division sequence is ~10 instructions per element and made
+    // this epilogue instruction-bound)
+    const float4 r = make_float4(__fdividef(l.vt.x, acc.x), __fdividef(l.vt.y, acc.y), __fdividef(l.vt.z, acc.z), __fdividef(l.vt.w, acc.w));
+    store_planes4(RT + (int64_t)n * ld + m, plane, r, valid, vec);
   }
 };
 
 // G2 (m = atom, n = frame): new = (old * pending_norm[m]) * (acc / (colsum[m] + alpha + eps))  (:81 then :76).
-// H^T is updated in place (float32 master + planes); the per-row sums of the new H go to rowsum_part[slot][m]
-// (one writer per (slot, m): plain stores, fixed order, no atomics).
+// H^T is updated in place (float32 master + planes); the per-row sums of the new H over the tile's columns go to
+// rowsum_part[tile_n][m] (one writer per value, fixed summation order, no atomics).
 struct EpiUpdateH {
-  struct State { float denom, pn, rsum; };
+  struct State { float4 rden, pn, rsum; };
+  struct Loaded { float4 old; };
+  static constexpr bool kRowReduce = true;
+  static constexpr int kRowValues = 2;   // 1 / (colsum(W)[m] + alpha + eps), pending norm[m]
   float* __restrict__ HT; bf16* __restrict__ HTp; const float* __restrict__ colsumW; const float* __restrict__ pending;
-  float* __restrict__ rowsum_part; float alpha, eps; int64_t ld, plane; int M, N; int colsum_slots;
-  __device__ void init(State& s, int m) const {
-    s.rsum = 0.f; s.denom = 1.f; s.pn = 1.f;
+  float* __restrict__ rowsum_part; float alpha, eps; int64_t ld, plane; int M, N; int colsum_slots; bool vec;
+  __device__ void row_values(int m, float* v) const {
+    v[0] = 1.f; v[1] = 1.f;
     if (m >= M) return;
-    float c = colsumW[m];
-    for (int b = 1; b < colsum_slots; ++b) c += colsumW[(int64_t)b * M + m];   // colsum(W): the W update's per-row-block partials
-    s.denom = (c + alpha) + eps;
-    s.pn = pending ? pending[m] : 1.f;
+    float c = 0.f;
+    for (int b0 = 0; b0 < colsum_slots; b0 += 8) {       // colsum(W): the W update's per-row-block partials, 8 loads in flight
+      float p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p[j] = (b0 + j < colsum_slots) ? colsumW[(int64_t)(b0 + j) * M + m] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c += p[j];
+    }
+    v[0] = 1.f / ((c + alpha) + eps);
+    if (pending) v[1] = pending[m];
   }
-  __device__ void finish(int m, int, int slot, State& s) const {
-    if (m < M) rowsum_part[(int64_t)slot * M + m] = s.rsum;
+  __device__ void init(State& s, int, const float* rowvals) const {
+    s.rsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    s.rden = *reinterpret_cast<const float4*>(rowvals);
+    s.pn = *reinterpret_cast<const float4*>(rowvals + tgemm::kBM);
+  }
+  __device__ float4 row_partial(const State& s) const { return s.rsum; }
+  __device__ void row_total(int m, int tile_n, float sum) const {
+    if (m < M) rowsum_part[(int64_t)tile_n * M + m] = sum;
   }
   __device__ void elem(int, int, float, int) const {}   // M = atoms is tiled without SIMT tail rows
-  template <int NC>
-  __device__ void tile(int m, int n0, float (&v)[32], int, int, State& s) const {
-    if (m >= M) return;
-#pragma unroll
-    for (int b = 0; b < NC; b += 16) {     // 16 loads in flight per batch (32 spill)
-      float old[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) old[j] = (n0 + b + j < N) ? HT[(int64_t)(n0 + b + j) * ld + m] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (n0 + b + j < N) {
-          float o = old[j];
-          if (pending) o = o * s.pn;
-          const float hv = o * (v[b + j] / s.denom);
-          bf16 hi, lo;
-          split_bf16(hv, hi, lo);
-          const int64_t i = (int64_t)(n0 + b + j) * ld + m;
-          HT[i] = hv;
-          HTp[i] = hi;
-          HTp[plane + i] = lo;
-          s.rsum += hv;
-        }
-      }
+  __device__ Loaded load(int m, int n) const { return Loaded{load4(HT + (int64_t)n * ld + m, max(0, min(4, M - m)), vec, 0.f)}; }
+  __device__ void store(int m, int n, const float4& acc, const Loaded& l, int, State& s) const {
+    const int valid = min(4, M - m);
+    if (valid <= 0) return;
+    float4 o = l.old;
+    if (pending) { o.x *= s.pn.x; o.y *= s.pn.y; o.z *= s.pn.z; o.w *= s.pn.w; }
+    // acc / denom as acc * (1 / denom): the reciprocal is one IEEE division per row, shared by the tile's columns
+    float4 hv = make_float4(o.x * (acc.x * s.rden.x), o.y * (acc.y * s.rden.y), o.z * (acc.z * s.rden.z), o.w * (acc.w * s.rden.w));
+    if (valid < 4) {
+      if (valid < 2) hv.y = 0.f;
+      if (valid < 3) hv.z = 0.f;
+      hv.w = 0.f;
     }
+    const int64_t i = (int64_t)n * ld + m;
+    store4(HT + i, hv, valid, vec);
+    store_planes4(HTp + i, plane, hv, valid, vec);
+    s.rsum.x += hv.x; s.rsum.y += hv.y; s.rsum.z += hv.z; s.rsum.w += hv.w;
   }
 };
 
@@ -462,6 +513,8 @@ int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int 
   }
   args.m_fastest = h->gemm_m_fastest ? 1 : 0;
   const int n_tiles = (N + BN - 1) / BN, m_rows = args.m_tiles + (use_tail ? 1 : 0);
+  const int tc_ctas = args.m_tiles * n_tiles * splits;
+  args.tail_ctas = !use_tail ? 0 : (tc_ctas >= h->sm_count ? n_tiles : std::max(1, std::min(n_tiles, (h->sm_count - tc_ctas) / splits)));
   const dim3 grid(args.m_fastest ? m_rows : n_tiles, args.m_fastest ? n_tiles : m_rows, splits);
   if (!timing && h->debug_timing) h->debug_timing_cursor += (size_t)grid.x * grid.y * grid.z * 8;
   return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl, map_a, map_b, args, epi);
@@ -517,7 +570,7 @@ struct Plan {
   int bn_wh;            // G1 / G3
   int bn_h;             // G2
   TilePlan w;           // G4
-  int rowsum_slots;     // 2 x n-tiles of G2
+  int rowsum_slots;     // n-tiles of G2
 };
 
 Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
@@ -525,7 +578,7 @@ Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
   p.bn_wh = plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 2).bn;
   p.bn_h = plan_tiles(h->sm_count, m_tiles_of(K, false), T2, F, false, kWidthsAll, 4).bn;
   p.w = plan_tiles(h->sm_count, m_tiles_of(K, false), F, T2, true, kWidthsAll, 4);
-  p.rowsum_slots = 2 * ((T2 + p.bn_h - 1) / p.bn_h);
+  p.rowsum_slots = (T2 + p.bn_h - 1) / p.bn_h;
   return p;
 }
 
@@ -538,7 +591,7 @@ struct TmaWorkspace {
   bool ok;
 };
 
-int max_rowsum_slots(int T2) { return 2 * ((T2 + 127) / 128); }
+int max_rowsum_slots(int T2) { return (T2 + 127) / 128; }
 
 TmaWorkspace tma_carve(void* ws, size_t bytes, int F, int T2, int K) {
   WorkspaceCarver c(ws, bytes);
@@ -612,7 +665,7 @@ int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, c
   const Operand Wk{pending_norms ? w.Wnp : w.Wp, (int64_t)K, w.plane_w, false};
   const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
   {  // G1: RT = split(VT / (Wn . H^T))
-    EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2};
+    EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2, true};
     if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream)) return st;
   }
   if (colsum_state == 0) GCCNMF_LAUNCH(h, tma_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
@@ -620,7 +673,7 @@ int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, c
     const Operand Wmn{w.Wp, (int64_t)K, w.plane_w, true};
     const Operand RTk{w.RTp, w.Fp, w.plane_rt, false};
     EpiUpdateH e{w.HT, w.HTp, w.colsum, pending_norms ? w.norms : nullptr, w.rowsum_part, alpha, eps, (int64_t)K, w.plane_ht, K, T2,
-                 colsum_state == 2 ? w.row_blocks : 1};
+                 colsum_state == 2 ? w.row_blocks : 1, true};
     if (int st = plane_gemm<true, false>(h, p.bn_h, Wmn, RTk, K, T2, F, 1, false, e, nullptr, stream)) return st;
   }
   return 0;
@@ -636,13 +689,13 @@ int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, 
   {  // G3: RT = split(VT / (W . H^T))
     const Operand Wk{w.Wp, (int64_t)K, w.plane_w, false};
     const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
-    EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2};
+    EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2, true};
     if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream)) return st;
   }
   {  // G4: partial[z][f][atom] = sum_t H^T[t][atom] R^T[t][f]
     const Operand HTmn{w.HTp, (int64_t)K, w.plane_ht, true};
     const Operand RTmn{w.RTp, w.Fp, w.plane_rt, true};
-    EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F};
+    EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F, true};
     if (int st = plane_gemm<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, false, e, nullptr, stream)) return st;
   }
   return 0;
@@ -729,7 +782,7 @@ int gccnmf_gemm_planes(gccnmf_handle* h, const float* A, int a_mn_major, const f
   GCCNMF_LAUNCH(h, tma_split_rows_kernel, (unsigned)((nb + 255) / 256), 256, 0, stream, B, b_rows, b_inner, Bp, b_pitch, (int64_t)b_rows * b_pitch);
   const Operand Ao{Ap, a_pitch, (int64_t)a_rows * a_pitch, a_mn_major != 0};
   const Operand Bo{Bp, b_pitch, (int64_t)b_rows * b_pitch, b_mn_major != 0};
-  EpiStoreT e{DT, (int64_t)M, (int64_t)N * M, M, N};
+  EpiStoreT e{DT, (int64_t)M, (int64_t)N * M, M, N, M % 4 == 0 && (reinterpret_cast<uintptr_t>(DT) & 15) == 0};
   if (!a_mn_major && !b_mn_major) return plane_gemm<false, false>(h, tile_n, Ao, Bo, M, N, Kc, splits, true, e, timing, stream);
   if (a_mn_major && !b_mn_major) return plane_gemm<true, false>(h, tile_n, Ao, Bo, M, N, Kc, splits, false, e, timing, stream);
   if (a_mn_major && b_mn_major) return plane_gemm<true, true>(h, tile_n, Ao, Bo, M, N, Kc, splits, false, e, timing, stream);

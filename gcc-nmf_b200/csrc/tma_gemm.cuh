@@ -33,7 +33,9 @@ using umma::smem_u32;
 constexpr int kBM = 128;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (2 + kEpiWarps) * 32;
-constexpr int kSmemBudget = 225 * 1024;   // stages; + barriers + alignment slack stays under the 227 KB per-CTA limit
+constexpr int kColumnsInFlight = 8;        // epilogue: independent column loads per thread before the first dependent store
+constexpr int kMaxRowValues = 4;           // per-row values an epilogue functor may stage in shared memory
+constexpr int kSmemBudget = 216 * 1024;    // stages; + barriers + epilogue scratch + alignment slack stays under the 227 KB per-CTA limit
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -51,7 +53,7 @@ __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) 
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory");
   return t;
 }
 // Programmatic dependent launch: both are no-ops for a kernel launched without the attribute.
@@ -84,6 +86,9 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// barrier 1: the 8 epilogue warps only
+__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
 // hi = bf16(x) (round to nearest even), lo = bf16(x - hi): x = hi + lo up to 2^-17 |x|.
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
@@ -110,6 +115,7 @@ struct PlaneGemmArgs {
   const __nv_bfloat16* B; int64_t b_plane, ldb;
   unsigned long long* timing;   // optional diagnostics, 8 slots per CTA: [0] / [7] globaltimer (ns) at CTA start / end (tail CTAs too),
                                 // [1..6] clock64: start, first stage full, last MMA issued, producer done, accumulator complete, epilogue end
+  int tail_ctas;           // SIMT tail CTAs (per split) that do work: CTA x handles the n tiles x, x + tail_ctas, ...
   int m_fastest;           // 0: grid (n tiles, m tiles + tail, splits); 1: grid (m tiles + tail, n tiles, splits) -- the CTAs sharing a B block are co-scheduled
 };
 
@@ -129,7 +135,10 @@ struct Config {
   static_assert(kStages >= 2, "tile too large for a 2-stage pipeline");
   static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;   // + alignment slack
+  static constexpr int kScratchBytes = kMaxRowValues * kBM * 4 + (kThreads / 32) * 32 * 16;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kScratchBytes + 1024;   // + alignment slack
+  static_assert(kStages * kStageBytes >= BN * kBM * 4, "the epilogue stages the accumulator tile in the pipeline buffers");
+  static_assert(kTotal <= 227 * 1024, "shared memory per CTA");
   // K-major rows: KB bf16 = 64 B (SWIZZLE_64B, 8-row groups of 512 B) or 128 B (SWIZZLE_128B, groups of 1024 B)
   static constexpr uint32_t kKRowBytes = KB * 2;
   static constexpr uint32_t kKLayout = (KB == 32) ? 4u : 2u;
@@ -144,13 +153,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
          ((uint32_t)(kBM >> 4) << 24);
 }
 
-// Epilogue concept (functors in klnmf_tma.cu):
-//   struct State;  __device__ void init(State&, int m) const;          m = the thread's accumulator row
-//   template <int NC> __device__ void tile(int m, int n0, float (&v)[32], int z, int slot, State&) const;
-//       the thread holds D[m][n0 .. n0 + NC), NC = 32 or 16; called in increasing n0 over the warp's column range;
-//       slot = 2 * tile_n + column half (for per-CTA partial outputs)
-//   __device__ void finish(int m, int z, int slot, State&) const;      after the warp's last chunk
-//   __device__ void elem(int m, int n, float acc, int z) const;        SIMT tail rows
+// Epilogue concept (functors in klnmf_tma.cu).  The kernel stages the accumulator tile in shared memory and hands it out by
+// columns: a warp owns column n, lane l rows m .. m + 3 with m = m0 + 4 l (contiguous in every output of the KL-NMF loop).
+//   static constexpr int kRowValues (<= kMaxRowValues);  __device__ void row_values(int m, float* v) const;
+//       per-row constants, fetched by one thread per row while the main loop runs and staged in shared memory
+//   struct State;   __device__ void init(State&, int m, const float* rowvals) const;    rowvals[i * 128 + 0..3] = value i of rows m .. m + 3
+//   struct Loaded;  __device__ Loaded load(int m, int n) const;          the column's global operands (issued kColumnsInFlight deep)
+//   __device__ void store(int m, int n, float4 acc, const Loaded&, int z, State&) const;
+//   static constexpr bool kRowReduce;  __device__ float4 row_partial(const State&) const;  __device__ void row_total(int m, int tile_n, float) const;
+//   __device__ void elem(int m, int n, float acc, int z) const;          SIMT tail rows (one column per lane)
 template <int BN, int KB, bool A_MN, bool B_MN, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
 plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, PlaneGemmArgs args, Epilogue epi) {
@@ -172,34 +183,47 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (args.timing && tid == 0) args.timing[cta_tail * 8 + 0] = globaltimer_ns();
     pdl_launch_dependents();
     pdl_wait_prior_grids();
-    // One accumulator row x BN columns x the split's k range: each warp takes two columns at a time, each lane 8 consecutive
-    // k per 16-byte load (hi and lo plane), four k-chunks in flight -- 24 independent loads per thread, so the whole tail
-    // costs a few L2 round trips (a scalar version of this loop took 3 x as long as the tensor-core tiles it runs beside).
+    // One accumulator row x the split's k range.  Tail CTA x handles the n tiles x, x + tail_ctas, ... (tail_ctas = the SMs
+    // the tensor-core tiles leave idle, so the whole grid stays one wave); CTAs past tail_ctas exit at once.
+    // Each warp takes two columns per step, each lane 8 consecutive k per 16-byte load (hi and lo plane), four k-chunks in
+    // flight -- 24 independent loads per thread.  The result of step i stays in lanes 2i / 2i + 1 and the epilogue functor
+    // runs once per tile with one column per lane, so its global loads overlap instead of serialising on lane 0.
     const int k_begin = kb_begin * KB, k_end = min(args.Kc, kb_end * KB);
-    const int n_end = min(args.N, n0 + BN);
+    constexpr int kWarps = kThreads / 32;
+    constexpr int kSteps = (BN / 2 + kWarps - 1) / kWarps;          // column pairs per warp per tile
+    static_assert(kSteps <= 16, "one result lane pair per step");
+    const int n_tiles_total = (args.N + BN - 1) / BN;
+    if (tile_n >= args.tail_ctas) return;
     for (int m = args.m_tiles * kBM; m < args.M; ++m) {
       const __nv_bfloat16* a_hi = args.A + (int64_t)m * args.lda;
       const __nv_bfloat16* a_lo = a_hi + args.a_plane;
-      for (int n = n0 + 2 * warp; n < n_end; n += 2 * (kThreads / 32)) {
-        const bool two = n + 1 < n_end;
-        const __nv_bfloat16* b_hi = args.B + (int64_t)n * args.ldb;
-        const __nv_bfloat16* b_lo = b_hi + args.b_plane;
-        const int64_t next = two ? args.ldb : 0;
-        float acc0 = 0.f, acc1 = 0.f;
+      for (int tn = tile_n; tn < n_tiles_total; tn += args.tail_ctas) {
+        const int nbase = tn * BN, n_end = min(args.N, nbase + BN);
+        float keep = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < kSteps; ++i) {
+          const int n = nbase + 2 * (warp + i * kWarps);
+          if (n >= n_end) break;
+          const bool two = n + 1 < n_end;
+          const __nv_bfloat16* b_hi = args.B + (int64_t)n * args.ldb;
+          const __nv_bfloat16* b_lo = b_hi + args.b_plane;
+          const int64_t next = two ? args.ldb : 0;
+          float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 4
-        for (int k = k_begin + 8 * lane; k < k_end; k += 256) {     // pitches are multiples of 8; pad columns hold zeros
-          float a[8], b0[8], b1[8];
-          load_planes8(a_hi + k, a_lo + k, a);
-          load_planes8(b_hi + k, b_lo + k, b0);
-          load_planes8(b_hi + next + k, b_lo + next + k, b1);
+          for (int k = k_begin + 8 * lane; k < k_end; k += 256) {     // pitches are multiples of 8; pad columns hold zeros
+            float a[8], b0[8], b1[8];
+            load_planes8(a_hi + k, a_lo + k, a);
+            load_planes8(b_hi + k, b_lo + k, b0);
+            load_planes8(b_hi + next + k, b_lo + next + k, b1);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { acc0 = fmaf(a[j], b0[j], acc0); acc1 = fmaf(a[j], b1[j], acc1); }
+            for (int j = 0; j < 8; ++j) { acc0 = fmaf(a[j], b0[j], acc0); acc1 = fmaf(a[j], b1[j], acc1); }
+          }
+          for (int o = 16; o > 0; o >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
+          if (lane == 2 * i) keep = acc0;
+          if (lane == 2 * i + 1) keep = acc1;
         }
-        for (int o = 16; o > 0; o >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
-        if (lane == 0) {
-          epi.elem(m, n, acc0, z);
-          if (two) epi.elem(m, n + 1, acc1, z);
-        }
+        const int n_mine = nbase + 2 * (warp + (lane >> 1) * kWarps) + (lane & 1);
+        if ((lane >> 1) < kSteps && n_mine < n_end) epi.elem(m, n_mine, keep, z);
       }
     }
     if (args.timing) {
@@ -214,6 +238,10 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* empty = bars + C::kStages;      // [kStages]  tcgen05.commit -> TMA
   uint64_t* accum_full = bars + 2 * C::kStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
+  // epilogue scratch behind the barriers (never touched by TMA): per-row functor values, row-sum partials of the 10 warps
+  float* rowvals = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + C::kBarrierBytes);   // [kMaxRowValues][128]
+  float4* red = reinterpret_cast<float4*>(rowvals + kMaxRowValues * kBM);                             // [10 warps][32 lanes]
+  float* tile = reinterpret_cast<float*>(smem);        // epilogue: [BN][128] float32, aliases the pipeline stages
   const int m0 = tile_m * kBM;
 
   const int cta_linear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
@@ -304,22 +332,27 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
+    // ------------------------------------------------------------------ epilogue, phase 1 (8 warps)
+    // TMEM -> registers -> shared tile[n][m] (the pipeline stages are idle by then: every TMA box has landed and every
+    // MMA has retired).  While the main loop runs, warps 2-5 fetch the functor's per-row values (one row per thread).
     const int e = warp - 2;
     const int quarter = warp & 3;                        // TMEM lanes 32 (warp % 4) .. + 31 are the ones this warp may read
     const int half = e >> 2;
-    const int col0 = half ? C::kCols0 : 0;
-    const int ncols = half ? BN - C::kCols0 : C::kCols0;
-    const int m = m0 + quarter * 32 + lane;
-    const int slot = tile_n * 2 + half;
-    typename Epilogue::State st;
-    epi.init(st, m);
+    if (Epilogue::kRowValues > 0 && e < 4) {
+      float rv[Epilogue::kRowValues > 0 ? Epilogue::kRowValues : 1];
+      epi.row_values(m0 + e * 32 + lane, rv);
+#pragma unroll
+      for (int i = 0; i < Epilogue::kRowValues; ++i) rowvals[i * kBM + e * 32 + lane] = rv[i];
+    }
     if (num_kb > 0) {
       mbar_wait(smem_u32(accum_full), 0);   // every MMA has retired: accumulator complete
       umma::tc_fence_after_sync();
       if (args.timing && tid == 64) args.timing[cta_linear * 8 + 5] = clock64();
     }
+    const int col0 = half ? C::kCols0 : 0;
+    const int ncols = half ? BN - C::kCols0 : C::kCols0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+    float* dst = tile + (size_t)col0 * kBM + quarter * 32 + lane;
     float v[32];
     int c = 0;
 #pragma unroll 1
@@ -330,7 +363,8 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      epi.template tile<32>(m, n0 + col0 + c, v, z, slot, st);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[(size_t)(c + j) * kBM] = v[j];
     }
     if (c < ncols) {   // 16-column remainder (BN = 176, 208)
       if (num_kb > 0) {
@@ -339,11 +373,52 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
-      epi.template tile<16>(m, n0 + col0 + c, v, z, slot, st);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[(size_t)(c + j) * kBM] = v[j];
     }
-    epi.finish(m, z, slot, st);
+  }
+  // ------------------------------------------------------------------ epilogue, phase 2 (all 10 warps)
+  // Each warp owns whole columns n -- 128 consecutive m are contiguous in every output -- one float4 of m per lane, so each
+  // global access of a warp is one 512-byte (float32) or 256-byte (bf16 plane) row segment, with kColumnsInFlight
+  // independent loads per thread before the first dependent store.
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  {
+    constexpr int kWarps = kThreads / 32;
+    const int m_first = m0 + 4 * lane;
+    typename Epilogue::State st;
+    epi.init(st, m_first, rowvals + 4 * lane);
+    const int n_valid = min(BN, args.N - n0);
+    constexpr int U = kColumnsInFlight;
+#pragma unroll 1
+    for (int c = warp; c < n_valid; c += kWarps * U) {
+      typename Epilogue::Loaded loaded[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cc = c + kWarps * u;
+        if (cc < n_valid) loaded[u] = epi.load(m_first, n0 + cc);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cc = c + kWarps * u;
+        if (cc < n_valid) {
+          const float4 acc = *reinterpret_cast<const float4*>(tile + (size_t)cc * kBM + 4 * lane);
+          epi.store(m_first, n0 + cc, acc, loaded[u], z, st);
+        }
+      }
+    }
+    if constexpr (Epilogue::kRowReduce) {   // per-row sums over the tile's columns: 10 warp partials -> one value per row
+      red[warp * 32 + lane] = epi.row_partial(st);
+      __syncthreads();
+      if (tid < kBM) {
+        const float* r = reinterpret_cast<const float*>(red);
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) sum += r[w * kBM + tid];
+        epi.row_total(m0 + tid, tile_n, sum);
+      }
+    }
     if (args.timing && tid == 64) args.timing[cta_linear * 8 + 6] = clock64();
-    umma::tc_fence_before_sync();
   }
   __syncthreads();
   if (args.timing && tid == 0) args.timing[cta_linear * 8 + 7] = globaltimer_ns();
