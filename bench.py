@@ -61,9 +61,19 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append([c.strip() for c in line.split(',')] + [time.perf_counter()])
 
-    def stop(self):
+    def wait_first_row(self, timeout=5.0):
+        """nvidia-smi takes a few hundred ms to print its first sample: block until it has."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, windows=None):
+        """windows: [(t0, t1), ...] perf_counter intervals of the timed regions; only samples inside them are used."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -73,7 +83,11 @@ class ClockSampler(object):
             pass
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        rows = self.rows
+        if windows:
+            inside = [r for r in rows if any(t0 <= r[-1] <= t1 + 0.05 for t0, t1 in windows)]
+            rows = inside or rows
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -191,10 +205,13 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local) if rank == 0 else None      # started before the warm-up: its first sample takes a while
     for _ in range(max(args.warmup, 3)):
         r = step_dev(x_dev)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_first_row()
+    windows = []
     launches0 = h.launches
     step_ms, stage_ms = [], {}
     barrier()
@@ -211,6 +228,7 @@ def run_gpu(args):
             stage_ms[k] = stage_ms.get(k, 0.0) + v / args.steps
     barrier()
     wall = time.perf_counter() - wall0
+    windows.append((wall0, wall0 + wall))
     launches = h.launches - launches0
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=h.device)
     if world > 1:
@@ -224,6 +242,7 @@ def run_gpu(args):
         out_host = step_host(out_host)
     barrier()
     e2e_ms = []
+    e2e_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
@@ -239,7 +258,8 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_value = total_frames * args.steps / (float(e2e_total.item()) * 1e-3)
-    clocks = sampler.stop() if sampler else None      # sampled over the device-resident AND the end-to-end timed regions
+    windows.append((e2e_wall0, time.perf_counter()))
+    clocks = sampler.stop(windows) if sampler else None      # samples inside the device-resident AND the end-to-end timed regions
 
     if rank == 0:
         F, K, I = CFG['windowSize'] // 2 + 1, CFG['dictionarySize'], CFG['numIterations']
@@ -257,7 +277,7 @@ def run_gpu(args):
             'wall_s_timed_region': wall, 'gpu_launches': int(launches), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(x_host.numel() * 4),
                     'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': float(e2e_total.item()) / args.steps},
-            'roofline': {'kernel': 'KL-NMF iteration: umma::gemm_tn_3xtf32_kernel x4 (tcgen05, 3xBF16 operand split) + W update, per rank',
+            'roofline': {'kernel': 'KL-NMF iteration: tgemm::plane_gemm_kernel x4 (TMA-fed tcgen05, 3xBF16 operand planes) + W update, per rank',
                          'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': achieved / peak_tf, 'traffic': NMF_ITERATION_DRAM_BYTES, 'peak_source': peak_src,
                          'algorithmic_flops_per_launch_group': flops_per_iter, 'ms_per_iteration': nmf_ms / I,
@@ -277,7 +297,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

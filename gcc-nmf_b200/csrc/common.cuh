@@ -17,7 +17,8 @@ struct gccnmf_handle {
   bool force_simt_nmf = false;   // GCCNMF_NMF_PATH=simt: float32 SIMT contractions instead of tcgen05 3xTF32
   bool nmf_tma = true;           // KL-NMF contractions on the TMA-fed plane GEMM (klnmf_tma.cu); 0 = loader-based kernel (klnmf_tc.cu)
   bool nmf_pdl = true;           // programmatic dependent launch between the kernels of a KL-NMF iteration
-  bool gemm_m_fastest = false;   // plane GEMM grid order (diagnostics): m tiles vary fastest
+  int wh_tile = 0;               // diagnostics: tile width of the W.H contractions (0 = planned)
+  int gemm_cluster = -1;         // diagnostics: force the plane GEMM cluster shape 10 CN + CM (11 = no cluster); -1 = automatic
   unsigned long long* debug_timing = nullptr;   // diagnostics (gccnmf_debug_timing): CTA stamps of every plane GEMM
   size_t debug_timing_cursor = 0;
   struct gccnmf_tmap_cache* tmaps = nullptr;   // TMA tensor maps, keyed by (buffer, shape, box)

@@ -59,10 +59,10 @@ EncodeTiledFn encode_tiled_fn() {
 struct TmapKey {
   const void* base;
   uint64_t inner, rows, pitch_bytes, plane_bytes;
-  uint32_t box_inner, box_rows;
+  uint32_t box_inner, box_rows, box_planes;
   bool operator==(const TmapKey& o) const {
     return base == o.base && inner == o.inner && rows == o.rows && pitch_bytes == o.pitch_bytes && plane_bytes == o.plane_bytes &&
-           box_inner == o.box_inner && box_rows == o.box_rows;
+           box_inner == o.box_inner && box_rows == o.box_rows && box_planes == o.box_planes;
   }
 };
 
@@ -79,12 +79,12 @@ void gccnmf_tmap_cache_free(gccnmf_handle* h) {
 
 namespace {
 
-// Tensor map over a plane pair [2][rows][pitch] of bf16: dims (inner, rows, 2), box (box_inner, box_rows, 2).
+// Tensor map over a plane pair [2][rows][pitch] of bf16: dims (inner, rows, 2), box (box_inner, box_rows, box_planes).
 // box_inner * 2 bytes = 64 -> SWIZZLE_64B (K-major k-blocks of 32), 128 -> SWIZZLE_128B (MN-major atoms of 64).
 int get_tmap(gccnmf_handle* h, const bf16* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint64_t plane_elems,
-             uint32_t box_inner, uint32_t box_rows, CUtensorMap* out) {
+             uint32_t box_inner, uint32_t box_rows, uint32_t box_planes, CUtensorMap* out) {
   if (!h->tmaps) h->tmaps = new gccnmf_tmap_cache();
-  const TmapKey key{base, inner, rows, pitch_elems * 2, plane_elems * 2, box_inner, box_rows};
+  const TmapKey key{base, inner, rows, pitch_elems * 2, plane_elems * 2, box_inner, box_rows, box_planes};
   for (auto& e : h->tmaps->entries)
     if (e.first == key) { *out = e.second; return 0; }
   EncodeTiledFn encode = encode_tiled_fn();
@@ -93,7 +93,7 @@ int get_tmap(gccnmf_handle* h, const bf16* base, uint64_t inner, uint64_t rows, 
     return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "tensor map: base / pitch / plane stride must be 16-byte aligned");
   const cuuint64_t dims[3] = {inner, rows, 2};
   const cuuint64_t strides[2] = {key.pitch_bytes, key.plane_bytes};
-  const cuuint32_t box[3] = {box_inner, box_rows, 2};
+  const cuuint32_t box[3] = {box_inner, box_rows, box_planes};
   const cuuint32_t elem_strides[3] = {1, 1, 1};
   const CUtensorMapSwizzle swz = (box_inner * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap m;
@@ -106,29 +106,40 @@ int get_tmap(gccnmf_handle* h, const bf16* base, uint64_t inner, uint64_t rows, 
   return 0;
 }
 
-// K-major operand: rows x kc, k contiguous.
+// K-major operand: rows x kc, k contiguous; one box = one plane of a row slice (box_rows = tile rows / cluster extent).
 int tmap_kmajor(gccnmf_handle* h, const bf16* planes, int rows, int kc, int64_t pitch, int64_t plane, int box_rows, CUtensorMap* out) {
-  return get_tmap(h, planes, (uint64_t)kc, (uint64_t)rows, (uint64_t)pitch, (uint64_t)plane, kKB, (uint32_t)box_rows, out);
+  return get_tmap(h, planes, (uint64_t)kc, (uint64_t)rows, (uint64_t)pitch, (uint64_t)plane, kKB, (uint32_t)box_rows, 1, out);
 }
-// MN-major operand: stored as kc rows x mn contiguous.
+// MN-major operand: stored as kc rows x mn contiguous; one box = one 64-wide atom, both planes.
 int tmap_mnmajor(gccnmf_handle* h, const bf16* planes, int mn, int kc, int64_t pitch, int64_t plane, CUtensorMap* out) {
-  return get_tmap(h, planes, (uint64_t)mn, (uint64_t)kc, (uint64_t)pitch, (uint64_t)plane, 64, kKB, out);
+  return get_tmap(h, planes, (uint64_t)mn, (uint64_t)kc, (uint64_t)pitch, (uint64_t)plane, 64, kKB, 2, out);
 }
 
 // ------------------------------------------------------------------------------------------------ launch helper
 template <class... KArgs, class... Args>
 int launch_ex(gccnmf_handle* h, const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, bool pdl,
-              Args&&... args) {
+              dim3 cluster, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster.x;
+    attr[n].val.clusterDim.y = cluster.y;
+    attr[n].val.clusterDim.z = cluster.z;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = n;
   const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
   if (err != cudaSuccess) return gccnmf_fail(h, GCCNMF_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(err));
   h->launches++;
@@ -485,39 +496,103 @@ struct Operand {
   bool mn_major;           // false: (rows, kc) k contiguous; true: (kc, rows) rows contiguous
 };
 
+struct GemmShape {
+  int M, N, Kc, splits, m_tiles, n_tiles, tail_rows;
+};
+
+// One instantiation: kernel attributes + how many of its clusters can be resident at once (queried once).
+template <int BN, bool A_MN, bool B_MN, int CN, int CM, class Epi>
+struct PlaneGemmInstance {
+  using C = tgemm::Config<BN, kKB, A_MN, B_MN>;
+  static int max_clusters(gccnmf_handle* h, int* out) {
+    static int cached = -1;
+    if (cached < 0) {
+      auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, Epi>;
+      GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+      if (CN * CM == 1) {
+        cached = h->sm_count;
+      } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(CN * 64, CM * 64, 1);
+        cfg.blockDim = dim3(tgemm::kThreads);
+        cfg.dynamicSmemBytes = C::kTotal;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CN; attr[0].val.clusterDim.y = CM; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        GCCNMF_CHECK_CUDA(h, cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+        cached = n;
+      }
+    }
+    *out = cached;
+    return 0;
+  }
+  static int launch(gccnmf_handle* h, const Operand& A, const Operand& B, const GemmShape& g, const Epi& epi, unsigned long long* timing, void* stream) {
+    auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, Epi>;
+    int unused;
+    if (int st = max_clusters(h, &unused)) return st;     // (sets the shared-memory attribute on first use)
+    CUtensorMap map_a, map_b;
+    if (int st = A_MN ? tmap_mnmajor(h, A.planes, g.M, g.Kc, A.pitch, A.plane, &map_a)
+                      : tmap_kmajor(h, A.planes, g.M, g.Kc, A.pitch, A.plane, tgemm::kBM / CN, &map_a)) return st;
+    if (int st = B_MN ? tmap_mnmajor(h, B.planes, g.N, g.Kc, B.pitch, B.plane, &map_b)
+                      : tmap_kmajor(h, B.planes, g.N, g.Kc, B.pitch, B.plane, BN / CM, &map_b)) return st;
+    PlaneGemmArgs args{};
+    args.M = g.M; args.N = g.N; args.Kc = g.Kc;
+    args.m_tiles = g.m_tiles;
+    args.tail_rows = g.tail_rows;
+    args.tail_cols = (((BN + g.m_tiles - 1) / g.m_tiles) + 1) & ~1;
+    const int total_kb = (g.Kc + kKB - 1) / kKB;
+    args.kblocks_per_split = (total_kb + g.splits - 1) / g.splits;
+    args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
+    args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
+    args.timing = timing;
+    const dim3 grid(g.n_tiles, g.m_tiles, g.splits);
+    if (!timing && h->debug_timing) {   // diagnostics: every plane GEMM of the KL-NMF loop appends its CTA stamps (8 per CTA)
+      args.timing = h->debug_timing + h->debug_timing_cursor;
+      h->debug_timing_cursor += (size_t)grid.x * grid.y * grid.z * 8;
+    }
+    return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl, dim3(CN, CM, 1),
+                     map_a, map_b, args, epi);
+  }
+};
+
+// Cluster shape (CN n tiles x CM m tiles share operand slices by TMA multicast): the largest of 2x2, then the pair that
+// shares the larger operand tile, that divides the grid and whose clusters are all resident in one wave (when the
+// single-CTA grid is); h->gemm_cluster (diagnostics) forces 10 CN + CM.
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, bool simt_tail,
                       const Epi& epi, unsigned long long* timing, void* stream) {
-  using C = tgemm::Config<BN, kKB, A_MN, B_MN>;
-  auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, Epi>;
-  static bool configured = false;
-  if (!configured) {
-    GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
-    configured = true;
-  }
-  CUtensorMap map_a, map_b;
-  if (int st = A_MN ? tmap_mnmajor(h, A.planes, M, Kc, A.pitch, A.plane, &map_a) : tmap_kmajor(h, A.planes, M, Kc, A.pitch, A.plane, tgemm::kBM, &map_a)) return st;
-  if (int st = B_MN ? tmap_mnmajor(h, B.planes, N, Kc, B.pitch, B.plane, &map_b) : tmap_kmajor(h, B.planes, N, Kc, B.pitch, B.plane, BN, &map_b)) return st;
-  PlaneGemmArgs args{};
-  args.M = M; args.N = N; args.Kc = Kc;
+  GemmShape g{};
+  g.M = M; g.N = N; g.Kc = Kc; g.splits = splits;
   const int tail = M % tgemm::kBM;
   const bool use_tail = simt_tail && !A_MN && !B_MN && tail != 0 && tail <= kTailRowsMax && M > tgemm::kBM;
-  args.m_tiles = use_tail ? M / tgemm::kBM : (M + tgemm::kBM - 1) / tgemm::kBM;
-  const int total_kb = (Kc + kKB - 1) / kKB;
-  args.kblocks_per_split = (total_kb + splits - 1) / splits;
-  args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
-  args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
-  args.timing = timing;
-  if (!timing && h->debug_timing) {   // diagnostics: every plane GEMM of the KL-NMF loop appends its CTA stamps (8 per CTA)
-    args.timing = h->debug_timing + h->debug_timing_cursor;
+  g.m_tiles = use_tail ? M / tgemm::kBM : (M + tgemm::kBM - 1) / tgemm::kBM;
+  g.tail_rows = use_tail ? tail : 0;
+  g.n_tiles = (N + BN - 1) / BN;
+  const int ctas = g.n_tiles * g.m_tiles * splits;
+  const int order_b_first[4][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}}, order_a_first[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
+  const int (*order)[2] = (BN > tgemm::kBM) ? order_b_first : order_a_first;
+  for (int i = 0; i < 4; ++i) {
+    const int cn = order[i][0], cm = order[i][1];
+    if (h->gemm_cluster >= 0 && h->gemm_cluster != 10 * cn + cm && !(cn == 1 && cm == 1)) continue;
+    if (g.n_tiles % cn != 0 || g.m_tiles % cm != 0) continue;
+    int resident = 0;
+#define GCCNMF_TRY_CLUSTER(CN_, CM_)                                                                                         \
+    if (cn == CN_ && cm == CM_) {                                                                                            \
+      if (int st = PlaneGemmInstance<BN, A_MN, B_MN, CN_, CM_, Epi>::max_clusters(h, &resident)) return st;                  \
+      /* a single-wave grid must keep all its clusters resident at once; a multi-wave grid only needs one to fit */            \
+      if (cn * cm == 1 || (resident > 0 && (ctas > h->sm_count || resident * cn * cm >= ctas)))                                \
+          return PlaneGemmInstance<BN, A_MN, B_MN, CN_, CM_, Epi>::launch(h, A, B, g, epi, timing, stream);                  \
+    }
+    GCCNMF_TRY_CLUSTER(2, 2)
+    GCCNMF_TRY_CLUSTER(1, 2)
+    GCCNMF_TRY_CLUSTER(2, 1)
+    GCCNMF_TRY_CLUSTER(1, 1)
+#undef GCCNMF_TRY_CLUSTER
   }
-  args.m_fastest = h->gemm_m_fastest ? 1 : 0;
-  const int n_tiles = (N + BN - 1) / BN, m_rows = args.m_tiles + (use_tail ? 1 : 0);
-  const int tc_ctas = args.m_tiles * n_tiles * splits;
-  args.tail_ctas = !use_tail ? 0 : (tc_ctas >= h->sm_count ? n_tiles : std::max(1, std::min(n_tiles, (h->sm_count - tc_ctas) / splits)));
-  const dim3 grid(args.m_fastest ? m_rows : n_tiles, args.m_fastest ? n_tiles : m_rows, splits);
-  if (!timing && h->debug_timing) h->debug_timing_cursor += (size_t)grid.x * grid.y * grid.z * 8;
-  return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl, map_a, map_b, args, epi);
+  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: no launchable cluster shape");
 }
 
 template <bool A_MN, bool B_MN, class Epi>
@@ -575,7 +650,7 @@ struct Plan {
 
 Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
   Plan p;
-  p.bn_wh = plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 2).bn;
+  p.bn_wh = h->wh_tile ? h->wh_tile : plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 2).bn;
   p.bn_h = plan_tiles(h->sm_count, m_tiles_of(K, false), T2, F, false, kWidthsAll, 4).bn;
   p.w = plan_tiles(h->sm_count, m_tiles_of(K, false), F, T2, true, kWidthsAll, 4);
   p.rowsum_slots = (T2 + p.bn_h - 1) / p.bn_h;
@@ -711,13 +786,13 @@ int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, c
   const float* rowsum = numer ? numer + (int64_t)F * K : w.rowsum_part;
   const dim3 grid((K + kApplyTile - 1) / kApplyTile, w.row_blocks), block(kApplyTile, 8);
   if (numer_is_multicast) {
-    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<true>, grid, block, 0, stream, h->nmf_pdl, W, partial, 1, rowsum, 1, F, K,
+    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, partial, 1, rowsum, 1, F, K,
                            w.sumsq_part)) return st;
   } else {
-    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<false>, grid, block, 0, stream, h->nmf_pdl, W, partial,
+    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<false>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, partial,
                            numer ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part)) return st;
   }
-  return launch_ex(h, "tma_apply_w2_kernel", tma_apply_w2_kernel, grid, block, 0, stream, h->nmf_pdl, W, w.Wp, w.Wnp, w.plane_w,
+  return launch_ex(h, "tma_apply_w2_kernel", tma_apply_w2_kernel, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.Wnp, w.plane_w,
                    (const float*)w.sumsq_part, w.row_blocks, F, K, w.norms, w.colsum);
 }
 

@@ -13,8 +13,11 @@
 // CTA = one 128 x BN accumulator tile, 10 warps:
 //   warp 0     lane 0 is the TMA producer: waits empty[s], arms full[s] with the stage's byte count, issues the boxes
 //   warp 1     allocates TMEM; lane 0 issues every tcgen05.mma and tcgen05.commit (-> empty[s], accum_full)
-//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> functor; warp w reads TMEM lane quarter w % 4
-// Rows past the last full 128-row tile (F = 513 = 4 x 128 + 1) are computed by extra SIMT CTAs of the same launch.
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> shared tile -> functor by columns (all 10 warps)
+// Rows past the last full 128-row tile (F = 513 = 4 x 128 + 1) are computed in float32 SIMT by the epilogue warps while
+// they wait for the accumulator.  A cluster of CN x CM CTAs (n tiles x m tiles) shares operand tiles: each CTA loads 1 / CN
+// of its A tile and 1 / CM of its B tile and TMA-multicasts the slice to the CTAs of its cluster row / column (the loop is
+// L2 -> SM bandwidth bound: 2 x 2 clusters halve that traffic).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -47,6 +50,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// Same, delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA of the cluster in `mask`.
+template <bool MULTICAST>
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  if (MULTICAST) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+  } else {
+    tma_load_3d(dst, map, bar, c0, c1, c2);
+  }
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`.
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -108,15 +131,15 @@ __device__ __forceinline__ void load_planes8(const __nv_bfloat16* hi, const __nv
 
 struct PlaneGemmArgs {
   int M, N, Kc;
-  int m_tiles;             // 128-row tiles on the tensor cores; blockIdx.y == m_tiles -> SIMT tail rows [128 m_tiles, M)
+  int m_tiles;             // 128-row tiles on the tensor cores (= gridDim.y)
+  int tail_rows;           // rows [128 m_tiles, M) computed in float32 SIMT by the epilogue warps while the main loop runs (K-major operands)
+  int tail_cols;           // columns of the n tile each m tile's CTA takes for those rows (multiple of 2)
   int kblocks_per_split;   // k-blocks of KB handled by one blockIdx.z
   // SIMT tail rows (both operands K-major only): element (r, k) of plane p at ptr[p * plane + r * ld + k]
   const __nv_bfloat16* A; int64_t a_plane, lda;
   const __nv_bfloat16* B; int64_t b_plane, ldb;
   unsigned long long* timing;   // optional diagnostics, 8 slots per CTA: [0] / [7] globaltimer (ns) at CTA start / end (tail CTAs too),
                                 // [1..6] clock64: start, first stage full, last MMA issued, producer done, accumulator complete, epilogue end
-  int tail_ctas;           // SIMT tail CTAs (per split) that do work: CTA x handles the n tiles x, x + tail_ctas, ...
-  int m_fastest;           // 0: grid (n tiles, m tiles + tail, splits); 1: grid (m tiles + tail, n tiles, splits) -- the CTAs sharing a B block are co-scheduled
 };
 
 template <int BN, int KB, bool A_MN, bool B_MN>
@@ -162,80 +185,33 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
 //   __device__ void store(int m, int n, float4 acc, const Loaded&, int z, State&) const;
 //   static constexpr bool kRowReduce;  __device__ float4 row_partial(const State&) const;  __device__ void row_total(int m, int tile_n, float) const;
 //   __device__ void elem(int m, int n, float acc, int z) const;          SIMT tail rows (one column per lane)
-template <int BN, int KB, bool A_MN, bool B_MN, class Epilogue>
+template <int BN, int KB, bool A_MN, bool B_MN, int CN, int CM, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
 plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, PlaneGemmArgs args, Epilogue epi) {
   using C = Config<BN, KB, A_MN, B_MN>;
+  constexpr int kCluster = CN * CM;
+  static_assert((CN == 1 || CN == 2) && (CM == 1 || CM == 2), "cluster of CN n-tiles x CM m-tiles");
+  static_assert(A_MN || (kBM / CN) % 8 == 0, "A row slices keep the swizzle atoms whole");
+  static_assert(B_MN || (BN / CM) % 8 == 0, "B row slices keep the swizzle atoms whole");
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile_n = args.m_fastest ? blockIdx.y : blockIdx.x, tile_m = args.m_fastest ? blockIdx.x : blockIdx.y, z = blockIdx.z;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y, z = blockIdx.z;
   const int n0 = tile_n * BN;
   const int total_kblocks = (args.Kc + KB - 1) / KB;
   const int kb_begin = z * args.kblocks_per_split;
   const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
   const int num_kb = max(0, kb_end - kb_begin);
-
-  if (tile_m >= args.m_tiles) {
-    // ---------------------------------------------------------------- SIMT tail rows (K-major planes; runs on SMs the tile grid leaves idle)
-    const int cta_tail = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    if (args.timing && tid == 0) args.timing[cta_tail * 8 + 0] = globaltimer_ns();
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();
-    // One accumulator row x the split's k range.  Tail CTA x handles the n tiles x, x + tail_ctas, ... (tail_ctas = the SMs
-    // the tensor-core tiles leave idle, so the whole grid stays one wave); CTAs past tail_ctas exit at once.
-    // Each warp takes two columns per step, each lane 8 consecutive k per 16-byte load (hi and lo plane), four k-chunks in
-    // flight -- 24 independent loads per thread.  The result of step i stays in lanes 2i / 2i + 1 and the epilogue functor
-    // runs once per tile with one column per lane, so its global loads overlap instead of serialising on lane 0.
-    const int k_begin = kb_begin * KB, k_end = min(args.Kc, kb_end * KB);
-    constexpr int kWarps = kThreads / 32;
-    constexpr int kSteps = (BN / 2 + kWarps - 1) / kWarps;          // column pairs per warp per tile
-    static_assert(kSteps <= 16, "one result lane pair per step");
-    const int n_tiles_total = (args.N + BN - 1) / BN;
-    if (tile_n >= args.tail_ctas) return;
-    for (int m = args.m_tiles * kBM; m < args.M; ++m) {
-      const __nv_bfloat16* a_hi = args.A + (int64_t)m * args.lda;
-      const __nv_bfloat16* a_lo = a_hi + args.a_plane;
-      for (int tn = tile_n; tn < n_tiles_total; tn += args.tail_ctas) {
-        const int nbase = tn * BN, n_end = min(args.N, nbase + BN);
-        float keep = 0.f;
-#pragma unroll 1
-        for (int i = 0; i < kSteps; ++i) {
-          const int n = nbase + 2 * (warp + i * kWarps);
-          if (n >= n_end) break;
-          const bool two = n + 1 < n_end;
-          const __nv_bfloat16* b_hi = args.B + (int64_t)n * args.ldb;
-          const __nv_bfloat16* b_lo = b_hi + args.b_plane;
-          const int64_t next = two ? args.ldb : 0;
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-          for (int k = k_begin + 8 * lane; k < k_end; k += 256) {     // pitches are multiples of 8; pad columns hold zeros
-            float a[8], b0[8], b1[8];
-            load_planes8(a_hi + k, a_lo + k, a);
-            load_planes8(b_hi + k, b_lo + k, b0);
-            load_planes8(b_hi + next + k, b_lo + next + k, b1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { acc0 = fmaf(a[j], b0[j], acc0); acc1 = fmaf(a[j], b1[j], acc1); }
-          }
-          for (int o = 16; o > 0; o >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
-          if (lane == 2 * i) keep = acc0;
-          if (lane == 2 * i + 1) keep = acc1;
-        }
-        const int n_mine = nbase + 2 * (warp + (lane >> 1) * kWarps) + (lane & 1);
-        if ((lane >> 1) < kSteps && n_mine < n_end) epi.elem(m, n_mine, keep, z);
-      }
-    }
-    if (args.timing) {
-      __syncthreads();
-      if (tid == 0) args.timing[cta_tail * 8 + 7] = globaltimer_ns();
-    }
-    return;
-  }
+  // position inside the cluster (x = n tile, y = m tile); rank = x + CN y (%cluster_ctarank)
+  const int cx = (CN > 1) ? (int)(blockIdx.x % CN) : 0, cy = (CM > 1) ? (int)(blockIdx.y % CM) : 0;
+  // CTAs that receive my slice of A (same m tile: my cluster row) / of B (same n tile: my cluster column)
+  const uint16_t mask_row = (uint16_t)(((1u << CN) - 1u) << (CN * cy));
+  const uint16_t mask_col = (uint16_t)((CM > 1 ? ((1u << cx) | (1u << (cx + CN))) : (1u << cx)));
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
   uint64_t* full = bars;                    // [kStages]  TMA -> MMA
-  uint64_t* empty = bars + C::kStages;      // [kStages]  tcgen05.commit -> TMA
+  uint64_t* empty = bars + C::kStages;      // [kStages]  tcgen05.commit (of every CTA that shares a slice with me) -> TMA
   uint64_t* accum_full = bars + 2 * C::kStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
   // epilogue scratch behind the barriers (never touched by TMA): per-row functor values, row-sum partials of the 10 warps
@@ -252,7 +228,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (tid == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&empty[s]), CN + CM - 1);     // one release per CTA whose multicast lands in this stage (incl. myself)
     }
     mbar_init(smem_u32(accum_full), 1);
     umma::fence_barrier_init();
@@ -261,7 +237,8 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
   if (warp == 1) umma::tmem_alloc(smem_u32(tmem_base_slot), C::kTmemCols);
   umma::tc_fence_before_sync();
-  __syncthreads();
+  if (kCluster > 1) cluster_sync();     // no peer may signal my barriers or write my stages before they are initialised
+  else __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_slot;
   // Everything above overlaps the previous kernel's tail under programmatic dependent launch; nothing below may
@@ -275,22 +252,30 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % C::kStages;
         const uint32_t use = i / C::kStages;
-        if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // the MMAs that read this stage have retired
+        if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // the MMAs (mine and my peers') that read this stage have retired
         const uint32_t bar = smem_u32(&full[s]);
-        mbar_arrive_expect_tx(bar, C::kStageBytes);
+        mbar_arrive_expect_tx(bar, C::kStageBytes);                    // my slices + the ones my peers multicast to me
         const uint32_t a_dst = smem_u32(smem + (size_t)s * C::kStageBytes), b_dst = a_dst + C::kABytes;
         const int k0 = (kb_begin + i) * KB;
         if (A_MN) {
 #pragma unroll
-          for (int a = 0; a < C::kAAtoms; ++a) tma_load_3d(a_dst + a * C::kAtomBytes, &map_a, bar, m0 + 64 * a, k0, 0);
+          for (int a = 0; a < C::kAAtoms; ++a)
+            if (a % CN == cx) tma_load_3d_mc<(CN > 1)>(a_dst + a * C::kAtomBytes, &map_a, bar, m0 + 64 * a, k0, 0, mask_row);
         } else {
-          tma_load_3d(a_dst, &map_a, bar, k0, m0, 0);
+          constexpr int kRows = kBM / CN;      // my row slice of the A tile, one box per plane
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+            tma_load_3d_mc<(CN > 1)>(a_dst + p * (kBM * KB * 2) + cx * (kRows * KB * 2), &map_a, bar, k0, m0 + cx * kRows, p, mask_row);
         }
         if (B_MN) {
 #pragma unroll
-          for (int a = 0; a < C::kBAtoms; ++a) tma_load_3d(b_dst + a * C::kAtomBytes, &map_b, bar, n0 + 64 * a, k0, 0);
+          for (int a = 0; a < C::kBAtoms; ++a)
+            if (a % CM == cy) tma_load_3d_mc<(CM > 1)>(b_dst + a * C::kAtomBytes, &map_b, bar, n0 + 64 * a, k0, 0, mask_col);
         } else {
-          tma_load_3d(b_dst, &map_b, bar, k0, n0, 0);
+          constexpr int kRows = BN / CM;
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+            tma_load_3d_mc<(CM > 1)>(b_dst + p * (BN * KB * 2) + cy * (kRows * KB * 2), &map_b, bar, k0, n0 + cy * kRows, p, mask_col);
         }
       }
       if (args.timing) args.timing[cta_linear * 8 + 4] = clock64();   // producer done issuing
@@ -304,6 +289,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       constexpr uint32_t a_lo_off = A_MN ? KB * 128 : kBM * KB * 2;
       constexpr uint32_t b_lo_off = B_MN ? KB * 128 : BN * KB * 2;
       constexpr uint32_t a_step = A_MN ? 2048u : 32u, b_step = B_MN ? 2048u : 32u;
+      const uint16_t mask_release = mask_row | mask_col;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % C::kStages;
         mbar_wait(smem_u32(&full[s]), (i / C::kStages) & 1);
@@ -325,25 +311,65 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             umma::mma_bf16(tmem_base, a_hi, b_hi, idesc, 1);
           }
         }
-        umma::mma_commit(smem_u32(&empty[s]));      // stage reusable once these MMAs retire
+        // stage reusable once these MMAs retire: tell every CTA whose multicast lands in it
+        if (kCluster > 1) mma_commit_multicast(smem_u32(&empty[s]), mask_release);
+        else umma::mma_commit(smem_u32(&empty[s]));
       }
       if (num_kb > 0) umma::mma_commit(smem_u32(accum_full));
       if (args.timing) args.timing[cta_linear * 8 + 3] = clock64();
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue, phase 1 (8 warps)
-    // TMEM -> registers -> shared tile[n][m] (the pipeline stages are idle by then: every TMA box has landed and every
-    // MMA has retired).  While the main loop runs, warps 2-5 fetch the functor's per-row values (one row per thread).
+    // ------------------------------------------------------------------ epilogue warps, while the main loop runs
     const int e = warp - 2;
     const int quarter = warp & 3;                        // TMEM lanes 32 (warp % 4) .. + 31 are the ones this warp may read
     const int half = e >> 2;
-    if (Epilogue::kRowValues > 0 && e < 4) {
+    if (Epilogue::kRowValues > 0 && e < 4) {             // the functor's per-row values, one row per thread
       float rv[Epilogue::kRowValues > 0 ? Epilogue::kRowValues : 1];
       epi.row_values(m0 + e * 32 + lane, rv);
 #pragma unroll
       for (int i = 0; i < Epilogue::kRowValues; ++i) rowvals[i * kBM + e * 32 + lane] = rv[i];
     }
+    if (!A_MN && !B_MN && args.tail_rows > 0) {
+      // Rows past the last full 128-row tile (F = 513 = 4 x 128 + 1), float32 SIMT from the K-major planes: the m tiles of
+      // this n tile share its columns (tail_cols each), each warp takes two columns per step, each lane 8 consecutive k per
+      // 16-byte load (hi and lo plane), four k-chunks in flight.  The result of step i stays in lanes 2i / 2i + 1 and the
+      // functor runs with one column per lane, so its global loads overlap.
+      const int k_begin = kb_begin * KB, k_end = min(args.Kc, kb_end * KB);
+      const int c_begin = n0 + tile_m * args.tail_cols, c_end = min(min(args.N, n0 + BN), c_begin + args.tail_cols);
+      for (int m = args.m_tiles * kBM; m < args.M; ++m) {
+        const __nv_bfloat16* a_hi = args.A + (int64_t)m * args.lda;
+        const __nv_bfloat16* a_lo = a_hi + args.a_plane;
+        float keep = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < 16; ++i) {
+          const int n = c_begin + 2 * (e + i * kEpiWarps);
+          if (n >= c_end) break;
+          const bool two = n + 1 < c_end;
+          const __nv_bfloat16* b_hi = args.B + (int64_t)n * args.ldb;
+          const __nv_bfloat16* b_lo = b_hi + args.b_plane;
+          const int64_t next = two ? args.ldb : 0;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+          for (int k = k_begin + 8 * lane; k < k_end; k += 256) {     // pitches are multiples of 8; pad columns hold zeros
+            float a[8], b0[8], b1[8];
+            load_planes8(a_hi + k, a_lo + k, a);
+            load_planes8(b_hi + k, b_lo + k, b0);
+            load_planes8(b_hi + next + k, b_lo + next + k, b1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc0 = fmaf(a[j], b0[j], acc0); acc1 = fmaf(a[j], b1[j], acc1); }
+          }
+          for (int o = 16; o > 0; o >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
+          if (lane == 2 * i) keep = acc0;
+          if (lane == 2 * i + 1) keep = acc1;
+        }
+        const int n_mine = c_begin + 2 * (e + (lane >> 1) * kEpiWarps) + (lane & 1);
+        if (n_mine < c_end) epi.elem(m, n_mine, keep, z);
+      }
+    }
+    // ------------------------------------------------------------------ epilogue, phase 1 (8 warps)
+    // TMEM -> registers -> shared tile[n][m] (the pipeline stages are idle by then: every TMA box has landed -- mine and the
+    // ones my peers multicast to me were all consumed by my MMAs -- and every MMA has retired).
     if (num_kb > 0) {
       mbar_wait(smem_u32(accum_full), 0);   // every MMA has retired: accumulator complete
       umma::tc_fence_after_sync();
@@ -420,7 +446,10 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     if (args.timing && tid == 64) args.timing[cta_linear * 8 + 6] = clock64();
   }
-  __syncthreads();
+  // No CTA of a cluster may exit while a peer can still signal its barriers (my last releases have been delivered by now:
+  // they precede accum_full, which the epilogue waited for).
+  if (kCluster > 1) cluster_sync();
+  else __syncthreads();
   if (args.timing && tid == 0) args.timing[cta_linear * 8 + 7] = globaltimer_ns();
   if (warp == 1) {
     umma::tc_fence_after_sync();

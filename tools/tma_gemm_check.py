@@ -26,8 +26,10 @@ def gemm():
     h = handle()
     shapes = [(128, 128, 64), (128, 256, 96), (256, 300, 1024), (513, 3744, 1024), (1024, 3744, 513), (1024, 513, 3744), (200, 130, 70)]
     bad = 0
-    for a_mn, b_mn in ((False, False), (True, False), (True, True)):
-        for M, N, Kc in shapes:
+    for cluster in (11, 22, 12, 21):
+      h.set_option('gemm_cluster', cluster)
+      for a_mn, b_mn in ((False, False), (True, False), (True, True)):
+        for M, N, Kc in (shapes if cluster in (11, 22) else shapes[2:6]):
             for tile_n in (128, 176, 208, 256):
                 for splits in ((1, 3) if Kc >= 1024 else (1,)):
                     g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + Kc)
@@ -49,7 +51,7 @@ def gemm():
                     e = err.max().item()
                     ok = e < 2e-5
                     bad += 0 if ok else 1
-                    msg = 'a_mn=%d b_mn=%d M=%d N=%d K=%d tile %d splits %d: max err/|a||b| %.2e %s' % (a_mn, b_mn, M, N, Kc, tile_n, splits, e, 'ok' if ok else 'BAD')
+                    msg = 'cluster %d a_mn=%d b_mn=%d M=%d N=%d K=%d tile %d splits %d: max err/|a||b| %.2e %s' % (cluster, a_mn, b_mn, M, N, Kc, tile_n, splits, e, 'ok' if ok else 'BAD')
                     if not ok:
                         # structure of the error: which rows / columns are wrong
                         wrong = err > 2e-5
@@ -58,6 +60,7 @@ def gemm():
                         msg += ' | wrong %.1f%% rows %s.. cols %s.. | D[0,:4]=%s ref=%s' % (
                             100 * wrong.float().mean().item(), rows[:12], cols[:12], D[0, :4].tolist(), ref[0, :4].tolist())
                     print(msg, flush=True)
+    h.set_option('gemm_cluster', -1)
     print('gemm: %d bad' % bad)
     return 1 if bad else 0
 
@@ -119,22 +122,27 @@ def timing():
     V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
     W0, H0 = orc.initKLNMF(F, T2, K)
     W0d, H0d = h.to_device(W0), h.to_device(H0)
-    for name, tma, pdl, mf in (('loader', 0, 0, 0), ('tma', 1, 0, 0), ('tma+pdl', 1, 1, 0), ('tma+pdl+m_fastest', 1, 1, 1)):
+    for name, tma, pdl, cl in (('loader', 0, 0, -1), ('tma no pdl, auto clusters', 1, 0, -1), ('tma+pdl, no clusters', 1, 1, 11), ('tma+pdl, clusters 1x2', 1, 1, 12),
+                               ('tma+pdl, clusters 2x1', 1, 1, 21), ('tma+pdl, clusters 2x2', 1, 1, 22), ('tma+pdl, auto clusters', 1, 1, -1)):
         h.set_option('nmf_tma', tma)
         h.set_option('nmf_pdl', pdl)
-        h.set_option('gemm_m_fastest', mf)
+        h.set_option('gemm_cluster', cl)
+        t_cpu = 0.0
         ms = []
         for rep in range(4):
             W, H = W0d.clone(), H0d.clone()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            tc = time.perf_counter()
             h.klnmf(V, W, H, iters)
+            t_cpu = time.perf_counter() - tc
             e1.record()
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
-        print('KL-NMF config 2 (%s): %s ms per 100 iterations; W finite %s' % (name, ['%.2f' % m for m in ms], bool(torch.isfinite(W).all())), flush=True)
-    h.set_option('nmf_pdl', 0)
-    h.set_option('gemm_m_fastest', 0)
+        print('KL-NMF config 2 (%s): %s ms per 100 iterations (host time of the call %.2f ms); W finite %s' % (
+            name, ['%.2f' % m for m in ms], t_cpu * 1e3, bool(torch.isfinite(W).all())), flush=True)
+    h.set_option('nmf_pdl', 1)
+    h.set_option('gemm_cluster', -1)
     # per-GEMM CTA phase stamps
     g = torch.Generator(device='cpu').manual_seed(1)
     for (a_mn, b_mn, M, N, Kc, tile, splits, label) in ((0, 0, 513, 3744, 1024, 128, 1, 'G1/G3'), (1, 0, 1024, 3744, 513, 208, 1, 'G2'),
@@ -175,6 +183,9 @@ def stamps():
     V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
     W0, H0 = orc.initKLNMF(F, T2, K)
     h.set_option('nmf_tma', 1)
+    WH = int(os.environ.get('WH_TILE', '128'))
+    h.set_option('wh_tile', WH)
+    h.set_option('gemm_cluster', int(os.environ.get('GEMM_CLUSTER', '-1')))
     for pdl in (0, 1):
         h.set_option('nmf_pdl', pdl)
         W, H = h.to_device(W0), h.to_device(H0)
@@ -186,7 +197,8 @@ def stamps():
         torch.cuda.synchronize()
         used = h.lib.gccnmf_debug_timing(h.h, None, 1)
         s = buf.cpu().numpy()[:used].reshape(-1, 8)
-        grids = [('G1', 30 * 5, 120), ('G2', 18 * 8, 144), ('G3', 30 * 5, 120), ('G4', 3 * 8 * 6, 144)] * 3
+        nt = (T2 + WH - 1) // WH
+        grids = [('G1', nt * 4, 120), ('G2', 18 * 8, 144), ('G3', nt * 4, 120), ('G4', 3 * 8 * 6, 144)] * 3
         off, prev_end = 0, None
         print('pdl=%d: %d CTA records' % (pdl, len(s)))
         for name, ctas, tc in grids:
@@ -200,8 +212,6 @@ def stamps():
             cyc = lambda a, b: np.median((k[is_tc, b] - k[is_tc, a]))   # noqa: E731
             msg = '%s: span %.1f us | CTA start offset p50 %.1f max %.1f us | tc CTA dur p50 %.1f max %.1f us' % (
                 name, en.max() / 1e3, np.median(st) / 1e3, st.max() / 1e3, np.median(dur[is_tc]) / 1e3, dur[is_tc].max() / 1e3)
-            if (~is_tc).any():
-                msg += ' | tail CTA dur p50 %.1f max %.1f, last tail end %.1f us' % (np.median(dur[~is_tc]) / 1e3, dur[~is_tc].max() / 1e3, en[~is_tc].max() / 1e3)
             msg += ' | cycles: prologue %.0f, main %.0f, drain %.0f, epilogue %.0f' % (cyc(1, 2), cyc(2, 3), cyc(3, 5), cyc(5, 6))
             if prev_end is not None:
                 msg += ' | gap after previous GEMM %.1f us' % ((t0 - prev_end) / 1e3)
