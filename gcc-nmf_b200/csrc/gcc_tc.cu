@@ -28,6 +28,10 @@ using umma::GemmArgs;
 constexpr float kMarginFactor = 6e-5f;
 
 // ------------------------------------------------------------------ step 1: G[(t, tau)][f]
+// CTA = 32 bins x 32 frames x all TDOAs.  Warp w owns the TDOAs d = w, w + 8, ... ; lane = bin f, so every store is one
+// 128-byte row segment of G.  E[f][d] is loaded once per (thread, d) -- its rows are D * 16 bytes apart, so a warp's load
+// touches 32 lines: doing it inside the frame loop made the kernel L1-wavefront-bound (321 us for 247 MB) -- and reused for
+// the 32 frames of the tile, whose coherence values sit in shared memory.
 __global__ void __launch_bounds__(256)
 build_gcc_matrix_kernel(const float2* __restrict__ coh, int F, int T, const double2* __restrict__ E, int D, float* __restrict__ G, int64_t ldg) {
   __shared__ float2 Cs[32][33];   // [f][t]
@@ -39,18 +43,21 @@ build_gcc_matrix_kernel(const float2* __restrict__ coh, int F, int T, const doub
   }
   __syncthreads();
   const int f = f0 + lane;
-  // each warp handles frames w, w+8, ...; lane = f (coalesced 128-byte row segments of G)
-  for (int tt = w; tt < 32; tt += 8) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    const float2 c = Cs[lane][tt];
-    for (int d = 0; d < D; ++d) {
-      float v = 0.f;
-      if (f < F) {
-        const double2 e = __ldg(E + (int64_t)f * D + d);
-        v = (float)((double)c.x * e.x - (double)c.y * e.y);
-      }
-      if (f < ldg) G[((int64_t)t * D + d) * ldg + f] = v;
+  if (f >= ldg) return;
+  const int t_end = min(32, T - t0);
+  for (int d0 = w; d0 < D; d0 += 32) {            // 4 TDOAs per pass: d0, d0 + 8, d0 + 16, d0 + 24
+    double2 e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + 8 * j;
+      e[j] = (f < F && d < D) ? __ldg(E + (int64_t)f * D + d) : double2{0.0, 0.0};
+    }
+    for (int tt = 0; tt < t_end; ++tt) {
+      const float2 c = Cs[lane][tt];
+      float* row = G + ((int64_t)(t0 + tt) * D + d0) * ldg + f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (d0 + 8 * j < D) row[(int64_t)(8 * j) * ldg] = (float)((double)c.x * e[j].x - (double)c.y * e[j].y);
     }
   }
 }
@@ -95,6 +102,8 @@ __device__ __forceinline__ bool argmax_better64(double v, int i, double bv, int 
   return v > bv || (v == bv && i < bi);
 }
 
+// Reference version: one warp per flagged (atom, frame), lane = TDOA (+ 32 j), every bin's row of E read from L2 by every
+// warp (13 485 pairs x 513 rows x 1 KB = 7 GB of L2 reads at the headline shape: L2-bandwidth bound, 0.8 ms).
 __global__ void __launch_bounds__(256)
 refine_argmax_kernel(const int2* __restrict__ list, const int* __restrict__ count, int capacity, const float2* __restrict__ coh,
                      int F, int T, const double2* __restrict__ E, int D, const float* __restrict__ W, int K, int32_t* __restrict__ argmax) {
@@ -128,6 +137,79 @@ refine_argmax_kernel(const int2* __restrict__ list, const int* __restrict__ coun
       if (argmax_better64(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
     if (lane == 0) argmax[(int64_t)k * T + t] = bi;
+  }
+}
+
+
+// Same arithmetic (bin order, one fma per bin: the float64 kernel's), with E staged through shared memory in chunks of
+// kRefineChunk bins and shared by the CTA's 8 warps x 4 pairs per warp: 32 x less L2 traffic for E.  The (strided)
+// coherence and W values of a chunk are fetched by the lanes -- lane l < 16: coherence of bin l for the warp's 4 pairs,
+// lane 16 + l: W -- and broadcast with shuffles.
+constexpr int kRefineChunk = 16, kRefinePairs = 4;
+__global__ void __launch_bounds__(256)
+refine_argmax_shared_kernel(const int2* __restrict__ list, const int* __restrict__ count, int capacity, const float2* __restrict__ coh,
+                            int F, int T, const double2* __restrict__ E, int D, const float* __restrict__ W, int K, int32_t* __restrict__ argmax) {
+  __shared__ double2 Es[kRefineChunk][64];        // D <= 64
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = min(*count, capacity);
+  const int per_cta = 8 * kRefinePairs;
+  for (int base = blockIdx.x * per_cta; base < n; base += gridDim.x * per_cta) {      // (uniform per CTA: the barriers below are safe)
+    int pk[kRefinePairs], pt[kRefinePairs];
+#pragma unroll
+    for (int p = 0; p < kRefinePairs; ++p) {
+      const int idx = base + warp * kRefinePairs + p;
+      const int2 kt = idx < n ? list[idx] : make_int2(0, 0);
+      pk[p] = kt.x; pt[p] = kt.y;
+    }
+    double acc[kRefinePairs][2];
+#pragma unroll
+    for (int p = 0; p < kRefinePairs; ++p) { acc[p][0] = 0.0; acc[p][1] = 0.0; }
+    for (int f0 = 0; f0 < F; f0 += kRefineChunk) {
+      __syncthreads();                            // the previous chunk has been consumed
+      for (int i = threadIdx.x; i < kRefineChunk * 64; i += 256) {
+        const int fl = i >> 6, d = i & 63, f = f0 + fl;
+        Es[fl][d] = (f < F && d < D) ? __ldg(E + (int64_t)f * D + d) : double2{0.0, 0.0};
+      }
+      // lane l < 16: coherence of bin f0 + l; lane >= 16: W of bin f0 + l - 16 (both for the warp's 4 pairs)
+      const int fm = min(f0 + (lane & 15), F - 1);
+      float cx[kRefinePairs], cy[kRefinePairs];   // (for lanes >= 16, cx carries W)
+#pragma unroll
+      for (int p = 0; p < kRefinePairs; ++p) {
+        if (lane < 16) {
+          const float2 c = __ldg(coh + (int64_t)fm * T + pt[p]);
+          cx[p] = c.x; cy[p] = c.y;
+        } else {
+          cx[p] = __ldg(W + (int64_t)fm * K + pk[p]);
+          cy[p] = 0.f;
+        }
+      }
+      __syncthreads();
+      const int fcount = min(kRefineChunk, F - f0);
+      for (int fl = 0; fl < fcount; ++fl) {
+        const double2 e0 = Es[fl][lane], e1 = Es[fl][lane + 32];
+#pragma unroll
+        for (int p = 0; p < kRefinePairs; ++p) {
+          const double c_re = (double)__shfl_sync(0xffffffffu, cx[p], fl), c_im = (double)__shfl_sync(0xffffffffu, cy[p], fl);
+          const double wd = (double)__shfl_sync(0xffffffffu, cx[p], 16 + fl);
+          acc[p][0] = fma(c_re * e0.x - c_im * e0.y, wd, acc[p][0]);
+          acc[p][1] = fma(c_re * e1.x - c_im * e1.y, wd, acc[p][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kRefinePairs; ++p) {
+      double bv = acc[p][0];
+      int bi = lane;
+      if (lane + 32 < D && argmax_better64(acc[p][1], lane + 32, bv, bi)) { bv = acc[p][1]; bi = lane + 32; }
+      if (lane >= D) { bv = -INFINITY; bi = 1 << 30; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (argmax_better64(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      const int idx = base + warp * kRefinePairs + p;
+      if (lane == 0 && idx < n) argmax[(int64_t)pk[p] * T + pt[p]] = bi;
+    }
   }
 }
 
@@ -231,8 +313,13 @@ int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, c
   GemmArgs args{w.WT, w.G, K, N, F, w.Fp, w.Fp, (F + umma::kBK - 1) / umma::kBK, (K + umma::kBM - 1) / umma::kBM, nullptr, nullptr, 1};
   EpiArgmaxTDOA epi{argmax, w.colsum, w.list, w.count, w.capacity, K, T, D, N};
   if (int st = launch_argmax_gemm(h, args, epi, stream)) return st;
-  GCCNMF_LAUNCH(h, refine_argmax_kernel, h->sm_count * 4, 256, 0, stream, w.list, w.count, w.capacity,
-                reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, W, K, argmax);
+  if (h->argmax_refine_shared && D <= 64) {
+    GCCNMF_LAUNCH(h, refine_argmax_shared_kernel, h->sm_count * 4, 256, 0, stream, w.list, w.count, w.capacity,
+                  reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, W, K, argmax);
+  } else {
+    GCCNMF_LAUNCH(h, refine_argmax_kernel, h->sm_count * 4, 256, 0, stream, w.list, w.count, w.capacity,
+                  reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, W, K, argmax);
+  }
   // more near-ties than the list holds (never seen: the list holds 1/8 of all decisions): the caller must fall back
   if (overflow_flag) GCCNMF_CHECK_CUDA(h, cudaMemcpyAsync(overflow_flag, w.count, sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return GCCNMF_OK;

@@ -74,6 +74,7 @@ __device__ __forceinline__ void cluster_sync() {
 __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory");
@@ -182,6 +183,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
 //       per-row constants, fetched by one thread per row while the main loop runs and staged in shared memory
 //   struct State;   __device__ void init(State&, int m, const float* rowvals) const;    rowvals[i * 128 + 0..3] = value i of rows m .. m + 3
 //   struct Loaded;  __device__ Loaded load(int m, int n) const;          the column's global operands (issued kColumnsInFlight deep)
+//   static constexpr bool kPrefetch;  __device__ void prefetch(int m, int n) const;     L2 prefetch of the line load(m, n) will read
 //   __device__ void store(int m, int n, float4 acc, const Loaded&, int z, State&) const;
 //   static constexpr bool kRowReduce;  __device__ float4 row_partial(const State&) const;  __device__ void row_total(int m, int tile_n, float) const;
 //   __device__ void elem(int m, int n, float acc, int z) const;          SIMT tail rows (one column per lane)
@@ -330,9 +332,16 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
       for (int i = 0; i < Epilogue::kRowValues; ++i) rowvals[i * kBM + e * 32 + lane] = rv[i];
     }
+    if (Epilogue::kPrefetch) {
+      // pull the epilogue's global operands of this tile towards L2 while the main loop runs (they were last touched an
+      // iteration ago and have partly been evicted to HBM since): one prefetch per 128-byte line, 4 lines per column
+      const int n_valid = min(BN, args.N - n0);
+      if ((lane & 7) == 0)
+        for (int c = e; c < n_valid; c += kEpiWarps) epi.prefetch(m0 + 4 * lane, n0 + c);
+    }
     if (!A_MN && !B_MN && args.tail_rows > 0) {
       // Rows past the last full 128-row tile (F = 513 = 4 x 128 + 1), float32 SIMT from the K-major planes: the m tiles of
-      // this n tile share its columns (tail_cols each), each warp takes two columns per step, each lane 8 consecutive k per
+      // this n tile share its columns (tail_cols <= 256 each), each warp takes two columns per step, each lane 8 consecutive k per
       // 16-byte load (hi and lo plane), four k-chunks in flight.  The result of step i stays in lanes 2i / 2i + 1 and the
       // functor runs with one column per lane, so its global loads overlap.
       const int k_begin = kb_begin * KB, k_end = min(args.Kc, kb_end * KB);

@@ -89,3 +89,35 @@ def test_pretraining_call_site(golden, tmp_path):
     assert relerr(W, Wo) < 1e-4
     assert np.array_equal(pre.loadPretrainedW(12, str(tmp_path)), W)             # second call hits the .npy cache
     assert np.array_equal(pre.getOrderedDictionary(g['W']), g['orderedW'])
+
+
+def test_headless_realtime_runner(tmp_path):
+    """wav file -> blocks -> GCCNMFProcessor through the overlap-add ring, against the oracle
+    restatements of both (gccNMF/realtime/gccNMFProcessor.py:201-231, utils.py:99-116) driven with the same blocks."""
+    from scipy.io import wavfile
+    from gcc_nmf_b200.realtime.runRealtimeGCCNMF import (HEADLESS_TARGET_TDOA_INDEX, RealtimeGCCNMFNoGUI, float2pcm,
+                                                         getGCCNMFConfigParams, pcm2float)
+    rng = np.random.default_rng(21)
+    sr, N, hop, B, K, D = 16000, 256, 128, 256, 64, 32
+    n = 24 * B                              # whole blocks: no silent (0 / 0 in the PHAT normalisation) frames
+    s = rng.standard_normal(n + 8).astype(np.float32)
+    x = 0.2 * np.stack([s[4:4 + n], 0.8 * s[2:2 + n] + 0.05 * rng.standard_normal(n).astype(np.float32)])
+    src = str(tmp_path / 'in.wav')
+    wavfile.write(src, sr, float2pcm(np.ascontiguousarray(x.T)))
+    W = (rng.random((N // 2 + 1, K)) ** 3).astype(np.float32)
+    params = getGCCNMFConfigParams(src, dictionariesW={'Pretrained': {K: W}}, windowSize=N, hopSize=hop, blockSize=B, numTDOAs=D,
+                                   dictionarySize=K, dictionarySizes=[K], sampleRate=sr)
+    runner = RealtimeGCCNMFNoGUI(params=params)
+    xq = pcm2float(wavfile.read(src)[1]).T
+    out = runner.processSamples(xq, flush=False)
+    nT = B // hop
+    ref = orc.GCCNMFProcessorOracle(sr, N, nT, W, D, 0.1, localizationEnabled=True, localizationWindowSize=6)
+    ref.setTargetTDOARange(HEADLESS_TARGET_TDOA_INDEX, params.targetTDOAEpsilon, params.targetTDOABeta, params.targetTDOANoiseFloor)
+    ring = orc.OverlapAddProcessorOracle(2, N, hop, B, nT)
+    expect = np.concatenate([ring.processFrames(xq[:, b * B:(b + 1) * B].copy(), ref.processFrames) for b in range(n // B)], axis=1)
+    assert out.shape == expect.shape == (2, n)
+    assert float(runner.gccNMFProcessor.targetTDOAIndex) == float(ref.targetTDOAIndex)
+    assert np.isfinite(out).all()
+    assert relerr(out, expect) < 5e-3          # float32 restatement vs float64-argmax device path; near-ties may differ
+    assert len(runner.processingTimes) == n // B
+    print('headless runner: %d blocks, rel error %.2e, processing times (min/max/avg) %s' % (n // B, relerr(out, expect), runner.processingTimeStats()))
