@@ -29,8 +29,9 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(sampleRate=16000, windowSize=1024, hopSize=256, dictionarySize=1024, numTDOAs=64,
            numIterations=100, microphoneSeparationInMetres=0.1, duration_s=30.0)
-# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one KL-NMF iteration (profiles/r01c_ncu_full_nmf_kernels.csv)
-NMF_ITERATION_DRAM_BYTES = 111.9e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one KL-NMF iteration (profiles/r01e_ncu_full_nmf_kernels.csv,
+# ncu --set full --cache-control none inside the running loop: 36.0 MB of it is the H update re-reading / writing back H^T)
+NMF_ITERATION_DRAM_BYTES = 36.4e6
 METRIC = 'STFT frames/sec (1024-FFT, K=1024) full GCC-NMF pipeline'
 UNIT = 'frames/s'
 
@@ -285,7 +286,7 @@ def run_gpu(args):
                          'note': 'achieved = algorithmic flops (16 F K T per iteration, SURVEY.md 8d) / CUDA-event time of the NMF stage '
                                  'inside the step; float32-level parity needs 3 tensor-core products per algorithmic product (hi.hi + hi.lo '
                                  '+ lo.hi of a bf16 hi/lo split), so executed tensor flops are 3x: frac_executed is the tensor-pipe view; '
-                                 'traffic = DRAM bytes per iteration from the ncu --set full capture in profiles/ (cold-cache replay)'},
+                                 'traffic = DRAM bytes per iteration from the ncu --set full capture in profiles/ (--cache-control none: the L2 state of the running loop)'},
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(3.0)

@@ -28,7 +28,7 @@ def launches(src, dst):
         tot[name][1] += float(r[-1])
     total = sum(v[1] for v in tot.values())
     with open(dst, 'w') as f:
-        f.write('ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n\n')
+        f.write('ncu --metrics gpu__time_duration.sum --clock-control none (serialised: compare SHARES; see the file header in profiles/README.md for the cache-control mode)\n\n')
         f.write('%d launches, %.3f ms total\n\n| launches | total ms | share | avg us | kernel |\n|---|---|---|---|---|\n' % (sum(v[0] for v in tot.values()), total / 1e6))
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             f.write('| %d | %.3f | %.1f %% | %.1f | `%s` |\n' % (v[0], v[1] / 1e6, 100 * v[1] / total, v[1] / v[0] / 1e3, k[:150]))
