@@ -265,12 +265,20 @@ static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->fo
 static bool use_tma(const gccnmf_handle* h, int F, int T2, int K) {
   return use_tc(h, F, T2, K) && h->nmf_tma && h->nmf_split_bf16 && gccnmf_klnmf_tma_supported(F, T2, K);
 }
-#define gccnmf_klnmf_tc_prepare(h, V, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_prepare(h, V, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_prepare(h, V, F, T2, __VA_ARGS__))
-#define gccnmf_klnmf_tc_update_H(h, V, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_update_H(h, V, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_update_H(h, V, F, T2, __VA_ARGS__))
-#define gccnmf_klnmf_tc_partial_W(h, V, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_partial_W(h, V, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_partial_W(h, V, F, T2, __VA_ARGS__))
-#define gccnmf_klnmf_tc_apply_W(h, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_apply_W(h, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_apply_W(h, F, T2, __VA_ARGS__))
-#define gccnmf_klnmf_tc_finish(h, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_finish(h, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_finish(h, F, T2, __VA_ARGS__))
-#define gccnmf_klnmf_tc_pack_numer(h, F, T2, ...) (use_tma(h, F, T2, K) ? gccnmf_klnmf_tma_pack_numer(h, F, T2, __VA_ARGS__) : gccnmf_klnmf_tc_pack_numer(h, F, T2, __VA_ARGS__))
+// The two tensor-core implementations expose the same protocol; every call site below goes through this table.
+struct TensorCoreOps {
+  decltype(&gccnmf_klnmf_tc_prepare) prepare;
+  decltype(&gccnmf_klnmf_tc_update_H) update_H;
+  decltype(&gccnmf_klnmf_tc_partial_W) partial_W;
+  decltype(&gccnmf_klnmf_tc_apply_W) apply_W;
+  decltype(&gccnmf_klnmf_tc_finish) finish;
+  decltype(&gccnmf_klnmf_tc_pack_numer) pack_numer;
+};
+static const TensorCoreOps kLoaderOps = {gccnmf_klnmf_tc_prepare, gccnmf_klnmf_tc_update_H, gccnmf_klnmf_tc_partial_W,
+                                         gccnmf_klnmf_tc_apply_W, gccnmf_klnmf_tc_finish, gccnmf_klnmf_tc_pack_numer};
+static const TensorCoreOps kTmaOps = {gccnmf_klnmf_tma_prepare, gccnmf_klnmf_tma_update_H, gccnmf_klnmf_tma_partial_W,
+                                      gccnmf_klnmf_tma_apply_W, gccnmf_klnmf_tma_finish, gccnmf_klnmf_tma_pack_numer};
+static const TensorCoreOps& tc_ops(const gccnmf_handle* h, int F, int T2, int K) { return use_tma(h, F, T2, K) ? kTmaOps : kLoaderOps; }
 
 extern "C" {
 
@@ -297,7 +305,7 @@ int gccnmf_klnmf_begin(gccnmf_handle* h, const float* V, int F, int T2, const fl
   if (int st = check_dims(h, F, T2, K)) return st;
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream);
+  if (use_tc(h, F, T2, K)) return tc_ops(h, F, T2, K).prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream);
   return GCCNMF_OK;
 }
 
@@ -310,10 +318,10 @@ int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, int T2, con
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (use_tc(h, F, T2, K)) {
-    if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0,
+    if (int st = tc_ops(h, F, T2, K).update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0,
                                           iteration > 0, stream)) return st;
-    if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
-    return gccnmf_klnmf_tc_pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
+    if (int st = tc_ops(h, F, T2, K).partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+    return tc_ops(h, F, T2, K).pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   if (int st = update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, false, stream)) return st;
@@ -327,7 +335,7 @@ int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H,
   GCCNMF_REQUIRE(h, numer != nullptr, "klnmf_step_apply: NULL numerator");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, numer, false, workspace, workspace_bytes, stream);
+  if (use_tc(h, F, T2, K)) return tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, numer, false, workspace, workspace_bytes, stream);
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   return apply_W_impl(h, F, T2, W, H, K, numer, w, stream);
 }
@@ -341,7 +349,7 @@ int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, 
   if (!use_tc(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_apply_multimem: only the tensor-core path reads the numerator through multimem");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  return gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, numer_multicast, true, workspace, workspace_bytes, stream);
+  return tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, numer_multicast, true, workspace, workspace_bytes, stream);
 }
 
 int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,
@@ -349,7 +357,7 @@ int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
   if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (int st = check_dims(h, F, T2, K)) return st;
   (void)W;
-  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tc_finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream);
+  if (use_tc(h, F, T2, K)) return tc_ops(h, F, T2, K).finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream);
   return GCCNMF_OK;
 }
 
@@ -362,17 +370,17 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (iterations == 0) return GCCNMF_OK;
   if (use_tc(h, F, T2, K)) {
-    if (int st = gccnmf_klnmf_tc_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
+    if (int st = tc_ops(h, F, T2, K).prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
     for (int it = 0; it < iterations; ++it) {
       // colsum(W) comes out of the previous W update; with a fixed dictionary it is computed once
       // and the H *= norms of :81 stays pending: the next iteration's G1 loader and G2 epilogue apply it
-      if (int st = gccnmf_klnmf_tc_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes,
+      if (int st = tc_ops(h, F, T2, K).update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes,
                                             it == 0 ? 0 : (update_W ? 2 : 1), update_W && it > 0, stream)) return st;
       if (!update_W) continue;
-      if (int st = gccnmf_klnmf_tc_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
-      if (int st = gccnmf_klnmf_tc_apply_W(h, F, T2, W, K, nullptr, false, workspace, workspace_bytes, stream)) return st;
+      if (int st = tc_ops(h, F, T2, K).partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+      if (int st = tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, nullptr, false, workspace, workspace_bytes, stream)) return st;
     }
-    return gccnmf_klnmf_tc_finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream);
+    return tc_ops(h, F, T2, K).finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   for (int it = 0; it < iterations; ++it) {

@@ -1,0 +1,140 @@
+"""GPU: the TMA-fed plane GEMM (gcc-nmf_b200/csrc/tma_gemm.cuh) -- every operand layout (K-major / MN-major), tile width,
+k-split and cluster shape against a float64 product -- and the KL-NMF path built on it (klnmf_tma.cu) against the
+loader-based path and the oracle, with the cluster shape forced both ways."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def h():
+    from gcc_nmf_b200._lib import default_handle
+    hd = default_handle()
+    yield hd
+    hd.set_option('gemm_cluster', -1)
+    hd.set_option('nmf_tma', 1)
+    hd.set_option('nmf_pdl', 1)
+
+
+def _gemm_error(h, M, N, Kc, a_mn, b_mn, tile_n, splits):
+    import torch
+    g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + Kc)
+    A = torch.randn(M, Kc, generator=g).to(h.device)
+    B = torch.rand(N, Kc, generator=g).to(h.device)
+    Ain = A.T.contiguous() if a_mn else A
+    Bin = B.T.contiguous() if b_mn else B
+    DT = h.gemm_planes(Ain, Bin, a_mn, b_mn, tile_n=tile_n, splits=splits)
+    torch.cuda.synchronize()
+    D = DT.sum(0).T.double()
+    ref = A.double() @ B.double().T
+    scale = A.abs().double() @ B.abs().double().T      # |a|.|b| bound for the error
+    return ((D - ref).abs() / scale).max().item()
+
+
+# (M, N, Kc): one full tile; ragged everything (rows past the tiles, k tail, n tail); the three KL-NMF contraction shapes
+# scaled down (M = 513 keeps the 513th-row SIMT tail, Kc = 513 the one-step k tail)
+SHAPES = [(128, 128, 64), (200, 130, 70), (513, 640, 256), (256, 416, 513), (256, 513, 1024)]
+
+
+@pytest.mark.parametrize('cluster', [11, 22, 12, 21])
+@pytest.mark.parametrize('layout', [(False, False), (True, False), (True, True)])
+def test_plane_gemm_matches_float64(h, layout, cluster):
+    """3 x bf16 products per algorithmic product: error <= 2^-17 per product (sign-symmetric) plus the truncating
+    float32 TMEM accumulator (~4e-8 per accumulation, coherent for all-positive data)."""
+    a_mn, b_mn = layout
+    h.set_option('gemm_cluster', cluster)      # 10 CN + CM; falls back to no cluster when it does not divide the tile grid
+    try:
+        for M, N, Kc in SHAPES:
+            for tile_n in (128, 176, 208, 256):
+                for splits in ((1, 3) if Kc >= 1024 else (1,)):
+                    err = _gemm_error(h, M, N, Kc, a_mn, b_mn, tile_n, splits)
+                    bound = 8e-6 + 4e-8 * (3 * Kc / 16)
+                    assert err < bound, (layout, cluster, (M, N, Kc), tile_n, splits, err, bound)
+    finally:
+        h.set_option('gemm_cluster', -1)
+
+
+def test_plane_gemm_rejects_bad_arguments(h):
+    import torch
+    from gcc_nmf_b200._lib import GCCNMFError, ParameterError
+    A = torch.rand(128, 64, device=h.device)
+    B = torch.rand(128, 64, device=h.device)
+    with pytest.raises(GCCNMFError):
+        h.gemm_planes(A, B, tile_n=100)                     # unsupported tile width
+    with pytest.raises(ParameterError):
+        h.gemm_planes(A, B, splits=99)                      # more k-splits than partial slabs
+    with pytest.raises(GCCNMFError):
+        h.gemm_planes(A, B.T.contiguous(), False, True)     # K-major A with MN-major B is not instantiated
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize('cluster', [-1, 11, 22])
+def test_klnmf_tma_path_matches_loader_path_and_oracle(h, cluster):
+    """F = 257 = 2 x 128 + 1 exercises the SIMT tail row; T2 = 512 and K = 256 give even tile grids, so the forced 2 x 2
+    cluster shape really runs the multicast paths of all four contractions."""
+    import torch
+    from oracle import gccnmf_oracle as orc
+    F, T2, K = 257, 512, 256
+    assert h.lib.gccnmf_klnmf_uses_tensor_cores(h.h, F, T2, K) == 1
+    rng = np.random.default_rng(9)
+    V = (rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32)
+    W0, H0 = orc.initKLNMF(F, T2, K)
+    Vd = h.to_device(V)
+    h.set_option('gemm_cluster', cluster)
+    try:
+        out = {}
+        for name, tma, pdl in (('loader', 0, 1), ('tma', 1, 1), ('tma_nopdl', 1, 0)):
+            h.set_option('nmf_tma', tma)
+            h.set_option('nmf_pdl', pdl)
+            for iters in (1, 25):
+                W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
+                h.klnmf(Vd, W, H, iters)
+                torch.cuda.synchronize()
+                out[name, iters] = (W.cpu().numpy(), H.cpu().numpy())
+        Wo, Ho = orc.performKLNMF(V, K, 25, 0, W0=W0, H0=H0)
+        for name in ('loader', 'tma', 'tma_nopdl'):
+            eW, eH = _rel(out[name, 25][0], Wo), _rel(out[name, 25][1], Ho)
+            print('KL-NMF %s cluster %d, 25 iterations: rel W %.2e rel H %.2e' % (name, cluster, eW, eH))
+            assert eW < 1e-4 and eH < 1e-4, (name, cluster, eW, eH)
+        # one iteration: both tensor-core paths compute the same three products, only rounding-level differences remain
+        assert _rel(out['tma', 1][0], out['loader', 1][0]) < 5e-6 and _rel(out['tma', 1][1], out['loader', 1][1]) < 5e-6
+        # programmatic dependent launch changes the schedule, not the arithmetic
+        assert np.array_equal(out['tma', 25][0], out['tma_nopdl', 25][0]) and np.array_equal(out['tma', 25][1], out['tma_nopdl', 25][1])
+        # sparsity (alpha > 0) goes through the per-row reciprocal of the H update
+        h.set_option('nmf_tma', 1)
+        h.set_option('nmf_pdl', 1)
+        W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
+        h.klnmf(Vd, W, H, 5, sparsity_alpha=0.3)
+        Wa, Ha = orc.performKLNMF(V, K, 5, 0.3, W0=W0, H0=H0)
+        assert _rel(W.cpu().numpy(), Wa) < 2e-5 and _rel(H.cpu().numpy(), Ha) < 2e-5
+    finally:
+        h.set_option('gemm_cluster', -1)
+        h.set_option('nmf_tma', 1)
+        h.set_option('nmf_pdl', 1)
+
+
+def test_debug_timing_records_every_cta(h):
+    """gccnmf_debug_timing: 8 stamps per CTA of every plane GEMM launched while it is armed."""
+    import torch
+    from oracle import gccnmf_oracle as orc
+    F, T2, K = 257, 640, 128
+    rng = np.random.default_rng(2)
+    V = h.to_device((rng.random((F, T2)) + 1e-3).astype(np.float32))
+    W0, H0 = orc.initKLNMF(F, T2, K)
+    W, H = h.to_device(W0), h.to_device(H0)
+    buf = torch.zeros(1 << 18, dtype=torch.int64, device=h.device)
+    h.lib.gccnmf_debug_timing(h.h, buf.data_ptr(), 1)
+    try:
+        h.klnmf(V, W, H, 1)
+        torch.cuda.synchronize()
+    finally:
+        used = h.lib.gccnmf_debug_timing(h.h, None, 1)
+    assert used > 0 and used % 8 == 0
+    s = buf.cpu().numpy()[:used].reshape(-1, 8)
+    assert (s[:, 0] > 0).all() and (s[:, 7] >= s[:, 0]).all()          # %globaltimer at CTA start / end
+    assert (s[:, 6] > s[:, 1]).all()                                    # clock64: epilogue end after kernel entry
+    assert h.lib.gccnmf_debug_timing(h.h, None, 1) == 0                 # disarmed and rewound
