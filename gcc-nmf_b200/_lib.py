@@ -68,6 +68,7 @@ SIGNATURES = {
     'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
     'gccnmf_gemm_tn_3xtf32': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _S]),
     'gccnmf_debug_timing': (c_int64, [_H, _P, c_int]),
+    'gccnmf_klnmf_tile_plan': (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int)]),
     'gccnmf_gemm_planes_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_gemm_planes': (c_int, [_H, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _S]),
     'gccnmf_gemm_tn_3xtf32_timed': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _S]),

@@ -829,6 +829,23 @@ int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* n
 
 extern "C" {
 
+// The tile plan of the TMA KL-NMF path for a device with `sm_count` SMs (pure host logic, no device needed):
+// out[0] tile width of the W.H contractions, out[1] of the H update, out[2] / out[3] tile width / k-splits of the W-update
+// numerator, out[4] row-sum slots (n tiles of the H update), out[5..7] CTAs of G1/G3, G2, G4.  Returns 0, or < 0 when the
+// shape is not covered by the TMA path.
+int gccnmf_klnmf_tile_plan(int sm_count, int F, int T2, int K, int* out) {
+  if (!out || sm_count <= 0 || F <= 0 || T2 <= 0 || K <= 0) return GCCNMF_ERR_INVALID_ARGUMENT;
+  if (!gccnmf_klnmf_tma_supported(F, T2, K)) return GCCNMF_ERR_UNSUPPORTED;
+  gccnmf_handle h;
+  h.sm_count = sm_count;
+  const Plan p = make_plan(&h, F, T2, K);
+  out[0] = p.bn_wh; out[1] = p.bn_h; out[2] = p.w.bn; out[3] = p.w.splits; out[4] = p.rowsum_slots;
+  out[5] = m_tiles_of(F, true) * ((T2 + p.bn_wh - 1) / p.bn_wh);
+  out[6] = m_tiles_of(K, false) * ((T2 + p.bn_h - 1) / p.bn_h);
+  out[7] = m_tiles_of(K, false) * ((F + p.w.bn - 1) / p.w.bn) * p.w.splits;
+  return GCCNMF_OK;
+}
+
 // Diagnostics: while `stamps` is non-NULL every plane GEMM launched through this handle appends 8 uint64 per CTA
 // (see tma_gemm.cuh) at a running offset; returns the offset (in uint64) reached so far and resets it when asked.
 int64_t gccnmf_debug_timing(gccnmf_handle* h, unsigned long long* stamps, int reset) {

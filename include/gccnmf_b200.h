@@ -241,6 +241,10 @@ GCCNMF_API int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int
  *   tile_n in {128, 176, 208, 256};  splits > 1: `splits` partial slabs DT[z] over k ranges (N * M floats each).
  *   timing: device uint64[8 x CTAs] stamps (layout: gccnmf_debug_timing) or NULL.
  */
+/* Tile plan of the KL-NMF loop on a device with sm_count SMs (host logic only; callable without a GPU):
+ * out[0] tile width of the W.H contractions, out[1] of the H update, out[2] / out[3] tile width / k-splits of the W-update
+ * numerator, out[4] n tiles of the H update, out[5..7] CTAs of the three launches.  < 0: shape not covered by this path. */
+GCCNMF_API int gccnmf_klnmf_tile_plan(int sm_count, int F, int T2, int K, int* out);
 GCCNMF_API size_t gccnmf_gemm_planes_workspace_bytes(int M, int N, int Kc);
 /* Diagnostics: while `stamps` (device uint64) is non-NULL every plane GEMM launched through the handle appends 8 values
  * per CTA at a running offset: [0] / [7] %globaltimer ns at CTA start / end, [1..6] clock64 at start, first stage full,
