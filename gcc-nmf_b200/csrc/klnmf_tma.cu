@@ -509,13 +509,13 @@ struct GemmShape {
 };
 
 // One instantiation: kernel attributes + how many of its clusters can be resident at once (queried once).
-template <int BN, bool A_MN, bool B_MN, int CN, int CM, class Epi>
+template <int BN, bool A_MN, bool B_MN, int CN, int CM, class Epi, bool PAIR = false>
 struct PlaneGemmInstance {
-  using C = tgemm::Config<BN, kKB, A_MN, B_MN>;
+  using C = tgemm::Config<BN, kKB, A_MN, B_MN, PAIR ? 2 : 1>;
   static int max_clusters(gccnmf_handle* h, int* out) {
     static int cached = -1;
     if (cached < 0) {
-      auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, Epi>;
+      auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, PAIR, Epi>;
       GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
       if (CN * CM == 1) {
         cached = h->sm_count;
@@ -538,7 +538,7 @@ struct PlaneGemmInstance {
     return 0;
   }
   static int launch(gccnmf_handle* h, const Operand& A, const Operand& B, const GemmShape& g, const Epi& epi, unsigned long long* timing, void* stream) {
-    auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, Epi>;
+    auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, PAIR, Epi>;
     int unused;
     if (int st = max_clusters(h, &unused)) return st;     // (sets the shared-memory attribute on first use)
     CUtensorMap map_a, map_b;
@@ -581,6 +581,18 @@ int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int 
   g.tail_rows = use_tail ? tail : 0;
   g.n_tiles = (N + BN - 1) / BN;
   const int ctas = g.n_tiles * g.m_tiles * splits;
+  if (h->gemm_pair) {
+    // cta_group::2 CTA pairs (two m tiles issue one 256 x BN MMA, each holding half of B): compiled, NOT yet validated on
+    // hardware -- reachable only through set_option("gemm_pair", 1), never chosen automatically.
+    constexpr bool kPairOk = B_MN ? (BN % 128 == 0) : ((BN / 2) % 8 == 0);
+    if constexpr (kPairOk) {
+      if (g.m_tiles % 2 == 0) {
+        int resident = 0;
+        if (int st = PlaneGemmInstance<BN, A_MN, B_MN, 1, 2, Epi, true>::max_clusters(h, &resident)) return st;
+        if (resident > 0) return PlaneGemmInstance<BN, A_MN, B_MN, 1, 2, Epi, true>::launch(h, A, B, g, epi, timing, stream);
+      }
+    }
+  }
   // Measured at the headline shape: sharing the B tile of the H update (208 K-major rows, pairs of m tiles) cuts its main
   // loop by 25 %; 128 x 128 tiles and the MN-major k-split contraction do not gain (their loops sit at the shared-memory
   // port limit, not at the L2 -> SM limit) and lose a little to the lock-step of the cluster.

@@ -67,6 +67,34 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster (ranks 0 / 1 = even / odd m tile) issue ONE 256 x BN MMA; each holds its
+// own 128 rows of A and half of the B tile.  NOT YET RUN ON HARDWARE ("next").
+// The leader's (even rank) barrier as seen from either CTA of the pair: clear the peer bit of the shared-window address.
+__device__ __forceinline__ uint32_t pair_leader_addr(uint32_t smem_addr) { return smem_addr & 0xFEFFFFFFu; }
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {     // arrives on the barrier at this offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -143,7 +171,7 @@ struct PlaneGemmArgs {
                                 // [1..6] clock64: start, first stage full, last MMA issued, producer done, accumulator complete, epilogue end
 };
 
-template <int BN, int KB, bool A_MN, bool B_MN>
+template <int BN, int KB, bool A_MN, bool B_MN, int BDIV = 1>     // BDIV = 2: CTA pair (cta_group::2), each CTA holds half of the B tile
 struct Config {
   static_assert(KB == 32 || KB == 64, "k-block of 32 (SWIZZLE_64B K-major rows) or 64 (SWIZZLE_128B)");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
@@ -151,7 +179,8 @@ struct Config {
   static constexpr int kBAtoms = (BN + 63) / 64;
   static constexpr int kAtomBytes = 2 * KB * 128;                 // one MN-major atom: 64 elements x KB k-rows x 2 planes
   static constexpr int kABytes = 2 * kBM * KB * 2;                // both layouts: 512 KB
-  static constexpr int kBBytes = B_MN ? kBAtoms * kAtomBytes : 2 * BN * KB * 2;
+  static_assert(BDIV == 1 || (B_MN ? kBAtoms % 2 == 0 : (BN / 2) % 8 == 0), "a CTA pair splits the B tile into two halves of whole swizzle atoms");
+  static constexpr int kBBytes = (B_MN ? kBAtoms * kAtomBytes : 2 * BN * KB * 2) / BDIV;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "operand blocks must keep 1024-byte alignment");
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
@@ -187,11 +216,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
 //   __device__ void store(int m, int n, float4 acc, const Loaded&, int z, State&) const;
 //   static constexpr bool kRowReduce;  __device__ float4 row_partial(const State&) const;  __device__ void row_total(int m, int tile_n, float) const;
 //   __device__ void elem(int m, int n, float acc, int z) const;          SIMT tail rows (one column per lane)
-template <int BN, int KB, bool A_MN, bool B_MN, int CN, int CM, class Epilogue>
+template <int BN, int KB, bool A_MN, bool B_MN, int CN, int CM, bool PAIR, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
 plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, PlaneGemmArgs args, Epilogue epi) {
-  using C = Config<BN, KB, A_MN, B_MN>;
+  using C = Config<BN, KB, A_MN, B_MN, PAIR ? 2 : 1>;
   constexpr int kCluster = CN * CM;
+  static_assert(!PAIR || (CN == 1 && CM == 2), "a CTA pair is a 1 x 2 cluster (two m tiles)");
   static_assert((CN == 1 || CN == 2) && (CM == 1 || CM == 2), "cluster of CN n-tiles x CM m-tiles");
   static_assert(A_MN || (kBM / CN) % 8 == 0, "A row slices keep the swizzle atoms whole");
   static_assert(B_MN || (BN / CM) % 8 == 0, "B row slices keep the swizzle atoms whole");
@@ -230,14 +260,17 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (tid == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), CN + CM - 1);     // one release per CTA whose multicast lands in this stage (incl. myself)
+      mbar_init(smem_u32(&empty[s]), PAIR ? 1 : CN + CM - 1);     // one release per CTA whose multicast lands in this stage (incl. myself); pair: the leader's commit
     }
     mbar_init(smem_u32(accum_full), 1);
     umma::fence_barrier_init();
     tma_prefetch_descriptor(&map_a);
     tma_prefetch_descriptor(&map_b);
   }
-  if (warp == 1) umma::tmem_alloc(smem_u32(tmem_base_slot), C::kTmemCols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(smem_u32(tmem_base_slot), C::kTmemCols);
+    else umma::tmem_alloc(smem_u32(tmem_base_slot), C::kTmemCols);
+  }
   umma::tc_fence_before_sync();
   if (kCluster > 1) cluster_sync();     // no peer may signal my barriers or write my stages before they are initialised
   else __syncthreads();
@@ -256,9 +289,32 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t use = i / C::kStages;
         if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);   // the MMAs (mine and my peers') that read this stage have retired
         const uint32_t bar = smem_u32(&full[s]);
-        mbar_arrive_expect_tx(bar, C::kStageBytes);                    // my slices + the ones my peers multicast to me
         const uint32_t a_dst = smem_u32(smem + (size_t)s * C::kStageBytes), b_dst = a_dst + C::kABytes;
         const int k0 = (kb_begin + i) * KB;
+        if constexpr (PAIR) {
+          // both CTAs of the pair fill their own stage and signal the LEADER's barrier, which expects the bytes of both
+          const uint32_t leader_bar = pair_leader_addr(bar);
+          if (cy == 0) mbar_arrive_expect_tx(bar, 2 * C::kStageBytes);
+          if (A_MN) {
+#pragma unroll
+            for (int a = 0; a < C::kAAtoms; ++a) tma_load_3d_pair(a_dst + a * C::kAtomBytes, &map_a, leader_bar, m0 + 64 * a, k0, 0);
+          } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) tma_load_3d_pair(a_dst + p * (kBM * KB * 2), &map_a, leader_bar, k0, m0, p);
+          }
+          if (B_MN) {
+            constexpr int kHalfAtoms = C::kBAtoms / 2;
+#pragma unroll
+            for (int a = 0; a < kHalfAtoms; ++a)
+              tma_load_3d_pair(b_dst + a * C::kAtomBytes, &map_b, leader_bar, n0 + 64 * (cy * kHalfAtoms + a), k0, 0);
+          } else {
+            constexpr int kRows = BN / 2;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) tma_load_3d_pair(b_dst + p * (kRows * KB * 2), &map_b, leader_bar, k0, n0 + cy * kRows, p);
+          }
+          continue;
+        }
+        mbar_arrive_expect_tx(bar, C::kStageBytes);                    // my slices + the ones my peers multicast to me
         if (A_MN) {
 #pragma unroll
           for (int a = 0; a < C::kAAtoms; ++a)
@@ -285,11 +341,11 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    if (lane == 0 && (!PAIR || cy == 0)) {      // pair: the leader issues for both CTAs
+      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN) + (PAIR ? ((uint32_t)(kBM >> 4) << 24) : 0u);   // pair: M = 256
       // plane offsets inside an operand block and the per-k16 start-address advance
       constexpr uint32_t a_lo_off = A_MN ? KB * 128 : kBM * KB * 2;
-      constexpr uint32_t b_lo_off = B_MN ? KB * 128 : BN * KB * 2;
+      constexpr uint32_t b_lo_off = B_MN ? KB * 128 : (BN / (PAIR ? 2 : 1)) * KB * 2;
       constexpr uint32_t a_step = A_MN ? 2048u : 32u, b_step = B_MN ? 2048u : 32u;
       const uint16_t mask_release = mask_row | mask_col;
       for (int i = 0; i < num_kb; ++i) {
@@ -308,16 +364,26 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint64_t a_lo = A_MN ? make_desc(a_addr + a_lo_off, C::kAtomBytes, 1024, 2) : make_desc(a_addr + a_lo_off, 16, C::kKSbo, C::kKLayout);
             const uint64_t b_hi = B_MN ? make_desc(b_addr, C::kAtomBytes, 1024, 2) : make_desc(b_addr, 16, C::kKSbo, C::kKLayout);
             const uint64_t b_lo = B_MN ? make_desc(b_addr + b_lo_off, C::kAtomBytes, 1024, 2) : make_desc(b_addr + b_lo_off, 16, C::kKSbo, C::kKLayout);
-            umma::mma_bf16(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
-            umma::mma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
-            umma::mma_bf16(tmem_base, a_hi, b_hi, idesc, 1);
+            if constexpr (PAIR) {
+              mma_bf16_pair(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
+              mma_bf16_pair(tmem_base, a_hi, b_lo, idesc, 1);
+              mma_bf16_pair(tmem_base, a_hi, b_hi, idesc, 1);
+            } else {
+              umma::mma_bf16(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
+              umma::mma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+              umma::mma_bf16(tmem_base, a_hi, b_hi, idesc, 1);
+            }
           }
         }
         // stage reusable once these MMAs retire: tell every CTA whose multicast lands in it
-        if (kCluster > 1) mma_commit_multicast(smem_u32(&empty[s]), mask_release);
+        if (PAIR) mma_commit_pair(smem_u32(&empty[s]));
+        else if (kCluster > 1) mma_commit_multicast(smem_u32(&empty[s]), mask_release);
         else umma::mma_commit(smem_u32(&empty[s]));
       }
-      if (num_kb > 0) umma::mma_commit(smem_u32(accum_full));
+      if (num_kb > 0) {
+        if (PAIR) mma_commit_pair(smem_u32(accum_full));
+        else umma::mma_commit(smem_u32(accum_full));
+      }
       if (args.timing) args.timing[cta_linear * 8 + 3] = clock64();
     }
     __syncwarp();
@@ -462,7 +528,8 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (args.timing && tid == 0) args.timing[cta_linear * 8 + 7] = globaltimer_ns();
   if (warp == 1) {
     umma::tc_fence_after_sync();
-    umma::tmem_dealloc(tmem_base, C::kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else umma::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 

@@ -1,6 +1,8 @@
 """GPU: the TMA-fed plane GEMM (gcc-nmf_b200/csrc/tma_gemm.cuh) -- every operand layout (K-major / MN-major), tile width,
 k-split and cluster shape against a float64 product -- and the KL-NMF path built on it (klnmf_tma.cu) against the
 loader-based path and the oracle, with the cluster shape forced both ways."""
+import os
+
 import numpy as np
 import pytest
 
@@ -138,3 +140,19 @@ def test_debug_timing_records_every_cta(h):
     assert (s[:, 0] > 0).all() and (s[:, 7] >= s[:, 0]).all()          # %globaltimer at CTA start / end
     assert (s[:, 6] > s[:, 1]).all()                                    # clock64: epilogue end after kernel entry
     assert h.lib.gccnmf_debug_timing(h.h, None, 1) == 0                 # disarmed and rewound
+
+
+@pytest.mark.skipif(os.environ.get('GCCNMF_TEST_EXPERIMENTAL') != '1',
+                    reason='cta_group::2 CTA-pair kernel: compiled, not yet validated on hardware (set GCCNMF_TEST_EXPERIMENTAL=1)')
+@pytest.mark.parametrize('layout', [(False, False), (True, False), (True, True)])
+def test_plane_gemm_cta_pairs_experimental(h, layout):
+    """set_option('gemm_pair', 1): two m tiles issue one 256 x BN tcgen05.mma.cta_group::2, each CTA holding half of B."""
+    a_mn, b_mn = layout
+    h.set_option('gemm_pair', 1)
+    try:
+        for M, N, Kc in [(256, 256, 64), (512, 640, 256), (256, 416, 513), (1024, 513, 1024)]:
+            for tile_n in ((128, 256) if b_mn else (128, 176, 208, 256)):
+                err = _gemm_error(h, M, N, Kc, a_mn, b_mn, tile_n, 1)
+                assert err < 8e-6 + 4e-8 * (3 * Kc / 16), (layout, (M, N, Kc), tile_n, err)
+    finally:
+        h.set_option('gemm_pair', 0)
