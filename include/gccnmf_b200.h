@@ -57,8 +57,16 @@ GCCNMF_API const char* gccnmf_last_error(const gccnmf_handle* h);
 GCCNMF_API const char* gccnmf_status_string(int status);
 /* Count of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 GCCNMF_API int64_t gccnmf_launch_count(const gccnmf_handle* h);
-/* Options: "force_simt_nmf" (0/1): run the KL-NMF contractions on the float32 SIMT kernels even where the
- * tcgen05 path applies (all ranks of a sharded run must use the same path so that W stays bit-identical). */
+/* Options (A/B switches between sm_100a code paths of this library; all ranks of a sharded run must use the same ones so
+ * that W stays bit-identical).  Defaults in brackets.
+ *   "force_simt_nmf" [0]        KL-NMF contractions on the float32 SIMT kernels even where the tcgen05 paths apply
+ *   "nmf_tma" [1]               KL-NMF on the TMA-fed plane GEMM (bf16 hi/lo operand planes); 0 = loader-based tcgen05 kernel
+ *   "nmf_split_bf16" [1]        3xBF16 operand split; 0 = 3xTF32 (loader-based kernel only)
+ *   "nmf_pdl" [1]               programmatic dependent launch between the kernels of a KL-NMF iteration
+ *   "gemm_cluster" [-1]         plane GEMM cluster shape 10 CN + CM (11, 12, 21, 22) instead of the automatic choice
+ *   "argmax_refine_shared" [1]  float64 refinement of near-tie argmax decisions with E staged in shared memory
+ *   "wh_tile" [0]               tile width of the W.H contractions (128 / 256) instead of the planned one
+ *   "gemm_pair" [0]             EXPERIMENTAL (not validated on hardware): plane GEMM on cta_group::2 CTA pairs */
 GCCNMF_API int gccnmf_set_option(gccnmf_handle* h, const char* name, int value);
 
 /* ---- a1: STFT  (gccNMF/librosaSTFT.py:20-181 via gccNMFFunctions.py:61-67) ------------------ */
