@@ -17,7 +17,8 @@
 // The rescaling H *= n (:81) is applied lazily: G1 contracts (W * n) with the unscaled H^T -- the W update writes the
 // planes of fl(W * n) next to those of W -- and G2's epilogue multiplies the old H by n (the reference's own float32
 // product), so the 30 MB of H^T are not rewritten every iteration; the last rescale happens in finish().
-// F = 513 = 4 x 128 + 1: the row past the last full 128-row tile of G1 / G3 is computed by SIMT CTAs of the same launch.
+// F = 513 = 4 x 128 + 1: the row past the last full 128-row tile of G1 / G3 is computed in float32 SIMT by the tile CTAs'
+// epilogue warps while the main loop runs.
 // Tile widths are chosen per contraction so that one wave fills the 148 SMs (G2: 8 x 18 tiles of 128 x 208 = 144 CTAs;
 // G4: 8 x 3 tiles of 128 x 176 x 6 k-splits = 144 CTAs at the headline shape).
 #include <algorithm>

@@ -4,8 +4,8 @@
 //
 // Each operand lives in global memory as TWO bf16 planes [2][rows][pitch] written by the kernel that produced it
 // (the KL-NMF epilogues / the W update), in ONE orientation; the contraction picks the matching shared-memory layout:
-//   K-major  : element (r, k) at rows r, k contiguous        TMA box {KB, rows, 2}   UMMA descriptor K-major
-//   MN-major : element (r, k) at rows k, r contiguous        TMA boxes {64, KB, 2}   UMMA descriptor MN-major, SWIZZLE_128B
+//   K-major  : element (r, k) at rows r, k contiguous        TMA boxes {KB, rows / cluster extent, 1 plane}, SWIZZLE_64B rows
+//   MN-major : element (r, k) at rows k, r contiguous        TMA boxes {64, KB, 2 planes} = 64-wide atoms, SWIZZLE_128B
 // so no matrix is ever transposed or re-split inside the loop (the loader-based kernel in umma_gemm.cuh converted
 // float32 operands on the fly: 32 KB of L2->SM traffic and 32 KB of shared-memory stores per k-block per CTA, its limiter).
 // Three tcgen05.mma.kind::f16 products per 16-deep k-step (lo.hi + hi.lo + hi.hi) accumulate in float32 TMEM.
@@ -16,8 +16,9 @@
 //   warps 2-9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> shared tile -> functor by columns (all 10 warps)
 // Rows past the last full 128-row tile (F = 513 = 4 x 128 + 1) are computed in float32 SIMT by the epilogue warps while
 // they wait for the accumulator.  A cluster of CN x CM CTAs (n tiles x m tiles) shares operand tiles: each CTA loads 1 / CN
-// of its A tile and 1 / CM of its B tile and TMA-multicasts the slice to the CTAs of its cluster row / column (the loop is
-// L2 -> SM bandwidth bound: 2 x 2 clusters halve that traffic).
+// of its A tile and 1 / CM of its B tile and TMA-multicasts the slice to the CTAs of its cluster row / column.  Measured
+// (DESIGN.md 4.1): that pays for the 128 x 208 tiles of the H update (1 x 2), not for the 128 x 128 tiles, whose loop sits at
+// the shared-memory port.  PAIR: compile-time cta_group::2 mode (256-row MMAs), not yet validated on hardware.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
