@@ -289,7 +289,7 @@ def run_gpu(args):
                                  'traffic = DRAM bytes per iteration from the ncu --set full capture in profiles/ (--cache-control none: the L2 state of the running loop)'},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline(3.0)
+            line['cpu_baseline'] = cpu_baseline(20.0)      # 10-15 s of CPU work on the host cores (bounded sample of the same clip)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
