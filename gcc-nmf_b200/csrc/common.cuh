@@ -68,6 +68,25 @@ inline int gccnmf_fail(gccnmf_handle* h, int status, const char* fmt, ...) {
     if (!(cond)) return gccnmf_fail((h), GCCNMF_ERR_INVALID_ARGUMENT, __VA_ARGS__);             \
   } while (0)
 
+// Every ABI entry that takes a handle starts here: NULL check + make the handle's device current (a process may hold
+// handles on several devices; kernel attributes and occupancy caches below are kept per device index).
+constexpr int kGccnmfMaxDevices = 64;
+inline int gccnmf_enter(gccnmf_handle* h) {
+  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  const cudaError_t err = cudaSetDevice(h->device);
+  if (err != cudaSuccess) return gccnmf_fail(h, GCCNMF_ERR_CUDA, "cudaSetDevice(%d) failed: %s", h->device, cudaGetErrorString(err));
+  return GCCNMF_OK;
+}
+#define GCCNMF_ENTER(h)                                                                         \
+  do {                                                                                          \
+    if (int st__ = gccnmf_enter(h)) return st__;                                                \
+  } while (0)
+// Per-device once-flag for cudaFuncSetAttribute and friends (function-local `static DeviceFlags configured;`).
+struct DeviceFlags {
+  bool done[kGccnmfMaxDevices] = {false};
+  bool& operator()(const gccnmf_handle* h) { return done[h->device % kGccnmfMaxDevices]; }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Carves aligned sub-buffers out of a caller-owned workspace.

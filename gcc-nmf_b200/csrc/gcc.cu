@@ -375,7 +375,7 @@ size_t gccnmf_phat_angspec_workspace_bytes(int F, int T, int D) {
 
 int gccnmf_phat_angspec(gccnmf_handle* h, const float* X, int F, int T, int x_is_coherence, const double* expJOmegaTau, int D, float* coherence,
                         double* angular, double* mean_angular, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, F > 0 && T > 0, "phat_angspec: F and T must be positive");
   GCCNMF_REQUIRE(h, X != nullptr, "phat_angspec: NULL spectrogram");
   const bool need_ang = angular || mean_angular;
@@ -404,7 +404,7 @@ int gccnmf_phat_angspec(gccnmf_handle* h, const float* X, int F, int T, int x_is
 
 int gccnmf_tdoa_gccnmf(gccnmf_handle* h, const float* coherence, int F, int T, const double* E, int D, const float* W, int K,
                        float* values, int32_t* argmax, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, F > 0 && T > 0 && D > 0 && K > 0, "tdoa_gccnmf: dimensions must be positive");
   GCCNMF_REQUIRE(h, coherence && E && W, "tdoa_gccnmf: NULL pointer");
   GCCNMF_REQUIRE(h, (int64_t)T * D < (int64_t)1 << 31, "tdoa_gccnmf: T * D overflows int32");
@@ -426,7 +426,7 @@ int gccnmf_tdoa_gccnmf(gccnmf_handle* h, const float* coherence, int F, int T, c
 }
 
 int gccnmf_coeff_mask(gccnmf_handle* h, const float* gccnmfs, int S, int K, int T, float* masks, int32_t* all_nan_flag, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, S > 0 && K > 0 && T > 0 && gccnmfs && masks, "coeff_mask: bad arguments");
   const int64_t KT = (int64_t)K * T;
   GCCNMF_LAUNCH(h, coeff_mask_kernel, (unsigned)((KT + 255) / 256), 256, 0, stream, gccnmfs, S, KT, masks, all_nan_flag);
@@ -434,7 +434,7 @@ int gccnmf_coeff_mask(gccnmf_handle* h, const float* gccnmfs, int S, int K, int 
 }
 
 int gccnmf_argmax_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, const uint8_t* lut, int D, float* mask, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, K > 0 && T > 0 && D > 0 && argmax && lut && mask, "argmax_mask: bad arguments");
   const int64_t KT = (int64_t)K * T;
   GCCNMF_LAUNCH(h, argmax_mask_kernel, (unsigned)((KT + 255) / 256), 256, 0, stream, argmax, KT, lut, D, mask);
@@ -443,7 +443,7 @@ int gccnmf_argmax_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, co
 
 int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W, const float* H, int S, int F,
                               int T, int K, float* out, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, S > 0 && F > 0 && T > 0 && K > 0 && masks && X && W && H && out, "masked_recon_phase: bad arguments");
   dim3 grid((T + RN - 1) / RN, (F + RM - 1) / RM, S * 2);
   GCCNMF_LAUNCH(h, masked_recon_kernel, grid, kReconThreads, 0, stream, masks, reinterpret_cast<const float2*>(X), W, H, F, T, K,
@@ -452,7 +452,7 @@ int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float*
 }
 
 int gccnmf_online_targets(gccnmf_handle* h, const double* angular, int D, int T, double* accumulated_max, int32_t* targets, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, angular && accumulated_max && targets && D > 0 && T > 0, "online_targets: bad arguments");
   GCCNMF_LAUNCH(h, cummax_time_kernel, (D + 63) / 64, 64, 0, stream, angular, D, T, accumulated_max);
   GCCNMF_LAUNCH(h, argmax_tdoa_kernel, (T + 127) / 128, 128, 0, stream, accumulated_max, D, T, targets);
@@ -461,7 +461,7 @@ int gccnmf_online_targets(gccnmf_handle* h, const double* angular, int D, int T,
 
 int gccnmf_atom_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, const int32_t* targets, float target_scalar, float epsilon,
                      int mode, float beta, float noise_floor, float* mask, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, argmax && mask && K > 0 && T > 0 && (mode == 0 || mode == 1), "atom_mask: bad arguments");
   const int64_t n = (int64_t)K * T;
   GCCNMF_LAUNCH(h, atom_mask_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, argmax, K, T, targets, 1, target_scalar, epsilon, mode,
@@ -473,7 +473,7 @@ size_t gccnmf_wiener_apply_workspace_bytes(int F) { return F > 0 ? align_up((siz
 
 int gccnmf_wiener_apply(gccnmf_handle* h, const float* mask, const float* W, const float* X, int F, int T, int K, float* Y,
                         float* wiener, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, mask && W && X && Y && F > 0 && T > 0 && K > 0, "wiener_apply: bad arguments");
   if (!workspace || workspace_bytes < gccnmf_wiener_apply_workspace_bytes(F)) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "wiener_apply workspace too small");
   float* rowsum = static_cast<float*>(workspace);

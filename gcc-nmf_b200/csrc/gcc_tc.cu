@@ -265,10 +265,10 @@ template <class Epi>
 int launch_argmax_gemm(gccnmf_handle* h, const GemmArgs& args, const Epi& epi, void* stream) {
   using S = umma::GemmSmem<128, umma::kSplitBF16>;
   auto kernel = umma::gemm_tn_3xtf32_kernel<128, false, umma::kSplitBF16, umma::kLoaderWarps, Epi>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceFlags configured;     // per device: the attribute belongs to the device's copy of the kernel
+  if (!configured(h)) {
     GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
+    configured(h) = true;
   }
   // x = atom tiles (fastest) so that the CTAs sharing one slab of G run together and it is read from HBM once
   dim3 grid(args.m_tiles, (args.N + 127) / 128, 1);
@@ -298,10 +298,13 @@ size_t gccnmf_tdoa_argmax_workspace_bytes(int F, int T, int D, int K) {
 
 int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, const double* E, int D, const float* W, int K,
                        int32_t* argmax, int32_t* overflow_flag, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, F > 0 && T > 0 && D > 0 && K > 0 && coherence && E && W && argmax, "tdoa_argmax: bad arguments");
-  if (h->force_simt_nmf || !gccnmf_tdoa_argmax_tc_supported(F, T, D, K))
-    return gccnmf_tdoa_gccnmf(h, coherence, F, T, E, D, W, K, nullptr, argmax, stream);   // exact float64 SIMT kernel
+  if (h->force_simt_nmf || !gccnmf_tdoa_argmax_tc_supported(F, T, D, K)) {
+    // exact float64 SIMT kernel: nothing to refine, and the caller must not read an unwritten counter
+    if (overflow_flag) GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(overflow_flag, 0, sizeof(int32_t), (cudaStream_t)stream));
+    return gccnmf_tdoa_gccnmf(h, coherence, F, T, E, D, W, K, nullptr, argmax, stream);
+  }
   ArgmaxWorkspace w = carve_argmax(workspace, workspace_bytes, F, T, D, K);
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "tdoa_argmax workspace too small: need %zu bytes", gccnmf_tdoa_argmax_workspace_bytes(F, T, D, K));
   GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.count, 0, 16, (cudaStream_t)stream));

@@ -301,7 +301,7 @@ size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K) {
 
 int gccnmf_klnmf_begin(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
@@ -312,7 +312,7 @@ int gccnmf_klnmf_begin(gccnmf_handle* h, const float* V, int F, int T2, const fl
 int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K,
                             float sparsity_alpha, float epsilon, int iteration, float* numer, void* workspace,
                             size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   GCCNMF_REQUIRE(h, numer != nullptr && iteration >= 0, "klnmf_step_numer: bad arguments");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
@@ -330,7 +330,7 @@ int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, int T2, con
 
 int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer,
                             void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   GCCNMF_REQUIRE(h, numer != nullptr, "klnmf_step_apply: NULL numerator");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
@@ -342,7 +342,7 @@ int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H,
 
 int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, const float* numer_multicast,
                                      void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   (void)H;
   GCCNMF_REQUIRE(h, numer_multicast != nullptr, "klnmf_step_apply_multimem: NULL multicast address");
@@ -354,7 +354,7 @@ int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, 
 
 int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,
                      size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   (void)W;
   if (use_tc(h, F, T2, K)) return tc_ops(h, F, T2, K).finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream);
@@ -363,7 +363,7 @@ int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
 
 int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, int iterations,
                  float sparsity_alpha, float epsilon, int update_W, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   GCCNMF_REQUIRE(h, iterations >= 0, "klnmf: iterations must be >= 0 (got %d)", iterations);
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))

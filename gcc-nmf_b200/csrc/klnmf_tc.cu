@@ -330,10 +330,10 @@ int launch_gemm_split(gccnmf_handle* h, const GemmArgs& args, int tail_rows, int
   using S = umma::GemmSmem<BN, SPLIT>;
   constexpr int LW = kNmfWorkerWarps;
   auto kernel = umma::gemm_tn_3xtf32_kernel<BN, SCALE_B, SPLIT, LW, Epi>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceFlags configured;     // per device: the attribute belongs to the device's copy of the kernel
+  if (!configured(h)) {
     GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
+    configured(h) = true;
   }
   dim3 grid((args.N + BN - 1) / BN, args.m_tiles + (tail_rows > 0 ? 1 : 0), splits);
   GCCNMF_LAUNCH(h, kernel, grid, LW * 32 + 32, S::kTotal, stream, args, epi);
@@ -545,7 +545,7 @@ int gccnmf_gemm_tn_3xtf32(gccnmf_handle* h, const float* A, int64_t lda, const f
 // [0] kernel start, [1] first stage full, [2] last MMA issued, [3] loaders finished, [4] accumulator complete, [5] epilogue end.
 int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd,
                                 int M, int N, int Kc, int tile_n, unsigned long long* timing, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, A && B && D && M > 0 && N > 0 && Kc > 0, "gemm_tn_3xtf32: bad arguments");
   GCCNMF_REQUIRE(h, lda % 4 == 0 && ldb % 4 == 0 && lda >= ((Kc + 3) & ~3) && ldb >= ((Kc + 3) & ~3),
                  "gemm_tn_3xtf32: leading dimensions must be multiples of 4 covering round_up(Kc, 4)");

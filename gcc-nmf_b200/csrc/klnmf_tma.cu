@@ -514,7 +514,9 @@ template <int BN, bool A_MN, bool B_MN, int CN, int CM, class Epi, bool PAIR = f
 struct PlaneGemmInstance {
   using C = tgemm::Config<BN, kKB, A_MN, B_MN, PAIR ? 2 : 1>;
   static int max_clusters(gccnmf_handle* h, int* out) {
-    static int cached = -1;
+    static int cached_per_device[kGccnmfMaxDevices];     // 0 = not queried yet, else value + 1 (per device: attribute + occupancy)
+    int& slot = cached_per_device[h->device % kGccnmfMaxDevices];
+    int cached = slot - 1;
     if (cached < 0) {
       auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, PAIR, Epi>;
       GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
@@ -534,6 +536,7 @@ struct PlaneGemmInstance {
         GCCNMF_CHECK_CUDA(h, cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
         cached = n;
       }
+      slot = cached + 1;
     }
     *out = cached;
     return 0;
@@ -881,7 +884,7 @@ size_t gccnmf_gemm_planes_workspace_bytes(int M, int N, int Kc) {
 // splits > 1 writes `splits` partial slabs DT[z] (N * M floats each).  timing: 6 clock64 stamps per CTA, or NULL.
 int gccnmf_gemm_planes(gccnmf_handle* h, const float* A, int a_mn_major, const float* B, int b_mn_major, float* DT, int M, int N, int Kc,
                        int tile_n, int splits, void* workspace, size_t workspace_bytes, unsigned long long* timing, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, A && B && DT && M > 0 && N > 0 && Kc > 0 && splits >= 1 && splits <= kMaxSplits, "gemm_planes: bad arguments");
   if (!workspace || workspace_bytes < gccnmf_gemm_planes_workspace_bytes(M, N, Kc))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "gemm_planes workspace too small: need %zu bytes", gccnmf_gemm_planes_workspace_bytes(M, N, Kc));

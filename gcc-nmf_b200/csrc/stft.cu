@@ -223,7 +223,7 @@ int gccnmf_stft_num_frames(int64_t num_samples, int n_fft, int hop) {
 
 int gccnmf_stft(gccnmf_handle* h, const float* samples, int64_t sample_stride, int channels, int64_t num_samples,
                 const double* window, int n_fft, int hop, int conjugate, float* X, float* V, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   const int log2n = ilog2_exact(n_fft);
   if (log2n < 5 || log2n > 12) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "stft: n_fft must be a power of two in [32, 4096] (got %d)", n_fft);
   GCCNMF_REQUIRE(h, channels == 1 || channels == 2, "stft: channels must be 1 or 2 (got %d)", channels);
@@ -263,7 +263,7 @@ size_t gccnmf_istft_workspace_bytes(int batch, int n_fft, int T) {
 
 int gccnmf_istft_ola(gccnmf_handle* h, const float* spec, int batch, int n_fft, int hop, int T, const double* window,
                      float gain, int center, int conjugate, float* y, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h) return GCCNMF_ERR_INVALID_ARGUMENT;
+  GCCNMF_ENTER(h);
   const int log2n = ilog2_exact(n_fft);
   if (log2n < 5 || log2n > 12) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "istft: n_fft must be a power of two in [32, 4096] (got %d)", n_fft);
   GCCNMF_REQUIRE(h, batch >= 1 && T >= 1 && hop >= 1, "istft: batch, T, hop must be positive");

@@ -28,12 +28,9 @@ def getSourceEstimateFileName(mixtureFileNamePrefix, targetIndex):
 
 def loadMixtureSignal(mixtureFileName):
     """gccNMFFunctions.py:47 -> wavfile.py:34-37: (channels, n) float32 in [-1, 1), sample rate."""
-    from scipy.io import wavfile
-    sampleRate, samples = wavfile.read(mixtureFileName)
-    if samples.dtype.kind == 'i':                      # wavfile.py:57-90 pcm2float
-        info = np.iinfo(samples.dtype)
-        samples = samples.astype(np.float32) / (2 ** (info.bits - 1))
-    return np.ascontiguousarray(samples.T.astype(np.float32)), sampleRate
+    from .wavio import wavread
+    samples, sampleRate = wavread(mixtureFileName)
+    return np.ascontiguousarray(samples, dtype=np.float32), sampleRate
 
 
 def getMaxTDOA(microphoneSeparationInMetres):
@@ -185,15 +182,10 @@ def getTargetSignalEstimates(targetSpectrogramEstimates, windowSize, hopSize, wi
 
 
 def saveTargetSignalEstimates(targetSignalEstimates, sampleRate, mixtureFileNamePrefix):
-    """gccNMFFunctions.py:165-169 -> wavfile.py:39-48 (int16 with clip protection)."""
-    from scipy.io import wavfile
+    """gccNMFFunctions.py:165-169 -> wavfile.py:39-48 (int16 = x * 2^15 clipped; a peak >= 1 is rescaled to 0.99)."""
+    from .wavio import wavwrite
     for targetIndex in range(targetSignalEstimates.shape[0]):
-        x = np.asarray(targetSignalEstimates[targetIndex]).T
-        peak = np.max(np.abs(x))
-        if peak > 1:
-            x = x / peak
-        wavfile.write(getSourceEstimateFileName(mixtureFileNamePrefix, targetIndex), sampleRate,
-                      (x * 32767).astype(np.int16))
+        wavwrite(np.asarray(targetSignalEstimates[targetIndex]), getSourceEstimateFileName(mixtureFileNamePrefix, targetIndex), sampleRate)
 
 
 # ----------------------------------------------------------------------------------------- a10 (notebook)

@@ -20,6 +20,7 @@ from collections import namedtuple
 
 import numpy as np
 
+from ..wavio import float2pcm, pcm2float  # noqa: F401  (re-exported: the reference keeps them in gccNMF/wavfile.py)
 from .utils import OverlapAddProcessor
 
 # gccNMF/realtime/config.py:46-82 (getDefaultConfig) -- the reference never reads a config file (:104-111)
@@ -51,28 +52,6 @@ def getGCCNMFConfigParams(audioPath=None, dataDir=None, dictionariesW=None, **ov
         dictionariesW = getDictionariesW(p['windowSize'], p['dictionarySizes'], dataDir, ordered=True)
     p['dictionariesW'] = dictionariesW
     return namedtuple('ParamsDict', p.keys())(**p)
-
-
-def pcm2float(sig, dtype='float32'):
-    """gccNMF/wavfile.py:57-90."""
-    sig = np.asarray(sig)
-    if sig.dtype.kind not in 'iu':
-        raise TypeError("'sig' must be an array of integers")
-    i = np.iinfo(sig.dtype)
-    abs_max = 2 ** (i.bits - 1)
-    offset = i.min + abs_max
-    return (sig.astype(dtype) - offset) / abs_max
-
-
-def float2pcm(sig, dtype='int16'):
-    """gccNMF/wavfile.py:92-125 (scales by 2^15 and clips)."""
-    sig = np.asarray(sig)
-    if sig.dtype.kind != 'f':
-        raise TypeError("'sig' must be a float array")
-    i = np.iinfo(dtype)
-    abs_max = 2 ** (i.bits - 1)
-    offset = i.min + abs_max
-    return (sig * abs_max + offset).clip(i.min, i.max).astype(dtype)
 
 
 class RealtimeGCCNMFNoGUI(object):

@@ -171,10 +171,34 @@ def golden_c1_digest():
          H_norm=np.array(np.linalg.norm(H.astype(np.float64))), meanAngularSpectrum=np.mean(A, axis=-1),
          targetTDOAIndexes=np.array(idx), maskSums=M.sum(axis=(1, 2)), y_shape=np.array(y.shape),
          y_strided=y[:, :, ::997], y_norm=np.array(np.linalg.norm(y.astype(np.float64))))
+    # teacher-forcing set for the stages after the NMF: the reference's W, H and its binary masks (bit-packed), a strided
+    # view of the per-target GCC-NMFs and of the spectrogram estimates (the recording itself travels as tests/golden/*.wav)
+    save('c1_full', W=W, H=H, masks_packed=np.packbits(M.astype(bool)), masks_shape=np.array(M.shape),
+         G_strided=G[:, ::5, ::7], Sp_strided=Sp[:, :, ::37, ::29], y_head=y[:, :, 20000:24096])
+
+
+def golden_wavfile():
+    """gccNMF/wavfile.py: wavwrite (clip protection, float2pcm) and wavread (pcm2float) on a signal that exceeds 1 and
+    one that does not, plus the unsigned-PCM offset; the written files travel as raw bytes."""
+    import tempfile
+    from gccNMF import wavfile as refwav
+    rng = np.random.default_rng(3)
+    quiet = (0.3 * rng.standard_normal((2, 400))).clip(-0.999, 0.999).astype(np.float32)
+    loud = (2.0 * rng.standard_normal((2, 400))).astype(np.float32)
+    d = tempfile.mkdtemp()
+    out = {}
+    for name, x in (('quiet', quiet), ('loud', loud)):
+        path = os.path.join(d, name + '.wav')
+        refwav.wavwrite(x, path, 16000)
+        out[name + '_bytes'] = np.frombuffer(open(path, 'rb').read(), dtype=np.uint8)
+        out[name + '_read'] = refwav.wavread(path)[0]
+    u8 = np.arange(256, dtype=np.uint8)
+    save('wavfile_mini', quiet=quiet, loud=loud, u8=u8, u8_float=refwav.pcm2float(u8), **out)
 
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    golden_wavfile()
     golden_separation()
     golden_enhancement()
     golden_online()

@@ -18,7 +18,10 @@ sys.path.insert(0, ROOT)
 
 def handle():
     from gcc_nmf_b200._lib import default_handle
-    return default_handle()
+    h = default_handle()
+    if os.environ.get('GEMM_PAIR'):          # cta_group::2 CTA pairs for every contraction whose tile shape allows them
+        h.set_option('gemm_pair', int(os.environ['GEMM_PAIR']))
+    return h
 
 
 def gemm():
@@ -122,8 +125,11 @@ def timing():
     V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
     W0, H0 = orc.initKLNMF(F, T2, K)
     W0d, H0d = h.to_device(W0), h.to_device(H0)
-    for name, tma, pdl, cl in (('loader', 0, 0, -1), ('tma no pdl, auto clusters', 1, 0, -1), ('tma+pdl, no clusters', 1, 1, 11), ('tma+pdl, clusters 1x2', 1, 1, 12),
-                               ('tma+pdl, clusters 2x1', 1, 1, 21), ('tma+pdl, clusters 2x2', 1, 1, 22), ('tma+pdl, auto clusters', 1, 1, -1)):
+    variants = (('loader', 0, 0, -1), ('tma no pdl, auto clusters', 1, 0, -1), ('tma+pdl, no clusters', 1, 1, 11), ('tma+pdl, clusters 1x2', 1, 1, 12),
+                ('tma+pdl, clusters 2x1', 1, 1, 21), ('tma+pdl, clusters 2x2', 1, 1, 22), ('tma+pdl, auto clusters', 1, 1, -1))
+    if os.environ.get('TIME_VARIANTS') == 'short':
+        variants = (('tma+pdl, auto clusters', 1, 1, -1),)
+    for name, tma, pdl, cl in variants:
         h.set_option('nmf_tma', tma)
         h.set_option('nmf_pdl', pdl)
         h.set_option('gemm_cluster', cl)
