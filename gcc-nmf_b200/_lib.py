@@ -74,6 +74,29 @@ SIGNATURES = {
     'gccnmf_gemm_tn_3xtf32_timed': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _S]),
 }
 
+
+
+class RtConfig(ctypes.Structure):
+    """gccnmf_rt_config (include/gccnmf_b200.h)."""
+    _fields_ = [('window_size', c_int), ('hop_size', c_int), ('block_size', c_int), ('windows_per_block', c_int), ('num_atoms', c_int),
+                ('num_tdoas', c_int), ('history_length', c_int), ('inference_iterations', c_int), ('sparsity_alpha', c_float),
+                ('epsilon', c_float)]
+
+
+_C = ctypes.POINTER(RtConfig)
+SIGNATURES.update({
+    'gccnmf_wiener_apply_h': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _S]),
+    'gccnmf_rt_state_bytes': (c_size_t, [_C]),
+    'gccnmf_rt_init': (c_int, [_H, _C, _P, _P, _P, _P, _P, _P, c_size_t, _S]),
+    'gccnmf_rt_set_params': (c_int, [_H, _C, _P, c_size_t, c_float, c_int, c_float, c_float, c_float, c_int, c_int, c_int, c_int, _S]),
+    'gccnmf_rt_process_frames': (c_int, [_H, _C, _P, c_size_t, _P, _P, _P, _S]),
+    'gccnmf_rt_process_block': (c_int, [_H, _C, _P, c_size_t, _P, _P, _P, _S]),
+    'gccnmf_rt_graph_create': (c_int, [_H, _C, _P, c_size_t, _P, _P, _P, _P, ctypes.POINTER(c_void_p), _S]),
+    'gccnmf_rt_graph_launch': (c_int, [_H, c_void_p, _S]),
+    'gccnmf_rt_graph_destroy': (c_int, [_H, c_void_p]),
+    'gccnmf_rt_export': (c_int, [_H, _C, _P, c_size_t, c_int, c_void_p, _S]),
+})
+
 _lib = None
 
 
@@ -344,6 +367,16 @@ class Handle(object):
         ws = self.workspace('wiener', self.lib.gccnmf_wiener_apply_workspace_bytes(F))
         self.check(self.lib.gccnmf_wiener_apply(self.h, _ptr(mask), _ptr(W), _ptr(X), F, T, K, _ptr(Y), _ptr(wiener), _ptr(ws),
                                                 ws.numel(), self.stream))
+        return (Y, wiener) if want_filter else Y
+
+    def wiener_apply_h(self, mask, W, H, X, want_filter=False):
+        """mask (K, T), W (F, K), H (K, 2T) [channel-major columns], X (2, F, T) c64 -> Y (2, F, T) c64 [, wiener (2, F, T) f32]."""
+        torch = self.torch
+        K, T = mask.shape
+        F = W.shape[0]
+        Y = self.empty((2, F, T), torch.complex64)
+        wiener = self.empty((2, F, T), torch.float32) if want_filter else None
+        self.check(self.lib.gccnmf_wiener_apply_h(self.h, _ptr(mask), _ptr(W), _ptr(H), _ptr(X), F, T, K, _ptr(Y), _ptr(wiener), self.stream))
         return (Y, wiener) if want_filter else Y
 
     def masked_recon_phase(self, masks, X, W, H, out_key=None):

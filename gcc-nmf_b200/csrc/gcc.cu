@@ -361,6 +361,45 @@ wiener_apply_kernel(const float* __restrict__ mask, const float* __restrict__ W,
   }
 }
 
+struct LoadHMaybeMasked {  // B(n = t, k = atom) = H[atom][c*T + t] (* mask[atom][t] when mask != NULL)
+  static constexpr bool kContigK = false;
+  const float* H; const float* mask; int K, T; int64_t ldh;
+  __device__ float operator()(int n, int k) const {
+    if (n >= T || k >= K) return 0.f;
+    const float hv = __ldg(H + (int64_t)k * ldh + n);
+    return mask ? hv * __ldg(mask + (int64_t)k * T + n) : hv;
+  }
+};
+
+// Wiener-like filter with inferred coefficients (onlineSpeechEnhancement.ipynb:435-440), per channel c = blockIdx.z:
+//   wiener[c] = (W . (H_c * mask)) / (W . H_c);   Y[c] = wiener[c] * X[c]          H (K, 2T), column c T + t
+__global__ void __launch_bounds__(kReconThreads, 2)
+wiener_apply_h_kernel(const float* __restrict__ mask, const float* __restrict__ W, const float* __restrict__ H, const float2* __restrict__ X,
+                      int F, int T, int K, float2* __restrict__ Y, float* __restrict__ wiener) {
+  const int c = blockIdx.z;
+  float num[RTM][RTN], den[RTM][RTN];
+  const int m0 = blockIdx.y * RM, n0 = blockIdx.x * RN;
+  LoadWRows a{W, F, K};
+  LoadHMaybeMasked masked{H + (int64_t)c * T, mask, K, T, (int64_t)2 * T}, plain{H + (int64_t)c * T, nullptr, K, T, (int64_t)2 * T};
+  gemm_simt_mainloop<float, RM, RN, RK, RTM, RTN>(num, m0, n0, K, a, masked);
+  gemm_simt_mainloop<float, RM, RN, RK, RTM, RTN>(den, m0, n0, K, a, plain);
+#pragma unroll
+  for (int i = 0; i < RTM; ++i) {
+    const int m = gemm_row<RM, RTM, RN / RTN>(m0, i);
+    if (m >= F) continue;
+#pragma unroll
+    for (int j = 0; j < RTN; ++j) {
+      const int n = gemm_col<RN, RTN, RN / RTN>(n0, j);
+      if (n >= T) continue;
+      const float w = num[i][j] / den[i][j];
+      const int64_t o = ((int64_t)c * F + m) * T + n;
+      if (wiener) wiener[o] = w;
+      const float2 x = X[o];
+      Y[o] = float2{w * x.x, w * x.y};
+    }
+  }
+}
+
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 }  // namespace
@@ -480,6 +519,18 @@ int gccnmf_wiener_apply(gccnmf_handle* h, const float* mask, const float* W, con
   GCCNMF_LAUNCH(h, rowsum_w_kernel, F, 128, 0, stream, W, F, K, rowsum);
   dim3 grid((T + RN - 1) / RN, (F + RM - 1) / RM);
   GCCNMF_LAUNCH(h, wiener_apply_kernel, grid, kReconThreads, 0, stream, mask, W, rowsum, reinterpret_cast<const float2*>(X), F, T, K,
+                reinterpret_cast<float2*>(Y), wiener);
+  return GCCNMF_OK;
+}
+
+// Y (2, F, T) c64 = wiener * X with wiener (2, F, T) f32 = (W . (H_c * mask)) / (W . H_c) per channel (ipynb:435-440):
+// the numInferenceIterations > 0 branch; H (K, 2T) holds channel c in columns [c T, (c + 1) T).
+int gccnmf_wiener_apply_h(gccnmf_handle* h, const float* mask, const float* W, const float* H, const float* X, int F, int T, int K, float* Y,
+                          float* wiener, void* stream) {
+  GCCNMF_ENTER(h);
+  GCCNMF_REQUIRE(h, mask && W && H && X && Y && F > 0 && T > 0 && K > 0, "wiener_apply_h: bad arguments");
+  dim3 grid((T + RN - 1) / RN, (F + RM - 1) / RM, 2);
+  GCCNMF_LAUNCH(h, wiener_apply_h_kernel, grid, kReconThreads, 0, stream, mask, W, H, reinterpret_cast<const float2*>(X), F, T, K,
                 reinterpret_cast<float2*>(Y), wiener);
   return GCCNMF_OK;
 }

@@ -524,12 +524,12 @@ struct PlaneGemmInstance {
         cached = h->sm_count;
       } else {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(CN * 64, CM * 64, 1);
+        cfg.gridDim = PAIR ? dim3(2 * 64, 64, 1) : dim3(CN * 64, CM * 64, 1);
         cfg.blockDim = dim3(tgemm::kThreads);
         cfg.dynamicSmemBytes = C::kTotal;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CN; attr[0].val.clusterDim.y = CM; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = PAIR ? 2 : CN; attr[0].val.clusterDim.y = PAIR ? 1 : CM; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int n = 0;
@@ -560,13 +560,14 @@ struct PlaneGemmInstance {
     args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
     args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
     args.timing = timing;
-    const dim3 grid(g.n_tiles, g.m_tiles, g.splits);
+    // pair: the two m tiles of a cta_group::2 pair sit next to each other along x (see the kernel)
+    const dim3 grid = PAIR ? dim3(2 * g.n_tiles, g.m_tiles / 2, g.splits) : dim3(g.n_tiles, g.m_tiles, g.splits);
     if (!timing && h->debug_timing) {   // diagnostics: every plane GEMM of the KL-NMF loop appends its CTA stamps (8 per CTA)
       args.timing = h->debug_timing + h->debug_timing_cursor;
       h->debug_timing_cursor += (size_t)grid.x * grid.y * grid.z * 8;
     }
-    return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl, dim3(CN, CM, 1),
-                     map_a, map_b, args, epi);
+    return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl,
+                     PAIR ? dim3(2, 1, 1) : dim3(CN, CM, 1), map_a, map_b, args, epi);
   }
 };
 

@@ -230,14 +230,20 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y, z = blockIdx.z;
+  // PAIR: the two CTAs of a pair must be neighbours along x (cta_group::2 pairs are formed along the cluster's x dimension: a
+  // (1, 2, 1) cluster is refused at launch with "cluster misconfiguration"), so the grid is (2 n_tiles, m_tiles / 2, splits) with
+  // (2, 1, 1) clusters and the m tile alternates with blockIdx.x.
+  const int tile_n = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_m = PAIR ? (int)(2 * blockIdx.y + (blockIdx.x & 1)) : (int)blockIdx.y;
+  const int z = blockIdx.z;
   const int n0 = tile_n * BN;
   const int total_kblocks = (args.Kc + KB - 1) / KB;
   const int kb_begin = z * args.kblocks_per_split;
   const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
   const int num_kb = max(0, kb_end - kb_begin);
   // position inside the cluster (x = n tile, y = m tile); rank = x + CN y (%cluster_ctarank)
-  const int cx = (CN > 1) ? (int)(blockIdx.x % CN) : 0, cy = (CM > 1) ? (int)(blockIdx.y % CM) : 0;
+  const int cx = (!PAIR && CN > 1) ? (int)(blockIdx.x % CN) : 0;
+  const int cy = PAIR ? (int)(blockIdx.x & 1) : ((CM > 1) ? (int)(blockIdx.y % CM) : 0);
   // CTAs that receive my slice of A (same m tile: my cluster row) / of B (same n tile: my cluster column)
   const uint16_t mask_row = (uint16_t)(((1u << CN) - 1u) << (CN * cy));
   const uint16_t mask_col = (uint16_t)((CM > 1 ? ((1u << cx) | (1u << (cx + CN))) : (1u << cx)));

@@ -1,31 +1,36 @@
 """Drop-in for the per-chunk processor of gccNMF/realtime/gccNMFProcessor.py:167-276.
 
-Same constructor arguments, attributes and methods (`processFrames`, `reset`, `setTargetTDOARange`,
-settable `numTDOAs`, `separationEnabled`, `localizationEnabled`, `localizationWindowSize`, `targetMode`); the
-Theano graph (:238-270) is replaced by the sm_100a kernels: windowed FFT -> PHAT coherence + real GCC ->
-GCC-NMF argmax over TDOA per atom -> boxcar / window atom mask -> Wiener-like TF mask (W.mask)/rowsum(W) ->
-inverse FFT x synthesis window.  `numHUpdates` is accepted and ignored exactly as in the reference (it is
-plumbed everywhere there but never used).  History buffers (the reference's SharedMemoryCircularBuffer
-objects) are optional duck-typed objects with `.set(values)` / `.getUnraveledArray()`.
+Same constructor arguments, attributes and methods (`processFrames`, `reset`, `setTargetTDOARange`, settable `numTDOAs`,
+`separationEnabled`, `localizationEnabled`, `localizationWindowSize`, `targetMode`).  The Theano graph (:238-270) and the
+numpy code around it (:201-231) run as ONE stream-ordered sequence of sm_100a kernels without a host synchronisation inside
+(csrc/rt.cu, `RealtimeEngine`): windowed FFT -> PHAT coherence -> real GCC -> float32 GCC-NMF `dot(realGCC.T, W)` -> argmax
+over TDOA per atom -> boxcar / window atom mask (float64, like the int64 - float32 promotion of the reference's graph) ->
+(W . mask) / rowsum(W) -> inverse FFT x synthesis window, plus the GCC-PHAT history ring and the sliding-window
+localisation, whose target TDOA index stays on the device from one call to the next.  Per call the host does one H2D of
+the windowed frames, one D2H of the result and one synchronisation.
 
-The argmax over TDOA is the exact float64 one (tensor cores + float64 refinement); the reference evaluates it in
-Theano float32 (and cannot be run here: Theano is not installed), so near-ties may resolve differently.
+`numHUpdates` is accepted and, exactly as in the reference, unused (it is plumbed everywhere there and never read);
+`coefficientInferenceIterations` (an extension, default 0) switches on the per-frame H-only KL updates of
+notebooks/onlineSpeechEnhancement.ipynb:433-438 in the same kernel sequence.  History buffers (the reference's
+SharedMemoryCircularBuffer objects) are optional duck-typed objects with `.set(values)` / `.getUnraveledArray()`.
 """
 import logging
 
 import numpy as np
 
 from .. import gccNMFFunctions as fn
-from .._lib import default_handle
+from . import engine as rt
 
-TARGET_MODE_BOXCAR = 0
-TARGET_MODE_WINDOW_FUNCTION = 1
+TARGET_MODE_BOXCAR = 0               # gccNMFProcessor.py:35-37
+TARGET_MODE_MULTIPLE = 1             # declared by the reference, not implemented there (its graph has no such branch, :262-265)
+TARGET_MODE_WINDOW_FUNCTION = 2
 
 
 class GCCNMFProcessor(object):
     def __init__(self, sampleRate, windowSize, numTimePerChunk, dictionariesW, dictionaryType, dictionarySize, numHUpdates,
                  microphoneSeparationInMetres, localizationEnabled, localizationWindowSize, gccPHATHistory=None, tdoaHistory=None,
-                 inputSpectrogramHistory=None, outputSpectrogramHistory=None, coefficientMaskHistories=None, device=0):
+                 inputSpectrogramHistory=None, outputSpectrogramHistory=None, coefficientMaskHistories=None, device=0,
+                 coefficientInferenceIterations=0):
         self.sampleRate = sampleRate
         self.windowSize = windowSize
         self.numTimePerChunk = numTimePerChunk
@@ -50,8 +55,11 @@ class GCCNMFProcessor(object):
         self.targetTDOAEpsilon = np.float32(2.0)
         self.targetTDOABeta = np.float32(1.0)
         self.targetTDOANoiseFloor = np.float32(0.0)
-        self.h = default_handle(device)
-        self._built = False
+        self.coefficientInferenceIterations = coefficientInferenceIterations
+        self.device = device
+        self.engine = None
+        self._sent = None
+        self._target_dirty = True
 
     # ------------------------------------------------------------------ :233-270
     def reset(self):
@@ -59,20 +67,28 @@ class GCCNMFProcessor(object):
         self.buildFunctions()
         logging.info('GCCNMFProcessor: done reset.')
 
-    def buildFunctions(self):
-        """Device constants that the reference bakes into its Theano functions (:241-248)."""
-        h = self.h
+    def buildFunctions(self, hopSize=None, blockSize=None):
+        """Device constants that the reference bakes into its Theano functions (:241-248) and the device-resident state.
+        hopSize / blockSize only matter for the ring entry (`processBlock`); `processFrames` gets its frames cut by the caller."""
         self.W = np.ascontiguousarray(self.dictionariesW[self.dictionaryType][self.dictionarySize], dtype=np.float32)
         self.numFrequencies, self.numAtom = self.W.shape
         self.frequenciesInHz = np.linspace(0, self.sampleRate / 2, self.numFrequencies).astype(np.float32)
         self.maxTDOA = self.microphoneSeparationInMetres / fn.SPEED_OF_SOUND_IN_METRES_PER_SECOND
         self.hypothesisTDOAs = np.linspace(-self.maxTDOA, self.maxTDOA, self.numTDOAs).astype(np.float32)
         self.expJOmegaTau = np.exp(np.outer(self.frequenciesInHz, -(2j * np.pi) * self.hypothesisTDOAs)).astype(np.complex64)
-        self._W = h.to_device(self.W)
-        self._E = h.to_device(np.ascontiguousarray(self.expJOmegaTau.astype(np.complex128)))
-        self._analysis = h.to_device(self.windowFunction[:, 0].astype(np.float64))
-        self._synthesis = h.to_device(self.synthesisWindowFunction[:, 0].astype(np.float64))
-        self._built = True
+        historyLength = self.gccPHATHistory.size() if self.gccPHATHistory else 128
+        if self.engine is not None:
+            self.engine.close()
+        self._geometry = (int(hopSize or self.windowSize), int(blockSize or self.windowSize * self.numTimePerChunk))
+        self.engine = rt.RealtimeEngine(self.W, self.expJOmegaTau, self.windowFunction[:, 0], self.synthesisWindowFunction[:, 0],
+                                        hopSize=self._geometry[0], blockSize=self._geometry[1], windowsPerBlock=self.numTimePerChunk,
+                                        historyLength=historyLength, numInferenceIterations=self.coefficientInferenceIterations,
+                                        device=self.device)
+        if self.targetMode not in (TARGET_MODE_BOXCAR, TARGET_MODE_WINDOW_FUNCTION):
+            raise ValueError('targetMode %r: the reference builds a mask for TARGET_MODE_BOXCAR and TARGET_MODE_WINDOW_FUNCTION only' % (self.targetMode,))
+        self._builtTargetMode = self.targetMode        # the reference bakes the mode into the graph at build time (:262-265)
+        self._sent = None
+        self._target_dirty = True
 
     buildTheanoFunctions = buildFunctions      # the reference's name (:238)
 
@@ -82,44 +98,53 @@ class GCCNMFProcessor(object):
         self.targetTDOAEpsilon = np.float32(targetTDOAEpsilon)
         self.targetTDOABeta = np.float32(targetTDOABeta)
         self.targetTDOANoiseFloor = np.float32(targetTDOANoiseFloor)
+        self._target_dirty = True
 
-    # ------------------------------------------------------------------ :201-231
-    def processFrames(self, windowedSamples):
-        """windowedSamples (2, N, nT) float32 -> (2, N, nT) float32."""
-        if not self._built:
-            self.buildFunctions()
-        h = self.h
-        windowedSamples = np.asarray(windowedSamples, dtype=np.float32)
-        _, N, nT = windowedSamples.shape
-        # frames as a non-overlapping signal: (2, nT * N), hop = N
-        x = h.to_device(np.ascontiguousarray(windowedSamples.transpose(0, 2, 1)).reshape(2, nT * N))
-        X = h.stft(x, self._analysis, N, N, conjugate=False)                                   # :202 rfft(frames * window)
-        coh, ang, _ = h.phat_angspec(X, self._E, want_mean=False)                              # :253-255 (sum over f of realGCC = F * nanmean)
-        if self.separationEnabled:
-            argmax, refined = h.tdoa_argmax(coh, self._E, self._W)                             # :259 + argmax of :263/:265
-            if int(refined.item()) > h.lib.gccnmf_tdoa_argmax_refine_capacity(self.numAtom, nT):
-                _, argmax = h.tdoa_gccnmf(coh, self._E, self._W, want_values=False, want_argmax=True)
-            mode = 0 if self.targetMode == TARGET_MODE_BOXCAR else 1
-            mask = h.atom_mask(argmax, targets=None, target_scalar=float(self.targetTDOAIndex), epsilon=float(self.targetTDOAEpsilon),
-                               mode=mode, beta=float(self.targetTDOABeta), noise_floor=float(self.targetTDOANoiseFloor))
-            out = h.wiener_apply(mask, self._W, X)                                             # :267-269, :209
-            if self.coefficientMaskHistories:
-                self.coefficientMaskHistories[self.dictionarySize].set(1 - mask.cpu().numpy())
-        else:
-            out = X
+    def _sync_params(self):
+        """Pushes the Python-side attributes to the device when they changed (stream-ordered, no synchronisation)."""
+        localize = bool(self.tdoaHistory) and bool(self.gccPHATHistory) and bool(self.localizationEnabled)     # :216-222
+        now = (float(self.targetTDOAEpsilon), float(self.targetTDOABeta), float(self.targetTDOANoiseFloor), int(self._builtTargetMode),
+               bool(self.separationEnabled), localize, int(self.localizationWindowSize))
+        if self._target_dirty or now != self._sent:
+            self.engine.set_params(float(self.targetTDOAIndex) if self._target_dirty else None, now[0], now[1], now[2],
+                                   0 if now[3] == TARGET_MODE_BOXCAR else 1, now[4], now[5], now[6])
+            self._sent = now
+            self._target_dirty = False
+
+    def _mirror_histories(self):
+        """Optional host-side mirrors for a GUI; the numbers are the device state of the call that just finished."""
+        e = self.engine
+        if self.separationEnabled and self.coefficientMaskHistories:
+            self.coefficientMaskHistories[self.dictionarySize].set(1 - e.export(rt.EXPORT_ATOM_MASK))
         if self.inputSpectrogramHistory:
-            self.inputSpectrogramHistory.set(-np.mean(np.abs(X.cpu().numpy()), axis=0) ** (1 / 3.0))
-        gccPHAT = ang.cpu().numpy() / float(self.numFrequencies)                               # :214 nanmean over frequency, (D, nT)
+            self.inputSpectrogramHistory.set(-np.mean(np.abs(e.export(rt.EXPORT_INPUT_SPEC)), axis=0) ** (1 / 3.0))
         if self.gccPHATHistory:
-            self.gccPHATHistory.set(gccPHAT)
+            self.gccPHATHistory.set(e.export(rt.EXPORT_GCCPHAT))
         if self.tdoaHistory:
-            if self.localizationEnabled:
-                history = self.gccPHATHistory.getUnraveledArray()
-                with np.errstate(all='ignore'):
-                    tdoaIndex = np.argmax(np.nanmean(history[:, -self.localizationWindowSize:], axis=-1))   # :221-222
-                self.targetTDOAIndex = np.float32(tdoaIndex)
+            self.targetTDOAIndex = np.float32(e.export(rt.EXPORT_TARGET)[0])      # the device took the localisation decision (:221-225)
             self.tdoaHistory.set(np.array([[self.targetTDOAIndex]]))
         if self.outputSpectrogramHistory:
-            self.outputSpectrogramHistory.set(-np.nanmean(np.abs(out.cpu().numpy()), axis=0) ** (1 / 3.0))
-        y = h.istft_ola(out, self._synthesis, N, N, gain=1.0, center=False, conjugate=False)   # :231 irfft * synthesis window
-        return np.ascontiguousarray(y.cpu().numpy().reshape(2, nT, N).transpose(0, 2, 1))
+            with np.errstate(all='ignore'):
+                self.outputSpectrogramHistory.set(-np.nanmean(np.abs(e.export(rt.EXPORT_OUTPUT_SPEC)), axis=0) ** (1 / 3.0))
+
+    # ------------------------------------------------------------------ :201-231
+    def processFrames(self, windowedSamples, forcedAtomMask=None):
+        """windowedSamples (2, N, nT) float32 -> (2, N, nT) float32.  forcedAtomMask (K, nT): use this atom mask instead of the
+        one derived from the TDOA argmax (teacher-forced parity tests)."""
+        if self.engine is None:
+            self.buildFunctions()
+        self._sync_params()
+        out = self.engine.process_frames(np.asarray(windowedSamples, dtype=np.float32), forcedAtomMask).copy()
+        self._mirror_histories()
+        return out
+
+    def processBlock(self, inputFrames, hopSize, blockSize, useGraph=True, forcedAtomMask=None):
+        """One audio block through the device-resident overlap-add rings AND processFrames as a single CUDA graph launch:
+        OverlapAddProcessor.processFrames(self.processFrames) of gccNMF/realtime/utils.py:99-116 / gccNMFProcessor.py:97.
+        inputFrames (2, blockSize) float32 -> the next output block (2, blockSize) float32 (two blocks of latency, utils.py:115)."""
+        if self.engine is None or self._geometry != (int(hopSize), int(blockSize)):
+            self.buildFunctions(hopSize, blockSize)
+        self._sync_params()
+        out = self.engine.process_block(np.asarray(inputFrames, dtype=np.float32), use_graph=useGraph, forcedAtomMask=forcedAtomMask)
+        self._mirror_histories()
+        return out

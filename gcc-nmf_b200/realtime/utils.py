@@ -1,10 +1,17 @@
-"""Drop-ins for the numeric helpers of gccNMF/realtime/utils.py: the circular history buffer (:34-70, without
-the multiprocessing shared memory) and the block overlap-add processor (:72-116)."""
+"""Block buffering around the real-time processor (gccNMF/realtime/utils.py): the circular history buffer of the GUI
+(:34-70, here a plain float64 array instead of multiprocessing shared memory) and the block overlap-add processor (:72-116).
+
+The overlap-add rings live ON THE DEVICE whenever the function handed to `OverlapAddProcessor.processFrames` is the bound
+`processFrames` of this package's GCCNMFProcessor: a block is then one H2D copy, one CUDA-graph launch (rings + FFTs + GCC-NMF
+mask + overlap-add + block emit, csrc/rt.cu) and one D2H copy.  Any other callable gets a host ring with the same semantics
+(in-place circular indexing; the reference moves seven blocks of memory per call instead).
+"""
 import numpy as np
 
 
 class CircularBuffer(object):
-    """gccNMF/realtime/utils.py:34-70 (`SharedMemoryCircularBuffer`) on a plain float64 array."""
+    """History ring of gccNMF/realtime/utils.py:34-70 (`SharedMemoryCircularBuffer`): columns are written at a moving index
+    that wraps; `getUnraveledArray` returns them oldest first."""
 
     def __init__(self, shape, initValue=0):
         self.values = np.full(shape, initValue, dtype=np.float64)
@@ -12,60 +19,76 @@ class CircularBuffer(object):
         self.index = 0
 
     def set(self, newValues, index=None):
-        index = self.index if index is None else index
+        start = self.index if index is None else index
         newValues = np.asarray(newValues)
-        n = newValues.shape[-1]
-        if index + n < self.numValues:
-            self.values[..., index:index + n] = newValues
-            self.index = index + n
-        else:
-            numAtEnd = self.numValues - index
-            numAtStart = n - numAtEnd
-            self.values[..., index:] = newValues[..., :numAtEnd]
-            self.values[..., :numAtStart] = newValues[..., numAtEnd:]
-            self.index = numAtStart
+        count = newValues.shape[-1]
+        columns = (start + np.arange(count)) % self.numValues
+        self.values[..., columns] = newValues
+        # a write that reaches the last column wraps the index to the start (:49-59)
+        self.index = int((start + count) % self.numValues)
         return self.index
 
     def get(self, index=None):
-        index = (self.index - 1) % self.numValues if index is None else (index % self.numValues)
-        return self.values[..., index]
+        return self.values[..., (self.index - 1 if index is None else index) % self.numValues]
 
     def getUnraveledArray(self):
-        return np.concatenate([self.values[:, self.index:], self.values[:, :self.index]], axis=-1)
+        return np.roll(self.values, -self.index, axis=-1)
 
     def size(self):
-        return self.values.shape[-1]
+        return self.numValues
 
 
 SharedMemoryCircularBuffer = CircularBuffer
 
 
 class OverlapAddProcessor(object):
-    """gccNMF/realtime/utils.py:72-116: 8-block input/output rings; each call shifts in one block, cuts
-    `windowsPerBlock` windows, runs `processFramesFunction` on (channels, windowSize, windowsPerBlock), overlap-adds
-    the result and emits block [-3B:-2B]."""
+    """gccNMF/realtime/utils.py:72-116.  Each `processFrames(fn)` call pushes `inputFrames` (channels, blockSize) into an 8-block
+    input ring, cuts `windowsPerBlock` windows ending at the newest sample, runs `fn` on (channels, windowSize, windowsPerBlock),
+    overlap-adds the result into an 8-block output ring and writes the block that lies two blocks in the past to `outputFrames`."""
+    numBlocksPerBuffer = 8                                       # utils.py:85
 
     def __init__(self, numChannels, windowSize, hopSize, blockSize, windowsPerBlock, inputFrames, outputFrames):
         self.numChannels, self.windowSize, self.hopSize = numChannels, windowSize, hopSize
         self.blockSize, self.windowsPerBlock = blockSize, windowsPerBlock
         self.inputFrames, self.outputFrames = inputFrames, outputFrames
-        self.numBlocksPerBuffer = 8
         self.inputBufferSize = self.outputBufferSize = blockSize * self.numBlocksPerBuffer
-        self.inputBuffer = np.zeros((numChannels, self.inputBufferSize), np.float32)
-        self.outputBuffer = np.zeros((numChannels, self.outputBufferSize), np.float32)
-        self.windowedSamples = np.zeros((numChannels, windowSize, windowsPerBlock), np.float32)
+        self._calls = 0
+        self._hostRings = None
+
+    # ---- device path
+    @staticmethod
+    def _fused_processor(processFramesFunction):
+        from .gccNMFProcessor import GCCNMFProcessor
+        owner = getattr(processFramesFunction, '__self__', None)
+        if isinstance(owner, GCCNMFProcessor) and getattr(processFramesFunction, '__func__', None) is GCCNMFProcessor.processFrames:
+            return owner
+        return None
 
     def processFrames(self, processFramesFunction):
-        B = self.blockSize
-        self.inputBuffer[:, :-B] = self.inputBuffer[:, B:]
-        self.inputBuffer[:, -B:] = self.inputFrames
-        self.outputBuffer[:, :-B] = self.outputBuffer[:, B:]
-        self.outputBuffer[:, -B:] = 0
-        windowIndexes = np.arange(self.inputBufferSize - self.windowSize - (self.windowsPerBlock - 1) * self.hopSize,
-                                  self.inputBufferSize - self.windowSize + 1, self.hopSize)
-        for i, w in enumerate(windowIndexes):
-            self.windowedSamples[..., i] = self.inputBuffer[:, w:w + self.windowSize]
-        processedFrames = processFramesFunction(self.windowedSamples)
-        for i, w in enumerate(windowIndexes):
-            self.outputBuffer[:, w:w + self.windowSize] += processedFrames[..., i]
-        self.outputFrames[:] = self.outputBuffer[:, -3 * B:-2 * B]
+        processor = self._fused_processor(processFramesFunction) if self.numChannels == 2 else None
+        if processor is not None and processor.numTimePerChunk == self.windowsPerBlock and processor.windowSize == self.windowSize:
+            self.outputFrames[:] = processor.processBlock(self.inputFrames, self.hopSize, self.blockSize)
+            return
+        self._process_on_host(processFramesFunction)
+
+    # ---- host path (any callable)
+    def _process_on_host(self, processFramesFunction):
+        L, B, N = self.inputBufferSize, self.blockSize, self.windowSize
+        if self._hostRings is None:
+            self._hostRings = (np.zeros((self.numChannels, L), np.float32), np.zeros((self.numChannels, L), np.float32))
+        ring_in, ring_out = self._hostRings
+        self._calls += 1
+        newest = self._calls * B                                  # stream position one past the newest sample
+
+        def span(first, count):                                   # ring indexes of stream positions first .. first + count - 1
+            return (first + np.arange(count)) % L
+        fresh = span(newest - B, B)
+        ring_in[:, fresh] = self.inputFrames
+        ring_out[:, fresh] = 0                                    # utils.py:105: the slots being recycled
+        starts = [newest - N - (self.windowsPerBlock - 1 - i) * self.hopSize for i in range(self.windowsPerBlock)]   # utils.py:107
+        windowed = np.stack([ring_in[:, span(s, N)] for s in starts], axis=-1).astype(np.float32)
+        processed = processFramesFunction(windowed)
+        for i, s in enumerate(starts):                            # frame order, float32 ring += frame (utils.py:113-114)
+            idx = span(s, N)
+            ring_out[:, idx] = ring_out[:, idx] + processed[..., i]
+        self.outputFrames[:] = ring_out[:, span(newest - 3 * B, B)]   # utils.py:115

@@ -240,6 +240,63 @@ GCCNMF_API int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int
                                 float* D, int64_t ldd, int M, int N, int Kc, int tile_n,
                                 unsigned long long* timing, void* stream);
 
+/* The numInferenceIterations > 0 branch of the notebooks' frame loop (onlineSpeechEnhancement.ipynb:433-440): with
+ * H (K, 2T) f32 the inferred coefficients (channel c in columns [c T, (c + 1) T)),
+ * wiener (2, F, T) f32 = (W . (H_c * mask)) / (W . H_c) and Y (2, F, T) c64 = wiener * X; wiener may be NULL. */
+GCCNMF_API int gccnmf_wiener_apply_h(gccnmf_handle* h, const float* mask, const float* W, const float* H, const float* X, int F,
+                          int T, int K, float* Y, float* wiener, void* stream);
+
+/* ---- a13 + f-2: the real-time block path as one stream-ordered unit ----------------------------------
+ * GCCNMFProcessor.processFrames (realtime/gccNMFProcessor.py:201-231 and the Theano graph of :245-270) with the
+ * OverlapAddProcessor rings around it (realtime/utils.py:72-116) and, optionally, the per-frame coefficient inference of
+ * notebooks/onlineSpeechEnhancement.ipynb:433-438.  Everything between the input block and the output block runs on
+ * the device without a host synchronisation: five kernels per block (+ two per inference iteration), capturable in a
+ * CUDA graph; the 8-block rings, the GCC-PHAT history, the sliding-window localisation and the target TDOA index are
+ * device-resident state inside the caller-owned `state` buffer (sized by gccnmf_rt_state_bytes, filled by gccnmf_rt_init). */
+typedef struct gccnmf_rt_config {
+  int window_size;           /* N: power of two in [64, 2048] (config.py:63 windowSize)                              */
+  int hop_size;              /* config.py:64                                                                          */
+  int block_size;            /* samples per channel per audio block (config.py:65); the rings hold 8 blocks (utils.py:85) */
+  int windows_per_block;     /* numTimePerChunk = blockSize // hopSize (config.py:112), at most 8                      */
+  int num_atoms;             /* K                                                                                     */
+  int num_tdoas;             /* D <= 128                                                                              */
+  int history_length;        /* columns of the gccPHATHistory ring (runRealtimeGCCNMF.py:58)                          */
+  int inference_iterations;  /* 0 = the reference's real-time class (numHUpdates is never used there); > 0: H-only KL updates */
+  float sparsity_alpha;      /* of the inference updates (gccNMFFunctions.py:76)                                       */
+  float epsilon;
+} gccnmf_rt_config;
+GCCNMF_API size_t gccnmf_rt_state_bytes(const gccnmf_rt_config* cfg);
+/* W (F, K) f32; E (F, D) complex64 = expJOmegaTau (:248); windows (N) f32 (:186); H0 (K, 2) f32 seeded initial coefficients
+ * (gccNMFFunctions.py:73 shape (K, 2)) or NULL when inference_iterations == 0.  Zeroes the rings and the history. */
+GCCNMF_API int gccnmf_rt_init(gccnmf_handle* h, const gccnmf_rt_config* cfg, const float* W, const float* E,
+                   const float* analysis_window, const float* synthesis_window, const float* H0, void* state,
+                   size_t state_bytes, void* stream);
+/* setTargetTDOARange (:272-276) and the attributes GCCNMFProcess sets (:136-151).  mode 0 boxcar / 1 window (:262-265).
+ * set_target = 0 keeps the device-resident target TDOA index (it is loop-carried when localisation is enabled). */
+GCCNMF_API int gccnmf_rt_set_params(gccnmf_handle* h, const gccnmf_rt_config* cfg, void* state, size_t state_bytes,
+                         float target_index, int set_target, float epsilon, float beta, float noise_floor, int mode,
+                         int separation_enabled, int localization_enabled, int localization_window, void* stream);
+/* processFrames: windowed (2, N, nT) f32 -> out (2, N, nT) f32 (device buffers); updates history / localisation.
+ * forced_atom_mask: NULL, or a (K, nT) f64 atom mask that replaces the one derived from the per-atom TDOA argmax
+ * (externally decided masks; teacher-forced parity tests). */
+GCCNMF_API int gccnmf_rt_process_frames(gccnmf_handle* h, const gccnmf_rt_config* cfg, void* state, size_t state_bytes,
+                             const float* windowed, float* out, const double* forced_atom_mask, void* stream);
+/* One audio block through rings + processFrames (utils.py:99-116): in_block (2, B) f32 -> out_block (2, B) f32. */
+GCCNMF_API int gccnmf_rt_process_block(gccnmf_handle* h, const gccnmf_rt_config* cfg, void* state, size_t state_bytes,
+                            const float* in_block, float* out_block, const double* forced_atom_mask, void* stream);
+/* The same block as an instantiated CUDA graph ([H2D of in_host ->] kernels [-> D2H to out_host]); in_host / out_host are
+ * pinned HOST buffers or NULL; `stream` must be a capturable (non-default) stream.  *graph_exec receives a cudaGraphExec_t. */
+GCCNMF_API int gccnmf_rt_graph_create(gccnmf_handle* h, const gccnmf_rt_config* cfg, void* state, size_t state_bytes,
+                           float* in_block, float* out_block, const float* in_host, float* out_host, void** graph_exec,
+                           void* stream);
+GCCNMF_API int gccnmf_rt_graph_launch(gccnmf_handle* h, void* graph_exec, void* stream);
+GCCNMF_API int gccnmf_rt_graph_destroy(gccnmf_handle* h, void* graph_exec);
+/* Stream-ordered copy of one item of the block state to dst (device or pinned host memory): 0 gccPHAT (D, nT) f32,
+ * 1 target TDOA index f32, 2 atom mask (K, nT) f64, 3 / 4 input / output spectrogram (2, F, nT) c64, 5 per-atom TDOA
+ * argmax (K, nT) i32, 6 inferred H (K, 2 nT) f32, 7 GCC-PHAT history ring (D, history_length) f64, 8 its write index i32. */
+GCCNMF_API int gccnmf_rt_export(gccnmf_handle* h, const gccnmf_rt_config* cfg, void* state, size_t state_bytes, int what,
+                     void* dst, void* stream);
+
 /*
  * The building block the KL-NMF loop runs on (klnmf_tma.cu): the same 3-product contraction, TMA-fed, over operands
  * that are pre-split into bf16 hi/lo planes and kept in ONE orientation each; an operand contracted over its

@@ -387,13 +387,18 @@ def performOnlineSpeechEnhancement(stereoSamples, sampleRate, W, analysisWindow,
 
 
 # ----------------------------------------------------------------------------- a13: RT chunk processor
-TARGET_MODE_BOXCAR = 0
-TARGET_MODE_WINDOW_FUNCTION = 1
+TARGET_MODE_BOXCAR = 0               # gccNMFProcessor.py:35-37
+TARGET_MODE_MULTIPLE = 1
+TARGET_MODE_WINDOW_FUNCTION = 2
 
 
 class GCCNMFProcessorOracle(object):
-    """numpy restatement of gccNMF/realtime/gccNMFProcessor.py:167-276.  PARITY UNPINNED (the
-    reference class needs Theano).  float32 / complex64 throughout like the Theano floatX graph.
+    """numpy restatement of gccNMF/realtime/gccNMFProcessor.py:167-276.  The reference class needs Theano, which is absent
+    here; it is PINNED to the output of the unmodified reference class executed over oracle/theano_numpy_shim.py (a numpy
+    evaluation of the reference's own graph): tests/golden/realtime_mini.npz, tests/test_oracle_golden.py.  What that cannot
+    pin is Theano's own arithmetic (BLAS summation order, elementwise kernels) -- say "pinned to the reference's code on numpy
+    arithmetic" when quoting it.  dtypes follow numpy's promotion, which for this graph is also Theano's: the float32 dot,
+    then float64 from `argmax (int64) - targetTDOAIndex (float32)` onwards.
 
     Localisation history: the (numTDOAs, numTDOAHistory) float64 ring of realtime/utils.py:34-65
     (zero-initialised) holding nanmean-over-frequency GCC-PHAT columns (:214-215), kept here in
@@ -432,14 +437,15 @@ class GCCNMFProcessorOracle(object):
         realGCC = (coh[:, :, np.newaxis] * self.expJOmegaTau[:, np.newaxis]).real                  # :254, (F,nT,D)
         self.lastRealGCC = realGCC
         if self.separationEnabled:
-            gccNMF = np.tensordot(realGCC.T, self.W, axes=([2], [0]))                              # :259 (D,nT,K)
-            dist = np.abs(np.argmax(gccNMF, axis=0).T - self.targetTDOAIndex).astype(np.float32)   # (K,nT)
+            gccNMF = np.dot(realGCC.T, self.W)                                                     # :259 (D,nT,K) float32
+            dist = np.abs(np.argmax(gccNMF, axis=0).T - self.targetTDOAIndex)                      # (K,nT): int64 - float32 -> float64
+            self.lastArgmax = np.argmax(gccNMF, axis=0).T
             if self.targetMode == TARGET_MODE_BOXCAR:
-                HMask = np.where(dist < self.targetTDOAEpsilon, np.float32(1), np.float32(0))      # :263
+                HMask = np.where(dist < self.targetTDOAEpsilon, 1.0, 0.0)                          # :263
             else:
                 HMask = (np.exp(-(dist / self.targetTDOAEpsilon) ** self.targetTDOABeta)
-                         / (1 + self.targetTDOANoiseFloor) + self.targetTDOANoiseFloor).astype(np.float32)  # :265
-            tfMask = (np.dot(self.W, HMask).T / np.sum(self.W, axis=-1)).T                         # :267-269
+                         / (1 + self.targetTDOANoiseFloor) + self.targetTDOANoiseFloor)            # :265
+            tfMask = (np.dot(self.W, HMask).T / np.sum(self.W, axis=-1, keepdims=False)).T         # :267-269
             self.lastHMask, self.lastTFMask = HMask, tfMask
             out = tfMask * X                                                                       # :209
         else:

@@ -196,8 +196,81 @@ def golden_wavfile():
     save('wavfile_mini', quiet=quiet, loud=loud, u8=u8, u8_float=refwav.pcm2float(u8), **out)
 
 
+def golden_realtime():
+    """gccNMF/realtime/gccNMFProcessor.py:167-276 (GCCNMFProcessor) and gccNMF/realtime/utils.py:72-116 (OverlapAddProcessor),
+    UNMODIFIED, executed over oracle/theano_numpy_shim.py (Theano itself is absent: the stand-in evaluates the reference's own
+    graph with numpy -- see its header for what that does and does not pin)."""
+    sys.path.insert(0, ROOT)
+    from oracle import theano_numpy_shim
+    theano_numpy_shim.install()
+    from gccNMF.realtime.gccNMFProcessor import GCCNMFProcessor, TARGET_MODE_BOXCAR, TARGET_MODE_WINDOW_FUNCTION
+    from gccNMF.realtime.utils import OverlapAddProcessor, SharedMemoryCircularBuffer
+    sr, N, K, D = 16000, 256, 64, 32
+    rng = np.random.default_rng(77)
+    W = (rng.random((N // 2 + 1, K)) ** 3).astype(np.float32)
+    out = dict(params=np.array([sr, N, K, D]), micSep=np.array(0.1), W=W, targetRange=np.array([10.0, 3.0, 2.0, 0.01]),
+               modes=np.array([TARGET_MODE_BOXCAR, TARGET_MODE_WINDOW_FUNCTION]))
+
+    def make(nT, mode):
+        p = GCCNMFProcessor(sr, N, nT, {'Pretrained': {K: W}}, 'Pretrained', K, 0, 0.1, True, 6,
+                            gccPHATHistory=SharedMemoryCircularBuffer((D, 128)), tdoaHistory=SharedMemoryCircularBuffer((1, 128)))
+        p.numTDOAs = D
+        p.targetMode = mode
+        p.reset()
+        p.setTargetTDOARange(10.0, 3.0, 2.0, 0.01)
+        return p
+
+    for tag, nT, mode in (('w1', 1, TARGET_MODE_WINDOW_FUNCTION), ('b4', 4, TARGET_MODE_BOXCAR), ('w4', 4, TARGET_MODE_WINDOW_FUNCTION)):
+        p = make(nT, mode)
+        steps = 12
+        frames_all, y_all, tgt, hm, am, gp = [], [], [], [], [], []
+        for step in range(steps):
+            # a delayed copy in the right channel gives a well-defined TDOA peak
+            s = rng.standard_normal((N + 8, nT)).astype(np.float32)
+            frames = np.stack([s[4:4 + N], 0.8 * s[2:2 + N] + 0.05 * rng.standard_normal((N, nT)).astype(np.float32)])
+            target_before = float(p.targetTDOAIndex.get_value())
+            y = p.processFrames(frames)
+            target_after = float(p.targetTDOAIndex.get_value())
+            realGCC = p.getComplexGCC()[0].real                    # (F, nT, D) of the spectrogram just processed
+            gccNMF = p.getGCCNMF(realGCC)[0]                       # (D, nT, K)
+            # the mask of this call used the target index of BEFORE its localisation update
+            p.targetTDOAIndex.set_value(np.float32(target_before))
+            hmask = p.getTFMask(realGCC)[1]
+            p.targetTDOAIndex.set_value(np.float32(target_after))
+            frames_all.append(frames); y_all.append(y); tgt.append(target_after)
+            hm.append(np.asarray(hmask, np.float64)); am.append(np.argmax(gccNMF, axis=0).T.astype(np.int32))
+            gp.append(np.nanmean(realGCC, axis=0).T.astype(np.float32))
+        out.update({tag + '_frames': np.stack(frames_all), tag + '_y': np.stack(y_all), tag + '_target': np.array(tgt),
+                    tag + '_hmask': np.stack(hm), tag + '_argmax': np.stack(am), tag + '_gccphat': np.stack(gp)})
+    # the overlap-add ring driving the processor (gccNMFProcessor.py:97), 24 blocks
+    hop, B = 128, 256
+    nT = B // hop
+    p = make(nT, TARGET_MODE_WINDOW_FUNCTION)
+    p.setTargetTDOARange(9.60, 5.0, 2.0, 0.0)                       # the headless runner's messages (runRealtimeGCCNMF.py:141-161)
+    n = 24 * B
+    s = rng.standard_normal(n + 8).astype(np.float32)
+    x = (0.2 * np.stack([s[4:4 + n], 0.8 * s[2:2 + n] + 0.05 * rng.standard_normal(n).astype(np.float32)])).astype(np.float32)
+    inputFrames, outputFrames = np.zeros((2, B), np.float32), np.zeros((2, B), np.float32)
+    olad = OverlapAddProcessor(2, N, hop, B, nT, inputFrames, outputFrames)
+    blocks, targets, masks = [], [], []
+    for b in range(n // B):
+        inputFrames[:] = x[:, b * B:(b + 1) * B]
+        target_before = float(p.targetTDOAIndex.get_value())
+        olad.processFrames(p.processFrames)
+        target_after = float(p.targetTDOAIndex.get_value())
+        p.targetTDOAIndex.set_value(np.float32(target_before))
+        masks.append(np.asarray(p.getTFMask(p.getComplexGCC()[0].real)[1], np.float64))     # the atom mask this block was filtered with
+        p.targetTDOAIndex.set_value(np.float32(target_after))
+        blocks.append(outputFrames.copy())
+        targets.append(target_after)
+    out.update(ola_params=np.array([hop, B, nT]), ola_x=x, ola_out=np.concatenate(blocks, axis=1), ola_target=np.array(targets),
+               ola_hmask=np.stack(masks))
+    save('realtime_mini', **out)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    golden_realtime()
     golden_wavfile()
     golden_separation()
     golden_enhancement()

@@ -109,3 +109,32 @@ def test_stft_istft_edge_cases():
     assert X.shape == (129, 1) and X.dtype == np.complex64
     y = orc.istft(X, 64, 256)
     assert y.shape == (0,) and y.dtype == np.float32   # center trim removes the whole single frame
+
+
+def test_realtime_processor_and_overlap_add_ring(golden):
+    """a13 / f-2: the restatements against the UNMODIFIED reference classes run over the numpy stand-in for Theano
+    (oracle/theano_numpy_shim.py, oracle/make_golden.py:golden_realtime): outputs, atom masks, per-atom TDOA argmax and
+    localisation decisions bit for bit, for both mask modes and 1 / 4 frames per chunk, then the overlap-add ring around it."""
+    g = golden('realtime_mini')
+    sr, N, K, D = [int(v) for v in g['params']]
+    assert list(g['modes']) == [orc.TARGET_MODE_BOXCAR, orc.TARGET_MODE_WINDOW_FUNCTION]
+    for tag, nT, mode in (('w1', 1, orc.TARGET_MODE_WINDOW_FUNCTION), ('b4', 4, orc.TARGET_MODE_BOXCAR), ('w4', 4, orc.TARGET_MODE_WINDOW_FUNCTION)):
+        p = orc.GCCNMFProcessorOracle(sr, N, nT, g['W'], D, float(g['micSep']), localizationEnabled=True, localizationWindowSize=6)
+        p.targetMode = mode
+        p.setTargetTDOARange(*g['targetRange'])
+        for i in range(g[tag + '_frames'].shape[0]):
+            y = p.processFrames(g[tag + '_frames'][i])
+            eq(y, g[tag + '_y'][i])
+            eq(p.lastHMask, g[tag + '_hmask'][i])
+            eq(p.lastArgmax.astype(np.int32), g[tag + '_argmax'][i])
+            assert float(p.targetTDOAIndex) == g[tag + '_target'][i]
+    hop, B, nT = [int(v) for v in g['ola_params']]
+    p = orc.GCCNMFProcessorOracle(sr, N, nT, g['W'], D, float(g['micSep']), localizationEnabled=True, localizationWindowSize=6)
+    p.setTargetTDOARange(9.60, 5.0, 2.0, 0.0)
+    ring = orc.OverlapAddProcessorOracle(2, N, hop, B, nT)
+    x = g['ola_x']
+    for b in range(x.shape[1] // B):
+        out = ring.processFrames(x[:, b * B:(b + 1) * B].copy(), p.processFrames)
+        eq(out, g['ola_out'][:, b * B:(b + 1) * B])
+        eq(p.lastHMask, g['ola_hmask'][b])
+        assert float(p.targetTDOAIndex) == g['ola_target'][b]
