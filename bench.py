@@ -12,7 +12,8 @@ spectrogram -> KL-NMF -> all-TDOA GCC-NMF argmax mask -> masked reconstruction -
          (an all-reduce of the (F x K + K) W-update numerator per KL-NMF iteration); weak scaling.
 
 `--impl reference` times the reference's own CPU algorithm (the numpy oracle port: the reference is
-pure Python and /root/reference does not exist on the GPU box) on this box's host cores.
+pure Python and /root/reference does not exist on the GPU box) on this box's host cores, on the same
+30 s clip per step, BLAS threads pinned and recorded, steps bounded by a time budget.
 """
 import argparse
 import json
@@ -104,53 +105,82 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+def blas_thread_limit():
+    """Threads given to the BLAS pool for the CPU arm: GCCNMF_CPU_THREADS, else every core the pool can use (OpenBLAS builds cap it, 64 here)."""
+    env = os.environ.get('GCCNMF_CPU_THREADS')
+    return int(env) if env else (os.cpu_count() or 1)
+
+
 def cpu_baseline(sample_seconds=3.0, repeats=1):
     """The oracle port of the reference numpy path (offlineSpeechEnhancement.ipynb cells 12-41 order)
-    timed on this box's host cores on a bounded sample of the same workload."""
+    timed on this box's host cores on a bounded sample of the same workload, BLAS threads pinned and recorded."""
     from oracle import gccnmf_oracle as orc
     from gcc_nmf_b200.synth import synthetic_stereo
-    try:
-        from threadpoolctl import threadpool_info
-        blas = [(i.get('internal_api'), i.get('num_threads')) for i in threadpool_info()]
-    except Exception:
-        blas = []
+    from threadpoolctl import threadpool_info, threadpool_limits
     x = synthetic_stereo(CFG['duration_s'])[:, :int(sample_seconds * CFG['sampleRate'])]
     frames = 1 + (x.shape[1] - CFG['windowSize']) // CFG['hopSize']
     best, stages = None, None
-    for _ in range(repeats):
-        tm = {}
-        t0 = time.perf_counter()
-        orc.runEnhancement(x, CFG['sampleRate'], CFG['windowSize'], CFG['hopSize'], CFG['numTDOAs'],
-                           CFG['microphoneSeparationInMetres'], CFG['dictionarySize'], CFG['numIterations'], timings=tm)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, stages = dt, tm
-    return {'value': frames / best, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+    with threadpool_limits(limits=blas_thread_limit()):
+        blas = sorted({(i.get('internal_api'), i.get('num_threads')) for i in threadpool_info()})
+        for _ in range(repeats):
+            tm = {}
+            t0 = time.perf_counter()
+            orc.runEnhancement(x, CFG['sampleRate'], CFG['windowSize'], CFG['hopSize'], CFG['numTDOAs'],
+                               CFG['microphoneSeparationInMetres'], CFG['dictionarySize'], CFG['numIterations'], timings=tm)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, stages = dt, tm
+    threads = max([n for _, n in blas] or [1])
+    return {'value': frames / best, 'unit': UNIT, 'cores': int(min(threads, os.cpu_count() or threads)), 'kind': 'port',
             'sample': '%.1f s of the same synthetic clip (%d frames), same N/hop/K/D/iterations; %.2f s of CPU work; '
-                      'numpy %s, BLAS threads %s' % (sample_seconds, frames, best, np.__version__, blas),
-            'seconds': best, 'frames': frames, 'stage_seconds': {k: round(v, 3) for k, v in stages.items()}}
+                      'numpy %s, BLAS pools %s, %d logical CPUs, %s' % (sample_seconds, frames, best, np.__version__, blas, os.cpu_count() or 0, cpu_model()),
+            'seconds': best, 'frames': frames, 'logical_cpus': os.cpu_count(), 'cpu_model': cpu_model(), 'blas_pools': [list(b) for b in blas],
+            'stage_seconds': {k: round(v, 3) for k, v in stages.items()}}
+
+
+REFERENCE_ARM_BUDGET_S = float(os.environ.get('GCCNMF_REFERENCE_BUDGET_S', '300'))
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU algorithm (the numpy oracle port: the reference is pure Python and does not
+    travel to the GPU box) on the SAME workload as the GPU arm -- every step is the whole 30 s clip (1872 frames).  One step
+    is ~30 s of host work, so the number of steps actually executed is bounded by a time budget (GCCNMF_REFERENCE_BUDGET_S,
+    default 300 s: one warm-up + as many timed steps as fit, at least one); `steps` reports what ran, `steps_requested` what was asked."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample_s = 3.0
+    t_start = time.perf_counter()
     vals = []
-    for i in range(args.warmup + args.steps):
-        b = cpu_baseline(sample_s)
-        if i >= args.warmup:
-            vals.append(b)
-    v = float(np.mean([b['value'] for b in vals]))
-    sec = float(np.mean([b['seconds'] for b in vals]))
-    b = vals[-1]
+    warm = cpu_baseline(CFG['duration_s']) if args.warmup > 0 else None      # thread pools, page cache
+    est = warm['seconds'] if warm else 40.0
+    while len(vals) < max(1, args.steps):
+        if vals and time.perf_counter() - t_start + est > REFERENCE_ARM_BUDGET_S:
+            break
+        vals.append(cpu_baseline(CFG['duration_s']))
+        est = vals[-1]['seconds']
+    v = [b['value'] for b in vals]
+    sec = [b['seconds'] for b in vals]
+    b = vals[int(np.argsort(sec)[len(sec) // 2])]                # the median step
+    value = float(np.median(v))
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(vals), 'steps_requested': args.steps,
+        'warmup': 1 if warm else 0, 'ms_per_step': float(np.median(sec)) * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(1),
-        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': b['cores'], 'kind': 'port', 'sample': b['sample'],
+        'value_min': float(min(v)), 'value_max': float(max(v)), 'value_median': value,
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': b['cores'], 'kind': 'port', 'sample': b['sample'],
+                         'logical_cpus': b['logical_cpus'], 'cpu_model': b['cpu_model'], 'blas_pools': b['blas_pools'],
                          'stage_seconds': b['stage_seconds']},
-        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm

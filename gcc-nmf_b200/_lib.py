@@ -65,7 +65,8 @@ SIGNATURES = {
     'gccnmf_atom_mask': (c_int, [_H, _P, c_int, c_int, _P, c_float, c_float, c_int, c_float, c_float, _P, _S]),
     'gccnmf_wiener_apply_workspace_bytes': (c_size_t, [c_int]),
     'gccnmf_wiener_apply': (c_int, [_H, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _S]),
-    'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _S]),
+    'gccnmf_masked_recon_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _S]),
     'gccnmf_gemm_tn_3xtf32': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _S]),
     'gccnmf_debug_timing': (c_int64, [_H, _P, c_int]),
     'gccnmf_klnmf_tile_plan': (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int)]),
@@ -379,14 +380,15 @@ class Handle(object):
         self.check(self.lib.gccnmf_wiener_apply_h(self.h, _ptr(mask), _ptr(W), _ptr(H), _ptr(X), F, T, K, _ptr(Y), _ptr(wiener), self.stream))
         return (Y, wiener) if want_filter else Y
 
-    def masked_recon_phase(self, masks, X, W, H, out_key=None):
+    def masked_recon_phase(self, masks, X, W, H, out_key=None, tensor_cores=True):
         """masks (S,K,T) f32, X (2,F,T) c64, W (F,K), H (K,2T) -> (S,2,F,T) c64."""
         torch = self.torch
         S, K, T = masks.shape
         F = X.shape[1]
         out = self._out(out_key, 'est', (S, 2, F, T), torch.complex64)
+        ws = self.workspace('masked_recon', self.lib.gccnmf_masked_recon_workspace_bytes(S, F, T, K)) if tensor_cores else None
         self.check(self.lib.gccnmf_masked_recon_phase(self.h, _ptr(masks), _ptr(X), _ptr(W), _ptr(H), S, F, T, K,
-                                                      _ptr(out), self.stream))
+                                                      _ptr(out), _ptr(ws), ws.numel() if ws is not None else 0, self.stream))
         return out
 
 

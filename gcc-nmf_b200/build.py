@@ -43,10 +43,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
-    cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-cudart', 'static', '-Xlinker', '--exclude-libs,ALL']
+    tmp = OUT + '.tmp%d' % os.getpid()      # link beside the target, then rename: a reader never sees a half-written library
+    cmd = [NVCC, '-shared', '-o', tmp] + objs + ['-cudart', 'static', '-Xlinker', '--exclude-libs,ALL']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    os.replace(tmp, OUT)
     return OUT
 
 

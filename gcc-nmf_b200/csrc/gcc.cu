@@ -404,6 +404,11 @@ bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 }  // namespace
 
+// gcc_tc.cu
+bool gccnmf_masked_recon_tc_supported(int S, int F, int T, int K);
+extern "C" int gccnmf_masked_recon_planes(gccnmf_handle* h, const float* masks, const float* X, const float* W, const float* H, int S, int F, int T,
+                                          int K, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" {
 
 size_t gccnmf_phat_angspec_workspace_bytes(int F, int T, int D) {
@@ -481,9 +486,13 @@ int gccnmf_argmax_mask(gccnmf_handle* h, const int32_t* argmax, int K, int T, co
 }
 
 int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W, const float* H, int S, int F,
-                              int T, int K, float* out, void* stream) {
+                              int T, int K, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   GCCNMF_ENTER(h);
   GCCNMF_REQUIRE(h, S > 0 && F > 0 && T > 0 && K > 0 && masks && X && W && H && out, "masked_recon_phase: bad arguments");
+  // tensor cores (plane GEMM over masked-H planes, gcc_tc.cu) when the caller provides the workspace and the shape is covered;
+  // else the float32 SIMT GEMM below
+  if (workspace && !h->force_simt_nmf && gccnmf_masked_recon_tc_supported(S, F, T, K))
+    return gccnmf_masked_recon_planes(h, masks, X, W, H, S, F, T, K, out, workspace, workspace_bytes, stream);
   dim3 grid((T + RN - 1) / RN, (F + RM - 1) / RM, S * 2);
   GCCNMF_LAUNCH(h, masked_recon_kernel, grid, kReconThreads, 0, stream, masks, reinterpret_cast<const float2*>(X), W, H, F, T, K,
                 reinterpret_cast<float2*>(out));

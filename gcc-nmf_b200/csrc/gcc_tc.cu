@@ -1,95 +1,133 @@
 // All-TDOA GCC-NMF argmax on the tensor cores with exact float64 refinement
-// (reference: notebooks/offlineSpeechEnhancement.ipynb cells 27+29, :444-467; online :422-423).
+// (reference: notebooks/offlineSpeechEnhancement.ipynb cells 27+29, :444-467; online :422-423), and the masked reconstruction
+// (gccNMF/gccNMFFunctions.py:145-151) on the same TMA-fed plane GEMM (tma_gemm.cuh) the KL-NMF loop runs on.
 //
 //   gccNMF[k, tau, t] = sum_f W[f, k] * Re(C[f, t] E[f, tau])        argmax over tau per (k, t)
 //
 // The reference evaluates this in float64 and the argmax must be the reference's, bit for bit.  A
 // float64 contraction is 126 GFLOP at the headline shape (10.9 ms on the SIMT float64 kernel), so:
-//   1. build  G[(t, tau), f] = Re(C E)  once, float64 product rounded to float32            (HBM-bound)
-//   2. argmax over tau of  W^T . G^T  with the 3xTF32 tcgen05 GEMM (M = atoms, N = (t, tau), over f):
-//      the epilogue keeps, per (atom, frame), the best and second-best value and the index of the best;
+//   1. build  G[(t, tau), f] = Re(C E)  once: float64 product, rounded to float32, split into bf16 hi / lo planes  (HBM-bound)
+//   2. W^T . G^T  on the plane GEMM (3 bf16 products per algorithmic product; M = atoms: W is consumed MN-major as it lies,
+//      N = (t, tau) in 256-column tiles = 256 / D whole frames, over f; m-fastest grid + TMA multicast of the G tile to the pair of
+//      m tiles that share it, so G streams from HBM once); the whole-tile epilogue keeps, per (atom, frame), the best and
+//      second-best value and the index of the best;
 //   3. every (atom, frame) whose margin best - second is below the worst-case error of step 2
-//      (kMarginFactor * sum_f |W[f, atom]|, since |G| <= 1) is appended to a list and recomputed EXACTLY in
+//      (margin_factor(F) * sum_f |W[f, atom]|, since |G| <= 1) is appended to a list and recomputed EXACTLY in
 //      float64 from C, E and W by a warp (the same arithmetic as the float64 kernel in gcc.cu).
 // Decisions with a safe margin cannot differ from the float64 ones; the others are the float64 ones.
 #include <algorithm>
 
 #include "common.cuh"
-#include "umma_gemm.cuh"
+#include "tma_gemm_host.cuh"
 
 namespace {
 
-using umma::GemmArgs;
+using namespace tgemm_host;
 
-// Error budget of step 2 relative to sum_f |W| (|G| <= 1): 3xBF16 operand split <= 2^-17 per product (worst case, all
-// coherent), float32 rounding of G 2^-24, accumulator truncation <= 2^-24 per accumulation x (3 F / 16) accumulations
-// (measured 1.2e-5 at 384 accumulations, tests/test_gpu_umma.py): < 2e-5 per value.  Margin = 2 x that + slack: two
-// values each off by the bound.
-constexpr float kMarginFactor = 6e-5f;
+// Error budget of step 2 relative to sum_f |W| (|G| <= 1): the bf16 hi / lo split leaves 2^-18 of each operand and drops the
+// lo.lo term (2^-18): <= 3 x 2^-18 per product, worst case all coherent; float32 rounding of G 2^-24; the truncating float32
+// TMEM accumulator <= 2^-24 per accumulation over 3 F / 16 accumulations (measured 1.2e-5 at 384 accumulations,
+// tests/test_gpu_tma.py).  The margin is twice that (two values, each off by the bound) plus 25 % slack; it grows with F.
+inline float margin_factor(int F) {
+  const double per_value = 3.0 / 262144.0 + (1.0 + 3.0 * F / 16.0) / 16777216.0;
+  return (float)(2.5 * per_value);
+}
 
-// ------------------------------------------------------------------ step 1: G[(t, tau)][f]
-// CTA = 32 bins x 32 frames x all TDOAs.  Warp w owns the TDOAs d = w, w + 8, ... ; lane = bin f, so every store is one
-// 128-byte row segment of G.  E[f][d] is loaded once per (thread, d) -- its rows are D * 16 bytes apart, so a warp's load
-// touches 32 lines: doing it inside the frame loop made the kernel L1-wavefront-bound (321 us for 247 MB) -- and reused for
-// the 32 frames of the tile, whose coherence values sit in shared memory.
+// ------------------------------------------------------------------ step 1: planes of G[(t, tau)][f]
+// CTA = 64 bins x 32 frames x all TDOAs.  Warp w owns the TDOAs d = w, w + 8, ... ; lane = bins 2 l, 2 l + 1, so every store is one
+// 128-byte row segment of a plane.  E[f][d] is loaded once per (thread, d) -- its rows are D * 16 bytes apart, so a warp's load
+// touches 32 lines: doing it inside the frame loop made the first version L1-wavefront-bound -- and reused for the 32 frames of
+// the tile, whose coherence values sit in shared memory.
 __global__ void __launch_bounds__(256)
-build_gcc_matrix_kernel(const float2* __restrict__ coh, int F, int T, const double2* __restrict__ E, int D, float* __restrict__ G, int64_t ldg) {
-  __shared__ float2 Cs[32][33];   // [f][t]
-  const int f0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+build_gcc_planes_kernel(const float2* __restrict__ coh, int F, int T, const double2* __restrict__ E, int D, bf16* __restrict__ G, int64_t pitch,
+                        int64_t plane) {
+  __shared__ float2 Cs[64][33];   // [f][t]
+  const int f0 = blockIdx.x * 64, t0 = blockIdx.y * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = w; i < 32; i += 8) {
+  for (int i = w; i < 64; i += 8) {
     const int f = f0 + i, t = t0 + lane;
     Cs[i][lane] = (f < F && t < T) ? coh[(int64_t)f * T + t] : float2{0.f, 0.f};
   }
   __syncthreads();
-  const int f = f0 + lane;
-  if (f >= ldg) return;
+  const int f = f0 + 2 * lane;
+  if (f >= pitch) return;
   const int t_end = min(32, T - t0);
-  for (int d0 = w; d0 < D; d0 += 32) {            // 4 TDOAs per pass: d0, d0 + 8, d0 + 16, d0 + 24
-    double2 e[4];
+  for (int d0 = w; d0 < D; d0 += 16) {            // 2 TDOAs per pass: d0, d0 + 8
+    double2 e[2][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int d = d0 + 8 * j;
-      e[j] = (f < F && d < D) ? __ldg(E + (int64_t)f * D + d) : double2{0.0, 0.0};
-    }
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int d = d0 + 8 * j;
+        e[j][q] = (f + q < F && d < D) ? __ldg(E + (int64_t)(f + q) * D + d) : double2{0.0, 0.0};
+      }
     for (int tt = 0; tt < t_end; ++tt) {
-      const float2 c = Cs[lane][tt];
-      float* row = G + ((int64_t)(t0 + tt) * D + d0) * ldg + f;
+      const float2 c0 = Cs[2 * lane][tt], c1 = Cs[2 * lane + 1][tt];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (d0 + 8 * j < D) row[(int64_t)(8 * j) * ldg] = (float)((double)c.x * e[j].x - (double)c.y * e[j].y);
+      for (int j = 0; j < 2; ++j) {
+        if (d0 + 8 * j >= D) break;
+        // float64 product rounded to float32 (what the float64 contraction sees to 2^-24), then the hi / lo split
+        const float g0 = (float)((double)c0.x * e[j][0].x - (double)c0.y * e[j][0].y);
+        const float g1 = (float)((double)c1.x * e[j][1].x - (double)c1.y * e[j][1].y);
+        bf16 h0, l0, h1, l1;
+        split_bf16(g0, h0, l0);
+        split_bf16(g1, h1, l1);
+        bf16* row = G + ((int64_t)(t0 + tt) * D + d0 + 8 * j) * pitch + f;
+        *reinterpret_cast<__nv_bfloat162*>(row) = __nv_bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162*>(row + plane) = __nv_bfloat162(l0, l1);
+      }
     }
   }
 }
 
-// ------------------------------------------------------------------ step 2: epilogue
-struct EpiArgmaxTDOA {
-  struct State { float best, second; int idx; int nan; };
+// planes[p][i] = split(src[i])  (W as it lies: (F, K) row-major = MN-major operand of the argmax GEMM, K-major of the reconstruction)
+__global__ void split_to_planes_kernel(const float* __restrict__ src, int64_t n, bf16* __restrict__ planes, int64_t plane) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bf16 hi, lo;
+  split_bf16(src[i], hi, lo);
+  planes[i] = hi;
+  planes[plane + i] = lo;
+}
+
+// ------------------------------------------------------------------ step 2: whole-tile epilogue of the plane GEMM
+// tile[n][m]: m = atom (128 per tile), n = (frame, TDOA) with BN / D whole frames per tile.  One thread per (atom, frame) scans the
+// D columns of its frame (consecutive atoms = consecutive shared-memory words: no bank conflicts).
+struct EpiArgmaxTile {
+  static constexpr bool kTileEpilogue = true;
+  static constexpr bool kRowReduce = false;
+  static constexpr int kRowValues = 0;
+  static constexpr bool kPrefetch = false;
+  struct State {};
+  struct Loaded {};
   int32_t* __restrict__ argmax;        // (K, T)
-  const float* __restrict__ colsumW;   // (K) sum_f |W[f,k]| = colsum (W >= 0)
+  const float* __restrict__ colsumW;   // (K) sum_f |W[f,k]|
   int2* __restrict__ list; int* __restrict__ count; int capacity;
-  int K, T, D, N;
-  __device__ void init(State& s) const { s.best = -INFINITY; s.second = -INFINITY; s.idx = 0; s.nan = 0; }
-  __device__ void elem(int, int, float, int) const {}   // M = atoms is tiled without SIMT tail rows (K % 128 handled by predication)
-  __device__ void tile(int m_base, int lane, int n0, float (&v)[32], int, int, float*, State& s) const {
-    const int d0 = n0 % D;
-    if (d0 == 0) init(s);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = v[j];
-      if (x != x) s.nan = 1;                 // NaN anywhere: let float64 decide with numpy's NaN rules
-      if (x > s.best) { s.second = s.best; s.best = x; s.idx = d0 + j; }
-      else if (x > s.second) s.second = x;
-    }
-    if (d0 + 32 == D) {
-      const int m = m_base + lane, t = n0 / D;
-      if (m < K && n0 < N) {
-        argmax[(int64_t)m * T + t] = s.idx;
-        const float margin = kMarginFactor * colsumW[m];
-        if (s.nan || !(s.best - s.second > margin)) {
-          const int slot = atomicAdd(count, 1);
-          if (slot < capacity) list[slot] = make_int2(m, t);
-        }
+  int K, T, D; float margin_factor;
+  __device__ void prefetch(int, int) const {}
+  __device__ void row_values(int, float*) const {}
+  __device__ void elem(int, int, float, int) const {}
+  __device__ void tile_epilogue(const float* __restrict__ tile, int m0, int n0, int n_valid, int) const {
+    const int frames = n_valid / D;                         // N = T D and the tile width is a multiple of D
+    for (int p = threadIdx.x; p < tgemm::kBM * frames; p += blockDim.x) {
+      const int ml = p & (tgemm::kBM - 1), j = p / tgemm::kBM;
+      const int m = m0 + ml;
+      if (m >= K) continue;
+      const float* col = tile + (size_t)(j * D) * tgemm::kBM + ml;
+      float best = -INFINITY, second = -INFINITY;
+      int idx = 0, nan = 0;
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) {
+        const float x = col[(size_t)d * tgemm::kBM];
+        if (x != x) nan = 1;                 // NaN anywhere: let float64 decide with numpy's NaN rules
+        if (x > best) { second = best; best = x; idx = d; }
+        else if (x > second) second = x;
+      }
+      const int t = n0 / D + j;
+      argmax[(int64_t)m * T + t] = idx;
+      if (nan || !(best - second > margin_factor * colsumW[m])) {
+        const int slot = atomicAdd(count, 1);
+        if (slot < capacity) list[slot] = make_int2(m, t);
       }
     }
   }
@@ -213,21 +251,6 @@ refine_argmax_shared_kernel(const int2* __restrict__ list, const int* __restrict
   }
 }
 
-__global__ void transpose_w_kernel(const float* __restrict__ W, int F, int K, float* __restrict__ WT, int64_t ldwt, float* __restrict__ colsum) {
-  __shared__ float tile[32][33];
-  const int k0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int f = f0 + i, k = k0 + threadIdx.x;
-    tile[i][threadIdx.x] = (f < F && k < K) ? W[(int64_t)f * K + k] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int k = k0 + i, f = f0 + threadIdx.x;
-    if (k < K && f < ldwt) WT[(int64_t)k * ldwt + f] = tile[threadIdx.x][i];
-  }
-  (void)colsum;
-}
-
 __global__ void abs_colsum_kernel(const float* __restrict__ W, int F, int K, float* __restrict__ colsum) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
@@ -236,11 +259,14 @@ __global__ void abs_colsum_kernel(const float* __restrict__ W, int F, int K, flo
   colsum[k] = s;
 }
 
+constexpr int kArgmaxTile = 256;       // columns (frame, TDOA) per tile: 256 / D whole frames
+
 struct ArgmaxWorkspace {
-  float *G, *WT, *colsum;
+  bf16 *Gp, *Wp;
+  float* colsum;
   int2* list;
   int* count;
-  int64_t Fp;
+  int64_t Fp, plane_g, plane_w;
   int capacity;
   bool ok;
 };
@@ -248,39 +274,135 @@ struct ArgmaxWorkspace {
 int list_capacity(int K, int T) { return (int)std::min<int64_t>((int64_t)K * T, std::max<int64_t>(1 << 16, (int64_t)K * T / 8)); }
 
 ArgmaxWorkspace carve_argmax(void* ws, size_t bytes, int F, int T, int D, int K) {
-  WorkspaceCarver c(ws, bytes);
+  WorkspaceCarver c(ws ? ws : reinterpret_cast<void*>(256), ws ? bytes : ~size_t(0) >> 1);
   ArgmaxWorkspace w;
-  w.Fp = (F + 3) & ~3;
+  w.Fp = (F + 7) & ~7;
+  w.plane_g = (int64_t)T * D * w.Fp;
+  w.plane_w = (int64_t)F * K;
   w.capacity = list_capacity(K, T);
-  w.G = c.take<float>((size_t)T * D * w.Fp);
-  w.WT = c.take<float>((size_t)K * w.Fp);
+  w.Gp = c.take<bf16>((size_t)2 * w.plane_g);
+  w.Wp = c.take<bf16>((size_t)2 * w.plane_w);
   w.colsum = c.take<float>(K);
   w.list = c.take<int2>(w.capacity);
   w.count = c.take<int>(4);
-  w.ok = c.ok();
+  w.ok = ws != nullptr && c.ok();
+  w.plane_g = (int64_t)T * D * w.Fp;
   return w;
 }
+size_t argmax_workspace_bytes(int F, int T, int D, int K) {
+  WorkspaceCarver c(reinterpret_cast<void*>(256), ~size_t(0) >> 1);
+  const size_t Fp = (F + 7) & ~7;
+  c.take<bf16>((size_t)2 * T * D * Fp); c.take<bf16>((size_t)2 * F * K); c.take<float>(K); c.take<int2>(list_capacity(K, T)); c.take<int>(4);
+  return align_up(c.used, 256);
+}
 
-template <class Epi>
-int launch_argmax_gemm(gccnmf_handle* h, const GemmArgs& args, const Epi& epi, void* stream) {
-  using S = umma::GemmSmem<128, umma::kSplitBF16>;
-  auto kernel = umma::gemm_tn_3xtf32_kernel<128, false, umma::kSplitBF16, umma::kLoaderWarps, Epi>;
-  static DeviceFlags configured;     // per device: the attribute belongs to the device's copy of the kernel
-  if (!configured(h)) {
-    GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured(h) = true;
+// ------------------------------------------------------------------ a8: masked reconstruction on the plane GEMM
+// est[s][c] (F, T) = (W . (H_c * M_s)) * exp(j angle(X_c))  (gccNMFFunctions.py:150-151), computed transposed so that every operand
+// is consumed as it lies:  D[m = (batch b = 2 s + c, t), n = f] = sum_k A(m, k) B(f, k),  A = masked H planes (K rows, frames
+// contiguous: MN-major; the batches are stacked along m, each padded to whole 128-frame tiles), B = W planes (F, K): K-major.
+// The by-column epilogue owns 4 consecutive frames of one bin: one 32-byte complex64 segment of est per lane.
+__global__ void masked_h_planes_kernel(const float* __restrict__ H, const float* __restrict__ masks, int S, int K, int T, int Tpad,
+                                       bf16* __restrict__ planes, int64_t pitch, int64_t plane) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)K * pitch) return;
+  const int k = (int)(i / pitch), col = (int)(i - (int64_t)k * pitch);
+  const int b = col / Tpad, t = col - b * Tpad;
+  float v = 0.f;
+  if (t < T) v = H[(int64_t)k * (2 * T) + (int64_t)(b & 1) * T + t] * masks[((int64_t)(b >> 1) * K + k) * T + t];   // H_c * M_s
+  bf16 hi, lo;
+  split_bf16(v, hi, lo);
+  planes[i] = hi;
+  planes[plane + i] = lo;
+  (void)S;
+}
+
+struct EpiReconPhase {
+  struct State {};
+  struct Loaded { float4 x01, x23; };
+  static constexpr bool kRowReduce = false;
+  static constexpr int kRowValues = 0;
+  static constexpr bool kPrefetch = false;
+  const float2* __restrict__ X;    // (2, F, T)
+  float2* __restrict__ out;        // (S, 2, F, T)
+  int F, T, Tpad, M; bool vec;     // M = batches * Tpad
+  __device__ void prefetch(int, int) const {}
+  __device__ void row_values(int, float*) const {}
+  __device__ void init(State&, int, const float*) const {}
+  __device__ float4 row_partial(const State&) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ void row_total(int, int, float) const {}
+  __device__ void elem(int, int, float, int) const {}
+  // exp(1j * angle(X)) (gccNMFFunctions.py:151): unit phasor of the mixture bin; angle(0) = 0
+  __device__ static float2 phase_times(float a, float2 x) {
+    const double mag = sqrt((double)x.x * x.x + (double)x.y * x.y);
+    float pr = 1.f, pi = 0.f;
+    if (mag > 0.0) { pr = (float)((double)x.x / mag); pi = (float)((double)x.y / mag); }
+    else if (mag != mag) { pr = pi = __int_as_float(0x7fc00000); }
+    return float2{a * pr, a * pi};
   }
-  // x = atom tiles (fastest) so that the CTAs sharing one slab of G run together and it is read from HBM once
-  dim3 grid(args.m_tiles, (args.N + 127) / 128, 1);
-  GCCNMF_LAUNCH(h, kernel, grid, umma::kThreads, S::kTotal, stream, args, epi);
-  return 0;
+  __device__ Loaded load(int m, int n) const {
+    Loaded l;
+    l.x01 = l.x23 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= M) return l;
+    const int b = m / Tpad, t = m - b * Tpad;
+    const float2* src = X + ((int64_t)(b & 1) * F + n) * T + t;
+    if (vec && t + 4 <= T) {
+      l.x01 = *reinterpret_cast<const float4*>(src);
+      l.x23 = *reinterpret_cast<const float4*>(src + 2);
+    } else {
+      float2 v[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+      for (int i = 0; i < 4; ++i)
+        if (t + i < T) v[i] = src[i];
+      l.x01 = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+      l.x23 = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+    }
+    return l;
+  }
+  __device__ void store(int m, int n, const float4& acc, const Loaded& l, int, State&) const {
+    if (m >= M) return;
+    const int b = m / Tpad, t = m - b * Tpad;      // (Tpad is a multiple of 4: the 4 rows of a lane lie in one batch)
+    if (t >= T) return;
+    float2* dst = out + ((int64_t)b * F + n) * T + t;
+    const float2 r0 = phase_times(acc.x, float2{l.x01.x, l.x01.y}), r1 = phase_times(acc.y, float2{l.x01.z, l.x01.w});
+    const float2 r2 = phase_times(acc.z, float2{l.x23.x, l.x23.y}), r3 = phase_times(acc.w, float2{l.x23.z, l.x23.w});
+    if (vec && t + 4 <= T) {
+      *reinterpret_cast<float4*>(dst) = make_float4(r0.x, r0.y, r1.x, r1.y);
+      *reinterpret_cast<float4*>(dst + 2) = make_float4(r2.x, r2.y, r3.x, r3.y);
+    } else {
+      const float2 r[4] = {r0, r1, r2, r3};
+      for (int i = 0; i < 4; ++i)
+        if (t + i < T) dst[i] = r[i];
+    }
+  }
+};
+
+struct ReconWorkspace {
+  bf16 *Ap, *Wp;
+  int64_t pitch, plane_a, plane_w;
+  int Tpad;
+  size_t bytes;
+  bool ok;
+};
+ReconWorkspace carve_recon(void* ws, size_t bytes, int S, int F, int T, int K) {
+  WorkspaceCarver c(ws ? ws : reinterpret_cast<void*>(256), ws ? bytes : ~size_t(0) >> 1);
+  ReconWorkspace w;
+  w.Tpad = (T + tgemm::kBM - 1) / tgemm::kBM * tgemm::kBM;
+  w.pitch = (int64_t)2 * S * w.Tpad;
+  w.plane_a = (int64_t)K * w.pitch;
+  w.plane_w = (int64_t)F * K;
+  w.Ap = c.take<bf16>((size_t)2 * w.plane_a);
+  w.Wp = c.take<bf16>((size_t)2 * w.plane_w);
+  w.bytes = align_up(c.used, 256);
+  w.ok = ws != nullptr && c.ok();
+  return w;
 }
 
 }  // namespace
 
 bool gccnmf_tdoa_argmax_tc_supported(int F, int T, int D, int K) {
-  return (D == 32 || D == 64) && K % 4 == 0 && K >= 32 && F >= 64 && (int64_t)T * D >= 128 && (int64_t)T * D < ((int64_t)1 << 31);
+  const bool d_ok = D >= 8 && D <= 128 && (D & (D - 1)) == 0;          // whole frames per 256-column tile; refinement kernels: D <= 128
+  return d_ok && K % 8 == 0 && K >= 64 && F >= 32 && (int64_t)T * D >= kArgmaxTile && (int64_t)T * D < ((int64_t)1 << 31);
 }
+bool gccnmf_masked_recon_tc_supported(int S, int F, int T, int K) { return S >= 1 && K % 8 == 0 && K >= 64 && F >= 64 && T >= 64; }
 
 extern "C" {
 
@@ -289,11 +411,7 @@ int gccnmf_tdoa_argmax_refine_capacity(int K, int T) { return (K > 0 && T > 0) ?
 size_t gccnmf_tdoa_argmax_workspace_bytes(int F, int T, int D, int K) {
   if (F <= 0 || T <= 0 || D <= 0 || K <= 0) return 0;
   if (!gccnmf_tdoa_argmax_tc_supported(F, T, D, K)) return 256;
-  const size_t Fp = (F + 3) & ~3;
-  size_t n = 0;
-  auto add = [&](size_t b) { n = align_up(n, 256) + b; };
-  add((size_t)T * D * Fp * 4); add((size_t)K * Fp * 4); add((size_t)K * 4); add((size_t)list_capacity(K, T) * 8); add(16);
-  return align_up(n, 256);
+  return argmax_workspace_bytes(F, T, D, K);
 }
 
 int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, const double* E, int D, const float* W, int K,
@@ -308,14 +426,16 @@ int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, c
   ArgmaxWorkspace w = carve_argmax(workspace, workspace_bytes, F, T, D, K);
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "tdoa_argmax workspace too small: need %zu bytes", gccnmf_tdoa_argmax_workspace_bytes(F, T, D, K));
   GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.count, 0, 16, (cudaStream_t)stream));
-  GCCNMF_LAUNCH(h, build_gcc_matrix_kernel, dim3((int)((w.Fp + 31) / 32), (T + 31) / 32), 256, 0, stream,
-                reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, w.G, w.Fp);
-  GCCNMF_LAUNCH(h, transpose_w_kernel, dim3((K + 31) / 32, (int)((w.Fp + 31) / 32)), dim3(32, 8), 0, stream, W, F, K, w.WT, w.Fp, w.colsum);
+  GCCNMF_LAUNCH(h, build_gcc_planes_kernel, dim3((int)((w.Fp + 63) / 64), (T + 31) / 32), 256, 0, stream,
+                reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, w.Gp, w.Fp, w.plane_g);
+  const int64_t nw = (int64_t)F * K;
+  GCCNMF_LAUNCH(h, split_to_planes_kernel, (unsigned)((nw + 255) / 256), 256, 0, stream, W, nw, w.Wp, w.plane_w);
   GCCNMF_LAUNCH(h, abs_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
   const int N = T * D;
-  GemmArgs args{w.WT, w.G, K, N, F, w.Fp, w.Fp, (F + umma::kBK - 1) / umma::kBK, (K + umma::kBM - 1) / umma::kBM, nullptr, nullptr, 1};
-  EpiArgmaxTDOA epi{argmax, w.colsum, w.list, w.count, w.capacity, K, T, D, N};
-  if (int st = launch_argmax_gemm(h, args, epi, stream)) return st;
+  const Operand Wmn{w.Wp, (int64_t)K, w.plane_w, true};          // A(m = atom, k = f): (F, K) as it lies
+  const Operand Gk{w.Gp, w.Fp, w.plane_g, false};                // B(n = (t, tau), k = f)
+  EpiArgmaxTile epi{argmax, w.colsum, w.list, w.count, w.capacity, K, T, D, margin_factor(F)};
+  if (int st = plane_gemm<true, false>(h, kArgmaxTile, Wmn, Gk, K, N, F, 1, false, epi, nullptr, stream, true)) return st;
   if (h->argmax_refine_shared && D <= 64) {
     GCCNMF_LAUNCH(h, refine_argmax_shared_kernel, h->sm_count * 4, 256, 0, stream, w.list, w.count, w.capacity,
                   reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, W, K, argmax);
@@ -326,6 +446,34 @@ int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, c
   // more near-ties than the list holds (never seen: the list holds 1/8 of all decisions): the caller must fall back
   if (overflow_flag) GCCNMF_CHECK_CUDA(h, cudaMemcpyAsync(overflow_flag, w.count, sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return GCCNMF_OK;
+}
+
+size_t gccnmf_masked_recon_workspace_bytes(int S, int F, int T, int K) {
+  if (S <= 0 || F <= 0 || T <= 0 || K <= 0 || !gccnmf_masked_recon_tc_supported(S, F, T, K)) return 256;
+  return carve_recon(nullptr, 0, S, F, T, K).bytes;
+}
+
+// Tensor-core masked reconstruction (gccnmf_masked_recon_phase routes here when the shape is covered and a workspace is given).
+int gccnmf_masked_recon_planes(gccnmf_handle* h, const float* masks, const float* X, const float* W, const float* H, int S, int F, int T, int K,
+                               float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  ReconWorkspace w = carve_recon(workspace, workspace_bytes, S, F, T, K);
+  if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "masked_recon workspace too small: need %zu bytes", w.bytes);
+  const int64_t na = (int64_t)K * w.pitch, nw = (int64_t)F * K;
+  GCCNMF_LAUNCH(h, masked_h_planes_kernel, (unsigned)((na + 255) / 256), 256, 0, stream, H, masks, S, K, T, w.Tpad, w.Ap, w.pitch, w.plane_a);
+  GCCNMF_LAUNCH(h, split_to_planes_kernel, (unsigned)((nw + 255) / 256), 256, 0, stream, W, nw, w.Wp, w.plane_w);
+  const int M = 2 * S * w.Tpad;
+  const Operand Amn{w.Ap, w.pitch, w.plane_a, true};             // A(m = (batch, t), k = atom): (K, batches x Tpad) as built
+  const Operand Wk{w.Wp, (int64_t)K, w.plane_w, false};          // B(n = f, k = atom)
+  EpiReconPhase epi{reinterpret_cast<const float2*>(X), reinterpret_cast<float2*>(out), F, T, w.Tpad, M,
+                    T % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0};
+  // tile width over the F bins: the smallest of the instantiated widths whose tiles waste the fewest columns
+  const int widths[4] = {128, 176, 208, 256};
+  int bn = 128, best = 1 << 30;
+  for (int i = 0; i < 4; ++i) {
+    const int waste = (F + widths[i] - 1) / widths[i] * widths[i] - F;
+    if (waste < best) { best = waste; bn = widths[i]; }
+  }
+  return plane_gemm<true, false>(h, bn, Amn, Wk, M, F, K, 1, false, epi, nullptr, stream, false);
 }
 
 }  // extern "C"

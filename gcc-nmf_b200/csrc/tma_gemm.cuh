@@ -165,6 +165,8 @@ struct PlaneGemmArgs {
   int tail_rows;           // rows [128 m_tiles, M) computed in float32 SIMT by the epilogue warps while the main loop runs (K-major operands)
   int tail_cols;           // columns of the n tile each m tile's CTA takes for those rows (multiple of 2)
   int kblocks_per_split;   // k-blocks of KB handled by one blockIdx.z
+  int m_fastest;           // 0: grid (n tiles, m tiles, splits); 1: grid (m tiles, n tiles, splits) -- the CTAs that share a B tile are
+                           // launched together, so a large B operand is read from HBM once (cluster shapes with CN == 1 only)
   // SIMT tail rows (both operands K-major only): element (r, k) of plane p at ptr[p * plane + r * ld + k]
   const __nv_bfloat16* A; int64_t a_plane, lda;
   const __nv_bfloat16* B; int64_t b_plane, ldb;
@@ -207,6 +209,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
          ((uint32_t)(kBM >> 4) << 24);
 }
 
+// Epilogues with `static constexpr bool kTileEpilogue = true` take the whole staged tile:
+//   __device__ void tile_epilogue(const float* tile /* [n][128] */, int m0, int n0, int n_valid, int z) const;   (all threads)
+template <class E, class = void>
+struct has_tile_epilogue { static constexpr bool value = false; };
+template <class E>
+struct has_tile_epilogue<E, decltype((void)E::kTileEpilogue)> { static constexpr bool value = E::kTileEpilogue; };
+
 // Epilogue concept (functors in klnmf_tma.cu).  The kernel stages the accumulator tile in shared memory and hands it out by
 // columns: a warp owns column n, lane l rows m .. m + 3 with m = m0 + 4 l (contiguous in every output of the KL-NMF loop).
 //   static constexpr int kRowValues (<= kMaxRowValues);  __device__ void row_values(int m, float* v) const;
@@ -231,10 +240,11 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // PAIR: the two CTAs of a pair must be neighbours along x (cta_group::2 pairs are formed along the cluster's x dimension: a
-  // (1, 2, 1) cluster is refused at launch with "cluster misconfiguration"), so the grid is (2 n_tiles, m_tiles / 2, splits) with
-  // (2, 1, 1) clusters and the m tile alternates with blockIdx.x.
-  const int tile_n = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_m = PAIR ? (int)(2 * blockIdx.y + (blockIdx.x & 1)) : (int)blockIdx.y;
+  // (1, 2, 1) cluster is refused at launch with "cluster misconfiguration"), so a pair always runs on the m-fastest grid
+  // (m tiles, n tiles, splits) with (2, 1, 1) clusters.
+  const bool mf = PAIR || args.m_fastest != 0;
+  const int tile_n = mf ? (int)blockIdx.y : (int)blockIdx.x;
+  const int tile_m = mf ? (int)blockIdx.x : (int)blockIdx.y;
   const int z = blockIdx.z;
   const int n0 = tile_n * BN;
   const int total_kblocks = (args.Kc + KB - 1) / KB;
@@ -242,8 +252,8 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int kb_end = min(total_kblocks, kb_begin + args.kblocks_per_split);
   const int num_kb = max(0, kb_end - kb_begin);
   // position inside the cluster (x = n tile, y = m tile); rank = x + CN y (%cluster_ctarank)
-  const int cx = (!PAIR && CN > 1) ? (int)(blockIdx.x % CN) : 0;
-  const int cy = PAIR ? (int)(blockIdx.x & 1) : ((CM > 1) ? (int)(blockIdx.y % CM) : 0);
+  const int cx = (!mf && CN > 1) ? (int)(blockIdx.x % CN) : 0;     // (the m-fastest grid is used with CN == 1 only)
+  const int cy = (CM > 1) ? tile_m % CM : 0;
   // CTAs that receive my slice of A (same m tile: my cluster row) / of B (same n tile: my cluster column)
   const uint16_t mask_row = (uint16_t)(((1u << CN) - 1u) << (CN * cy));
   const uint16_t mask_col = (uint16_t)((CM > 1 ? ((1u << cx) | (1u << (cx + CN))) : (1u << cx)));
@@ -491,7 +501,12 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // independent loads per thread before the first dependent store.
   umma::tc_fence_before_sync();
   __syncthreads();
-  {
+  if constexpr (has_tile_epilogue<Epilogue>::value) {
+    // whole-tile epilogue: the functor reads the staged accumulator tile[n][m] itself (reductions ACROSS columns, e.g. the argmax
+    // over the TDOAs of a frame, which the by-column hand-out below cannot express)
+    epi.tile_epilogue(tile, m0, n0, min(BN, args.N - n0), z);
+    if (args.timing && tid == 64) args.timing[cta_linear * 8 + 6] = clock64();
+  } else {
     constexpr int kWarps = kThreads / 32;
     const int m_first = m0 + 4 * lane;
     typename Epilogue::State st;

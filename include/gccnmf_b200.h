@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GCCNMF_ABI_VERSION 1
+#define GCCNMF_ABI_VERSION 2
 
 typedef struct gccnmf_handle gccnmf_handle;
 
@@ -220,9 +220,14 @@ GCCNMF_API int gccnmf_wiener_apply(gccnmf_handle* h, const float* mask, const fl
                         int K, float* Y, float* wiener, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a8: masked reconstruction with mixture phase  (gccNMFFunctions.py:145-151) -------------- */
-/* out[s, c] = (W . (H[:, c*T:(c+1)*T] * masks[s])) * exp(i angle(X[c])) ; out (S, 2, F, T) c64. */
+/* out[s, c] = (W . (H[:, c*T:(c+1)*T] * masks[s])) * exp(i angle(X[c])) ; out (S, 2, F, T) c64.
+ * With a workspace of gccnmf_masked_recon_workspace_bytes the S x 2 products run on the tensor cores (the plane GEMM of the
+ * KL-NMF loop over masked-H planes: 3 bf16 products per product, ~3e-6 relative); with workspace == NULL, or a shape the
+ * tensor-core path does not cover, on the float32 SIMT kernel. */
+GCCNMF_API size_t gccnmf_masked_recon_workspace_bytes(int S, int F, int T, int K);
 GCCNMF_API int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W,
-                              const float* H, int S, int F, int T, int K, float* out, void* stream);
+                              const float* H, int S, int F, int T, int K, float* out, void* workspace,
+                              size_t workspace_bytes, void* stream);
 
 /* ---- tensor-core building block of a2 (the four contractions of gccNMFFunctions.py:76-77) ------ */
 /*

@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_host_helpers(lib):
-    assert lib.gccnmf_abi_version() == 1
+    assert lib.gccnmf_abi_version() == 2
     assert lib.gccnmf_stft_num_frames(160000, 1024, 512) == 311          # config 1
     assert lib.gccnmf_stft_num_frames(480000, 1024, 256) == 1872         # config 2
     assert lib.gccnmf_stft_num_frames(100, 1024, 256) < 0                # buffer too short

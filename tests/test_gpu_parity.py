@@ -310,3 +310,26 @@ def test_full_size_properties_config2(h, fn):
     ref = orc.getGCCNMFAllTDOAs(cohh[:, 500:532], E, W.cpu().numpy())
     assert np.array_equal(argmax.cpu().numpy()[:, 500:532], np.argmax(ref, axis=1))
     assert fn.estimateTargetTDOAIndexesFromAngularSpectrum(mean.cpu().numpy(), 0.1, D, 1) == [12]
+
+
+@pytest.mark.parametrize('S,F,T,K', [(1, 513, 1872, 1024), (3, 513, 311, 128), (2, 257, 100, 64)])
+def test_masked_reconstruction_tensor_cores_vs_float32_kernel(h, S, F, T, K):
+    """a8 on the plane GEMM (masked-H planes, 3 bf16 products per product) against the float32 SIMT kernel and float64 numpy:
+    T = 1872 (whole vector segments), 311 (T % 4 != 0: scalar epilogue path, ragged last tile) and 100 (a single partial tile)."""
+    import torch
+    rng = np.random.default_rng(S * 1000 + T)
+    W = (rng.random((F, K)) ** 2).astype(np.float32)
+    H = (rng.random((K, 2 * T)) ** 3).astype(np.float32)
+    masks = (rng.random((S, K, T)) < 0.3).astype(np.float32)
+    X = (rng.standard_normal((2, F, T)) + 1j * rng.standard_normal((2, F, T))).astype(np.complex64)
+    X[0, 3, 5] = 0                                                   # angle(0) = 0
+    Wd, Hd, Md, Xd = h.to_device(W), h.to_device(H), h.to_device(masks), h.to_device(X)
+    assert h.lib.gccnmf_masked_recon_workspace_bytes(S, F, T, K) > 256                  # the tensor-core path takes these shapes
+    tc = h.masked_recon_phase(Md, Xd, Wd, Hd, tensor_cores=True).cpu().numpy()
+    simt = h.masked_recon_phase(Md, Xd, Wd, Hd, tensor_cores=False).cpu().numpy()
+    torch.cuda.synchronize()
+    stereoH = np.array(np.hsplit(H, 2))
+    ref = orc.getTargetSpectrogramEstimates(masks, X, W, stereoH)
+    assert tc.shape == ref.shape == (S, 2, F, T)
+    assert relerr(simt, ref) < 2e-6
+    assert relerr(tc, ref) < 1e-5 and np.abs(tc - ref).max() < 3e-5 * np.abs(ref).max()

@@ -149,12 +149,13 @@ def test_config1_real_recording_against_reference_fixtures(golden, fn):
     mask_agreement_tf = float(np.mean(masks == masks_ref))
     assert np.array_equal(masks.sum(axis=(1, 2)), d['maskSums']) and mask_agreement_tf == 1.0, mask_agreement_tf   # bit-exact decisions
     Sp = fn.getTargetSpectrogramEstimates(masks_ref, X, Wr, stereoH)
-    assert np.abs(Sp[:, :, ::37, ::29] - full['Sp_strided']).max() < 3e-6 * np.abs(full['Sp_strided']).max()
+    # (S x 2 products on the tensor cores at this shape: 3 bf16 products per product, measured ~3e-6; float32 SIMT kernel: 1e-6)
+    assert np.abs(Sp[:, :, ::37, ::29] - full['Sp_strided']).max() < 2e-5 * np.abs(full['Sp_strided']).max()
     y = fn.getTargetSignalEstimates(Sp, N, hop, np.hanning)
     assert list(y.shape) == list(d['y_shape'])
     scale = np.abs(d['y_strided']).max()
-    assert np.abs(y[:, :, ::997] - d['y_strided']).max() < 1e-5 * scale
-    assert np.abs(y[:, :, 20000:24096] - full['y_head']).max() < 1e-5 * scale
+    assert np.abs(y[:, :, ::997] - d['y_strided']).max() < 2e-5 * scale
+    assert np.abs(y[:, :, 20000:24096] - full['y_head']).max() < 2e-5 * scale
     assert abs(np.linalg.norm(y.astype(np.float64)) - float(d['y_norm'])) < 1e-5 * float(d['y_norm'])
     # ---- free-running back half (own W, H): mask agreement is reported, the signal is not asserted (one flipped
     # near-tie moves it by 5e-3, SURVEY.md section 7 hard part 2)
@@ -192,7 +193,7 @@ def test_config1_pipeline_on_the_recording(golden):
     out = pipe._back(r2, pipe.h.to_device(masks_ref.astype(np.float32)))
     y2 = out['targetSignalEstimates'].cpu().numpy()
     scale = np.abs(d['y_strided']).max()
-    assert np.abs(y2[:, :, ::997] - d['y_strided']).max() < 1e-5 * scale
+    assert np.abs(y2[:, :, ::997] - d['y_strided']).max() < 2e-5 * scale
     assert abs(np.linalg.norm(y2.astype(np.float64)) - float(d['y_norm'])) < 1e-5 * float(d['y_norm'])
     assert torch.isfinite(out['targetSignalEstimates']).all()
 
@@ -220,3 +221,30 @@ def test_klnmf_config4_shape_three_iterations(h, fn):
     assert figs['W']['fro'] < 1e-5 and figs['H']['fro'] < 1e-5, figs
     assert figs['W']['maxnorm'] < 2e-5 and figs['H']['maxnorm'] < 2e-5, figs
     np.testing.assert_allclose(torch.linalg.norm(W, dim=0).cpu().numpy(), 1.0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ configs[4] shape: D = 128, K = 256, hop 64
+def test_argmax_config5_shape_128_tdoas(h, fn):
+    """1024-sample analysis window, 64-sample hop, K = 256, D = 128 (two frames per 256-column tile of the argmax GEMM): the
+    tensor-core argmax + float64 refinement must equal the float64 kernel on every decision, and the oracle on a slice."""
+    import torch
+    from gcc_nmf_b200.synth import synthetic_stereo
+    N, hop, K, D = 1024, 64, 256, 128
+    x = synthetic_stereo(10.0)
+    X = h.stft(h.to_device(x), h.to_device(np.hanning(N)), N, hop, conjugate=False)
+    F, T = X.shape[1], X.shape[2]
+    assert h.lib.gccnmf_tdoa_argmax_workspace_bytes(F, T, D, K) > 2 * T * D * F * 2        # the tensor-core path takes this shape
+    E = np.ascontiguousarray(fn.getExpJOmegaTau(fn.getFrequenciesInHz(16000, F), fn.getTDOAsInSeconds(0.1, D)))
+    Ed = h.to_device(E)
+    coh, _, _ = h.phat_angspec(X, Ed, want_angular=False, want_mean=False)
+    W = (np.random.default_rng(4).random((F, K)) ** 3).astype(np.float32)
+    W /= np.sqrt((W ** 2).sum(axis=0))
+    Wd = h.to_device(W)
+    argmax, refined = h.tdoa_argmax(coh, Ed, Wd)
+    _, argmax64 = h.tdoa_gccnmf(coh, Ed, Wd)
+    n_ref = int(refined.item())
+    assert torch.equal(argmax, argmax64)
+    assert 0 < n_ref <= h.lib.gccnmf_tdoa_argmax_refine_capacity(K, T)
+    ref = orc.getGCCNMFAllTDOAs(coh.cpu().numpy()[:, 1000:1016], E, W)
+    assert np.array_equal(argmax.cpu().numpy()[:, 1000:1016], np.argmax(ref, axis=1))
+    _record('argmax_config5_shape', {'F': F, 'T': T, 'K': K, 'D': D, 'decisions': int(argmax.numel()), 'refined_in_float64': n_ref})

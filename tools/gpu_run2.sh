@@ -23,9 +23,16 @@ echo "== rt latency" >> $S
 timeout 900 python tools/rt_latency.py --chunks 2000 --json gpurun_out/r2b_rt_latency.json > gpurun_out/r2b_rt_latency.log 2>&1
 echo "latency rc=$?" >> $S; cat gpurun_out/r2b_rt_latency.log >> $S
 echo "== full-size parity" >> $S
-timeout 1200 python -m pytest tests/test_gpu_parity_full.py -q -s -k "config1" > gpurun_out/r2b_parity_full.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_parity_full.py -q -s > gpurun_out/r2b_parity_full.log 2>&1
 echo "parity_full rc=$?" >> $S; tail -4 gpurun_out/r2b_parity_full.log >> $S
 echo "== whole gpu suite" >> $S
 timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_parity_full.py --deselect tests/test_gpu_online.py > gpurun_out/r2b_pytest.log 2>&1
 echo "suite rc=$?" >> $S; tail -4 gpurun_out/r2b_pytest.log >> $S
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err
+echo "bench rc=$?" >> $S
+python - <<'PY' >> $S 2>&1
+import json
+d=json.load(open('gpurun_out/r2b_bench.json'))
+print('bench value', d['value'], 'e2e', d['e2e']['value'], d['stage_ms'])
+PY
 cat $S
