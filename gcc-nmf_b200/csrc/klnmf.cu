@@ -259,6 +259,13 @@ int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, c
 int gccnmf_klnmf_tma_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
                             size_t workspace_bytes, void* stream);
 int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
+// The TMA path keeps W unnormalised inside the loop (see klnmf_tma.cu): the caller's W is normalised here, once
+int gccnmf_klnmf_tma_finish_W(gccnmf_handle* h, int F, int T2, float* W, int K, void* workspace, size_t workspace_bytes, void* stream);
+// cross-rank signalling folded into the numerator pack / the W update (no host-launched barrier in between)
+int gccnmf_klnmf_tma_pack_numer_mc(gccnmf_handle* h, int F, int T2, int K, float* numer, unsigned* mc_counter, void* workspace, size_t workspace_bytes,
+                                   void* stream);
+int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
+                                const unsigned* arrival_counter, unsigned arrivals_expected, void* workspace, size_t workspace_bytes, void* stream);
 
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tc_supported(F, T2, K); }
 // The TMA path is the 3xBF16 split over pre-split planes; the 3xTF32 option and shapes it does not cover use the loader-based kernel.
@@ -352,12 +359,35 @@ int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, 
   return tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, numer_multicast, true, workspace, workspace_bytes, stream);
 }
 
+// One KL-NMF iteration of a frame-sharded run with the cross-rank sum of the W-update numerator formed INSIDE the NVSwitch and no
+// host-side step in between:  G1..G4 -> pack (this rank's (F*K + K) partial into its symmetric buffer; the last CTA adds 1 to the
+// arrival counter of EVERY rank through the multicast address) -> W update (waits until its own copy of the counter shows
+// `arrivals_expected` arrivals, then reads every word with multimem.ld_reduce).  numer_local / counter_local: this rank's addresses of
+// the symmetric buffer; numer_multicast / counter_multicast: the multicast addresses of the same offsets.
+int gccnmf_klnmf_step_multimem(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float sparsity_alpha, float epsilon,
+                               int iteration, float* numer_local, const float* numer_multicast, const uint32_t* counter_local,
+                               uint32_t* counter_multicast, uint32_t arrivals_expected, void* workspace, size_t workspace_bytes, void* stream) {
+  GCCNMF_ENTER(h);
+  if (int st = check_dims(h, F, T2, K)) return st;
+  GCCNMF_REQUIRE(h, numer_local && numer_multicast && counter_local && counter_multicast && iteration >= 0, "klnmf_step_multimem: bad arguments");
+  if (!use_tma(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_multimem: shape not covered by the TMA tensor-core path");
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0,
+                                         stream)) return st;
+  if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+  if (int st = gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer_local, counter_multicast, workspace, workspace_bytes, stream)) return st;
+  return gccnmf_klnmf_tma_apply_W_mc(h, F, T2, W, K, numer_multicast, true, counter_local, arrivals_expected, workspace, workspace_bytes, stream);
+}
+
 int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,
                      size_t workspace_bytes, void* stream) {
   GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
-  (void)W;
-  if (use_tc(h, F, T2, K)) return tc_ops(h, F, T2, K).finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream);
+  if (use_tc(h, F, T2, K)) {
+    if (int st = tc_ops(h, F, T2, K).finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream)) return st;
+    if (use_tma(h, F, T2, K) && iterations_done > 0) return gccnmf_klnmf_tma_finish_W(h, F, T2, W, K, workspace, workspace_bytes, stream);
+  }
   return GCCNMF_OK;
 }
 
@@ -380,7 +410,9 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
       if (int st = tc_ops(h, F, T2, K).partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
       if (int st = tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, nullptr, false, workspace, workspace_bytes, stream)) return st;
     }
-    return tc_ops(h, F, T2, K).finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream);
+    if (int st = tc_ops(h, F, T2, K).finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream)) return st;
+    if (use_tma(h, F, T2, K) && update_W) return gccnmf_klnmf_tma_finish_W(h, F, T2, W, K, workspace, workspace_bytes, stream);
+    return GCCNMF_OK;
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   for (int it = 0; it < iterations; ++it) {

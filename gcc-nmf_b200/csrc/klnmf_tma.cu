@@ -2,21 +2,27 @@
 //
 // Every matrix lives in ONE orientation; the four contractions of an iteration pick the UMMA operand layout
 // (K-major / MN-major) that matches it, so nothing is transposed or re-split inside the loop:
-//   W    (F, K)   float32 master (the caller's buffer) + bf16 hi/lo planes Wp (F, K); Wnp = planes of W * pending norms
-//   H^T  (T2, K)  float32 master HT32 + planes HTp          (the caller's H (K, T2) is read once and written once)
+//   U    (F, K)   float32 master (the caller's W buffer) + bf16 hi/lo planes Up (F, K)
+//   G^T  (T2, K)  float32 master HT32 + planes HTp          (the caller's H (K, T2) is read once and written once)
 //   V^T  (T2, Fp) float32 (epilogue operand only)
-//   R^T  (T2, Fp) planes RTp only, R = V / (W H)            Fp = F rounded up to 8 (16-byte plane rows)
+//   R^T  (T2, Fp) planes RTp only, R = V / (U G)            Fp = F rounded up to 8 (16-byte plane rows)
 //
-// One iteration, reference order (:76-:81); M = accumulator rows (TMEM lanes = the coalesced store direction):
-//   G1  RTp = split(VT / (Wn . H^T))      M = f,    N = t,    over atoms   A = Wnp K-major, B = HTp K-major  (Wn = W * n, see below)
-//   G2  HT32, HTp = (n*H) * (W^T . R) / (colsum(W) + alpha + eps); row-sum partials
-//                                          M = atom, N = t,    over f       A = Wp MN-major,  B = RTp K-major
-//   G3  RTp = split(VT / (W . H^T))       M = f,    N = t,    over atoms   A = Wp K-major,   B = HTp K-major
-//   G4  partial[z] = (R . H^T)^T          M = atom, N = f,    over frames  A = HTp MN-major, B = RTp MN-major, split over z
-//   A   W *= sum_z partial / rowsum(H); unit-L2 atoms; Wp, Wnp, colsum(W), n = norms
-// The rescaling H *= n (:81) is applied lazily: G1 contracts (W * n) with the unscaled H^T -- the W update writes the
-// planes of fl(W * n) next to those of W -- and G2's epilogue multiplies the old H by n (the reference's own float32
-// product), so the 30 MB of H^T are not rewritten every iteration; the last rescale happens in finish().
+// Gauge.  The reference renormalises after every W update: n = ||W'[:, k]||, W = W' / n, H = n H (:79-:81).  W.H, both
+// multiplicative updates and the next norms are covariant under that per-atom rescaling, so the loop carries the UNNORMALISED pair
+// (U, G) with W_ref = U / c, H_ref = c G, c = column norms of U -- and c enters the arithmetic in exactly one place, the
+// sparsity / epsilon term of the H update:
+//      G <- G * (U^T R) / (colsum(U) + c (alpha + eps))           (:76 multiplied through by c)
+//      U <- U * (R G^T) / rowsum(G)                                (:77; the c's cancel)         c <- ||U[:, k]||
+// Nothing is rescaled inside the loop (the reference rewrites W and the 15 MB of H every iteration); the normalisation is applied
+// once, when the caller's W and H are written (finish).  Before the first W update c = 1 (the reference's W0 is not normalised).
+//
+// One iteration, reference order (:76-:77); M = accumulator rows (TMEM lanes = the coalesced store direction):
+//   G1  RTp = split(VT / (U . G^T))       M = f,    N = t,    over atoms   A = Up K-major,   B = HTp K-major
+//   G2  HT32, HTp = G * (U^T . R) / (colsum(U) + c (alpha + eps)); row-sum partials
+//                                          M = atom, N = t,    over f       A = Up MN-major,  B = RTp K-major
+//   G3  RTp = split(VT / (U . G^T))       again with the new G
+//   G4  partial[z] = (R . G^T)^T          M = atom, N = f,    over frames  A = HTp MN-major, B = RTp MN-major, split over z
+//   A   U *= sum_z partial / rowsum(G); planes Up; per-row-block partial column sums and sums of squares (-> colsum(U), c)
 // F = 513 = 4 x 128 + 1: the row past the last full 128-row tile of G1 / G3 is computed in float32 SIMT by the tile CTAs'
 // epilogue warps while the main loop runs.
 // Tile widths are chosen per contraction so that one wave fills the 148 SMs (G2: 8 x 18 tiles of 128 x 208 = 144 CTAs;
@@ -92,38 +98,40 @@ struct EpiRatioPlanes {   // RT[n][m] = split(VT[n][m] / acc)     G1 / G3 (m = f
   }
 };
 
-// G2 (m = atom, n = frame): new = (old * pending_norm[m]) * (acc / (colsum[m] + alpha + eps))  (:81 then :76).
-// H^T is updated in place (float32 master + planes); the per-row sums of the new H over the tile's columns go to
+// G2 (m = atom, n = frame): G <- G * acc / (colsum(U)[m] + c[m] (alpha + eps))  (:76 in the (U, G) gauge, see the header).
+// G^T is updated in place (float32 master + planes); the per-row sums of the new G over the tile's columns go to
 // rowsum_part[tile_n][m] (one writer per value, fixed summation order, no atomics).
 struct EpiUpdateH {
-  struct State { float4 rden, pn, rsum; };
+  struct State { float4 rden, rsum; };
   struct Loaded { float4 old; };
   static constexpr bool kRowReduce = true;
-  static constexpr int kRowValues = 2;   // 1 / (colsum(W)[m] + alpha + eps), pending norm[m]
+  static constexpr int kRowValues = 1;   // 1 / (colsum(U)[m] + c[m] (alpha + eps))
   static constexpr bool kPrefetch = true;
   __device__ void prefetch(int m, int n) const {
     if (m < M) tgemm::prefetch_l2(HT + (int64_t)n * ld + m);
   }
-  float* __restrict__ HT; bf16* __restrict__ HTp; const float* __restrict__ colsumW; const float* __restrict__ pending;
-  float* __restrict__ rowsum_part; float alpha, eps; int64_t ld, plane; int M, N; int colsum_slots; bool vec;
+  float* __restrict__ HT; bf16* __restrict__ HTp; const float* __restrict__ colsum_part; const float* __restrict__ sumsq_part;
+  float* __restrict__ rowsum_part; float alpha, eps; int64_t ld, plane; int M, N; int slots; bool vec;
   __device__ void row_values(int m, float* v) const {
-    v[0] = 1.f; v[1] = 1.f;
+    v[0] = 1.f;
     if (m >= M) return;
-    float c = 0.f;
-    for (int b0 = 0; b0 < colsum_slots; b0 += 8) {       // colsum(W): the W update's per-row-block partials, 8 loads in flight
-      float p[8];
+    float c = 0.f, q = 0.f;
+    for (int b0 = 0; b0 < slots; b0 += 8) {       // the W update's per-row-block partials, 8 (+ 8) loads in flight
+      float p[8], r[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) p[j] = (b0 + j < colsum_slots) ? colsumW[(int64_t)(b0 + j) * M + m] : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        p[j] = (b0 + j < slots) ? colsum_part[(int64_t)(b0 + j) * M + m] : 0.f;
+        r[j] = (sumsq_part && b0 + j < slots) ? sumsq_part[(int64_t)(b0 + j) * M + m] : 0.f;
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) c += p[j];
+      for (int j = 0; j < 8; ++j) { c += p[j]; q += r[j]; }
     }
-    v[0] = 1.f / ((c + alpha) + eps);
-    if (pending) v[1] = pending[m];
+    const float nrm = sumsq_part ? sqrtf(q) : 1.f;         // c = ||U[:, m]||; 1 before the first W update (W0 is not normalised)
+    v[0] = 1.f / ((c + nrm * alpha) + nrm * eps);
   }
   __device__ void init(State& s, int, const float* rowvals) const {
     s.rsum = make_float4(0.f, 0.f, 0.f, 0.f);
     s.rden = *reinterpret_cast<const float4*>(rowvals);
-    s.pn = *reinterpret_cast<const float4*>(rowvals + tgemm::kBM);
   }
   __device__ float4 row_partial(const State& s) const { return s.rsum; }
   __device__ void row_total(int m, int tile_n, float sum) const {
@@ -134,8 +142,7 @@ struct EpiUpdateH {
   __device__ void store(int m, int n, const float4& acc, const Loaded& l, int, State& s) const {
     const int valid = min(4, M - m);
     if (valid <= 0) return;
-    float4 o = l.old;
-    if (pending) { o.x *= s.pn.x; o.y *= s.pn.y; o.z *= s.pn.z; o.w *= s.pn.w; }
+    const float4 o = l.old;
     // acc / denom as acc * (1 / denom): the reciprocal is one IEEE division per row, shared by the tile's columns
     float4 hv = make_float4(o.x * (acc.x * s.rden.x), o.y * (acc.y * s.rden.y), o.z * (acc.z * s.rden.z), o.w * (acc.w * s.rden.w));
     if (valid < 4) {
@@ -210,19 +217,31 @@ __device__ __forceinline__ float multimem_sum_f32(const float* p) {
   return v;
 }
 
-// W update, two fully parallel passes over 32 x 32 tiles (grid: atoms / 32 x rows / 32):
-//   pass 1  W' = W * (sum_z partial[z]) / rowsum(H)  (:77); per-tile column sums of squares -> sumsq_part[row block][atom]
-//   pass 2  norm = sqrt(sum of the row-block partials) (:79); W = W' / norm (:80); planes of W and of W * norm (the lazily
-//           applied H rescale of :81, see the header); per-tile column sums -> colsum_part[row block][atom]; norms[atom]
+// W update, one fully parallel pass over 32 x 32 tiles (grid: atoms / 32 x rows / 32):
+//   U <- U * (sum_z partial[z]) / rowsum(G)  (:77 in the (U, G) gauge); planes of U; per-tile column sums and column sums of
+//   squares -> colsum_part / sumsq_part[row block][atom] (summed by their consumers: colsum(U) and c = ||U[:, k]||)
 template <bool MULTIMEM>
 __global__ void __launch_bounds__(kApplyTile * 8)
-tma_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, int splits, const float* __restrict__ rowsum,
-                    int rowsum_slots, int F, int K, float* __restrict__ sumsq_part) {
+tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, const float* __restrict__ partial, int splits,
+                   const float* __restrict__ rowsum, int rowsum_slots, int F, int K, float* __restrict__ sumsq_part, float* __restrict__ colsum_part,
+                   const unsigned* arrival_counter, unsigned arrivals_expected) {
   __shared__ float rs_s[kApplyTile];
-  __shared__ float part[8][kApplyTile + 1];
+  __shared__ float part[2][8][kApplyTile + 1];
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
   const int c = threadIdx.x, g = threadIdx.y;
+  if (MULTIMEM && arrival_counter) {
+    // every rank's partial numerator is in its symmetric buffer once my copy of the counter has received all arrivals
+    if (c == 0 && g == 0) {
+      unsigned seen;
+      unsigned long long spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrival_counter) : "memory");
+        if (++spins > (1ull << 31)) __trap();   // a lost peer must not hang the box
+      } while ((int)(seen - arrivals_expected) < 0);
+    }
+    __syncthreads();
+  }
   const int k = blockIdx.x * kApplyTile + c;
   const int64_t slab = (int64_t)F * K;
   if (g == 0) {
@@ -235,7 +254,7 @@ tma_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, in
     rs_s[c] = rs;
   }
   __syncthreads();
-  float sumsq = 0.f;
+  float sumsq = 0.f, csum = 0.f;
   if (k < K) {
     const float rs = rs_s[c];
 #pragma unroll
@@ -255,73 +274,48 @@ tma_apply_w1_kernel(float* __restrict__ W, const float* __restrict__ partial, in
           for (int z = 1; z < kMaxSplits; ++z)
             if (z < splits) numer += p[z];
         }
-        const float w = W[i] * (numer / rs);
-        W[i] = w;
-        sumsq += w * w;
+        const float u = U[i] * (numer / rs);
+        U[i] = u;
+        sumsq += u * u;
+        csum += u;
+        bf16 hi, lo;
+        split_bf16(u, hi, lo);
+        Up[i] = hi;
+        Up[plane + i] = lo;
       }
     }
   }
-  part[g][c] = sumsq;
+  part[0][g][c] = sumsq;
+  part[1][g][c] = csum;
   __syncthreads();
-  if (g == 0 && k < K) {
+  if (g < 2 && k < K) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += part[j][c];
-    sumsq_part[(int64_t)blockIdx.y * K + k] = s;
+    for (int j = 0; j < 8; ++j) s += part[g][j][c];
+    (g == 0 ? sumsq_part : colsum_part)[(int64_t)blockIdx.y * K + k] = s;
   }
 }
 
-__global__ void __launch_bounds__(kApplyTile * 8)
-tma_apply_w2_kernel(float* __restrict__ W, bf16* __restrict__ Wp, bf16* __restrict__ Wnp, int64_t plane, const float* __restrict__ sumsq_part,
-                    int row_blocks, int F, int K, float* __restrict__ norms, float* __restrict__ colsum_part) {
-  __shared__ float norm_s[kApplyTile];
-  __shared__ float part[8][kApplyTile + 1];
-  tgemm::pdl_launch_dependents();
-  tgemm::pdl_wait_prior_grids();
-  const int c = threadIdx.x, g = threadIdx.y;
-  const int k = blockIdx.x * kApplyTile + c;
-  if (g == 0) {
-    float s = 0.f;
-    if (k < K)
-      for (int b = 0; b < row_blocks; ++b) s += sumsq_part[(int64_t)b * K + k];
-    const float nrm = sqrtf(s);
-    norm_s[c] = nrm;
-    if (k < K && blockIdx.y == 0) norms[k] = nrm;
-  }
-  __syncthreads();
-  const float nrm = norm_s[c];
-  float csum = 0.f;
-#pragma unroll
-  for (int r = 0; r < kApplyTile / 8; ++r) {
-    const int f = blockIdx.y * kApplyTile + g + 8 * r;
-    if (k < K && f < F) {
-      const int64_t i = (int64_t)f * K + k;
-      const float w = W[i] / nrm;
-      W[i] = w;
-      csum += w;
-      bf16 hi, lo;
-      split_bf16(w, hi, lo);
-      Wp[i] = hi;
-      Wp[plane + i] = lo;
-      split_bf16(w * nrm, hi, lo);
-      Wnp[i] = hi;
-      Wnp[plane + i] = lo;
-    }
-  }
-  part[g][c] = csum;
-  __syncthreads();
-  if (g == 0 && k < K) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += part[j][c];
-    colsum_part[(int64_t)blockIdx.y * K + k] = s;
-  }
+// finish: the reference's normalisation (:79-:81), applied once.  c[k] = sqrt(sum of the row-block partial sums of squares).
+__device__ __forceinline__ float column_norm(const float* __restrict__ sumsq_part, int row_blocks, int K, int k) {
+  float q = 0.f;
+  for (int b = 0; b < row_blocks; ++b) q += sumsq_part[(int64_t)b * K + k];
+  return sqrtf(q);
+}
+__global__ void tma_finish_w_kernel(float* __restrict__ W, int F, int K, const float* __restrict__ sumsq_part, int row_blocks) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float nrm = column_norm(sumsq_part, row_blocks, K, k);
+  for (int f = blockIdx.y; f < F; f += gridDim.y) W[(int64_t)f * K + k] = W[(int64_t)f * K + k] / nrm;      // W /= norms (:80)
 }
 
-// H (K, T2; caller) = HT32 (T2, K)^T * norms (pending :81) or a plain transpose.
-__global__ void tma_finish_h_kernel(const float* __restrict__ HT, int T2, int K, const float* __restrict__ norms, float* __restrict__ H) {
+// H (K, T2; caller) = HT32 (T2, K)^T * c (H *= norms, :81) -- or a plain transpose when there was no W update.
+__global__ void tma_finish_h_kernel(const float* __restrict__ HT, int T2, int K, const float* __restrict__ sumsq_part, int row_blocks,
+                                    float* __restrict__ H) {
   __shared__ float tile[32][33];
+  __shared__ float nrm_s[32];
   const int k0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  if (threadIdx.y == 0) nrm_s[threadIdx.x] = (sumsq_part && k0 + threadIdx.x < K) ? column_norm(sumsq_part, row_blocks, K, k0 + threadIdx.x) : 1.f;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, k = k0 + threadIdx.x;
     tile[i][threadIdx.x] = (t < T2 && k < K) ? HT[(int64_t)t * K + k] : 0.f;
@@ -331,13 +325,20 @@ __global__ void tma_finish_h_kernel(const float* __restrict__ HT, int T2, int K,
     const int k = k0 + i, t = t0 + threadIdx.x;
     if (k < K && t < T2) {
       const float v = tile[threadIdx.x][i];
-      H[(int64_t)k * T2 + t] = norms ? v * norms[k] : v;
+      H[(int64_t)k * T2 + t] = sumsq_part ? v * nrm_s[i] : v;
     }
   }
 }
 
-// numer = [sum_z partial[z] (F*K) | sum_s rowsum_part[s] (K)] for the cross-rank all-reduce.
-__global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t n, const float* rowsum, int rowsum_slots, int K, float* numer) {
+// numer = [sum_z partial[z] (F*K) | sum_s rowsum_part[s] (K)] for the cross-rank sum.
+// With `mc_counter` (the NVLink multicast address of a per-buffer arrival counter that every rank holds at the same offset of its
+// symmetric buffer): the last CTA to finish adds 1 to that counter ON EVERY RANK with one multimem.red -- "this rank's partial is
+// complete" -- so no host-launched barrier sits between the numerator and the W update (tma_apply_w_kernel<true> waits on its own
+// copy of the counter).
+__global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t n, const float* rowsum, int rowsum_slots, int K, float* numer,
+                                      unsigned* done_counter, unsigned* mc_counter) {
+  tgemm::pdl_launch_dependents();
+  tgemm::pdl_wait_prior_grids();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float s = partial[i];
@@ -347,6 +348,18 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
     float s = 0.f;
     for (int j = 0; j < rowsum_slots; ++j) s += rowsum[(int64_t)j * K + (i - n)];
     numer[i] = s;
+  }
+  if (mc_counter) {
+    __threadfence_system();                     // my stores are visible system-wide before the CTA is counted as done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(done_counter, 1u);
+      if (prev == gridDim.x - 1) {
+        *done_counter = 0;                      // ready for the next iteration (this kernel is never concurrent with itself)
+        __threadfence_system();
+        asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
+      }
+    }
   }
 }
 
@@ -402,17 +415,19 @@ Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
 
 // ------------------------------------------------------------------------------------------------ workspace
 struct TmaWorkspace {
-  float *HT, *VT, *partial, *colsum, *sumsq_part, *rowsum_part, *norms;
-  bf16 *HTp, *Wp, *Wnp, *RTp;
+  float *HT, *VT, *partial, *colsum, *sumsq_part, *rowsum_part;
+  unsigned* done;          // CTA completion counter of the numerator pack (cross-rank signalling)
+  bf16 *HTp, *Wp, *RTp;
   int64_t Fp, plane_w, plane_ht, plane_rt;
   int row_blocks;
+  size_t bytes;
   bool ok;
 };
 
 int max_rowsum_slots(int T2) { return (T2 + 127) / 128; }
 
 TmaWorkspace tma_carve(void* ws, size_t bytes, int F, int T2, int K) {
-  WorkspaceCarver c(ws, bytes);
+  WorkspaceCarver c(ws ? ws : reinterpret_cast<void*>(256), ws ? bytes : ~size_t(0) >> 1);
   TmaWorkspace w;
   w.Fp = (F + 7) & ~7;
   w.plane_w = (int64_t)F * K;
@@ -425,25 +440,16 @@ TmaWorkspace tma_carve(void* ws, size_t bytes, int F, int T2, int K) {
   w.colsum = c.take<float>((size_t)w.row_blocks * K);
   w.sumsq_part = c.take<float>((size_t)w.row_blocks * K);
   w.rowsum_part = c.take<float>((size_t)max_rowsum_slots(T2) * K);
-  w.norms = c.take<float>(K);
+  w.done = c.take<unsigned>(4);
   w.HTp = c.take<bf16>((size_t)2 * w.plane_ht);
   w.Wp = c.take<bf16>((size_t)2 * w.plane_w);
-  w.Wnp = c.take<bf16>((size_t)2 * w.plane_w);
   w.RTp = c.take<bf16>((size_t)2 * w.plane_rt);
-  w.ok = c.ok();
+  w.bytes = align_up(c.used, 256);
+  w.ok = ws != nullptr && c.ok();
   return w;
 }
 
-size_t tma_workspace_bytes(int F, int T2, int K) {
-  const size_t Fp = (F + 7) & ~7;
-  size_t n = 0;
-  auto add = [&](size_t bytes) { n = align_up(n, 256) + bytes; };
-  add((size_t)T2 * K * 4); add((size_t)T2 * Fp * 4); add((size_t)kMaxSplits * F * K * 4);
-  add((size_t)((F + 31) / 32) * K * 4); add((size_t)((F + 31) / 32) * K * 4);
-  add((size_t)max_rowsum_slots(T2) * K * 4); add((size_t)K * 4);
-  add((size_t)2 * T2 * K * 2); add((size_t)2 * F * K * 2); add((size_t)2 * F * K * 2); add((size_t)2 * T2 * Fp * 2);
-  return align_up(n, 256);
-}
+size_t tma_workspace_bytes(int F, int T2, int K) { return tma_carve(nullptr, 0, F, T2, K).bytes; }
 
 #define TMA_CARVE_OR_FAIL(w)                                                                                        \
   TmaWorkspace w = tma_carve(workspace, workspace_bytes, F, T2, K);                                                 \
@@ -460,6 +466,7 @@ int gccnmf_klnmf_tma_prepare(gccnmf_handle* h, const float* V, int F, int T2, co
                              void* workspace, size_t workspace_bytes, bool need_vt, bool need_w, bool need_ht, void* stream) {
   TMA_CARVE_OR_FAIL(w);
   const dim3 block(32, 8);
+  GCCNMF_CHECK_CUDA(h, cudaMemsetAsync(w.done, 0, 16, (cudaStream_t)stream));
   if (need_vt)
     GCCNMF_LAUNCH(h, tma_transpose_split_kernel, dim3((T2 + 31) / 32, (int)((w.Fp + 31) / 32)), block, 0, stream, V, F, T2, (int64_t)T2, w.VT, w.Fp,
                   (bf16*)nullptr, (int64_t)0, (int64_t)0);
@@ -473,24 +480,25 @@ int gccnmf_klnmf_tma_prepare(gccnmf_handle* h, const float* V, int F, int T2, co
   return 0;
 }
 
-// :76 (preceded by the pending :81 when pending_norms): H = (n*H) * (W^T (V / (W (n*H)))) / (colsum(W) + alpha + eps).
+// :76 in the (U, G) gauge: G = G * (U^T (V / (U G))) / (colsum(U) + c (alpha + eps)).
 int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
                               void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream) {
-  // colsum_state: 0 = compute colsum(W) now; 1 = reuse the one computed before (fixed dictionary); 2 = per-row-block partials left by the W update
+  // colsum_state: 0 = compute colsum(U) now, c = 1 (before the first W update); 1 = reuse the one computed before (fixed dictionary);
+  // 2 = per-row-block partial column sums and sums of squares left by the W update
   TMA_CARVE_OR_FAIL(w);
-  (void)V; (void)H;
+  (void)V; (void)H; (void)pending_norms;
   const Plan p = make_plan(h, F, T2, K);
-  const Operand Wk{pending_norms ? w.Wnp : w.Wp, (int64_t)K, w.plane_w, false};
+  const Operand Wk{w.Wp, (int64_t)K, w.plane_w, false};
   const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
-  {  // G1: RT = split(VT / (Wn . H^T))
+  {  // G1: RT = split(VT / (U . G^T))
     EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2, true};
     if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream)) return st;
   }
   if (colsum_state == 0) GCCNMF_LAUNCH(h, tma_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
-  {  // G2: HT32, HTp = (n*H) * (W^T . R) / denom
+  {  // G2: HT32, HTp = G * (U^T . R) / denom
     const Operand Wmn{w.Wp, (int64_t)K, w.plane_w, true};
     const Operand RTk{w.RTp, w.Fp, w.plane_rt, false};
-    EpiUpdateH e{w.HT, w.HTp, w.colsum, pending_norms ? w.norms : nullptr, w.rowsum_part, alpha, eps, (int64_t)K, w.plane_ht, K, T2,
+    EpiUpdateH e{w.HT, w.HTp, w.colsum, colsum_state == 2 ? w.sumsq_part : nullptr, w.rowsum_part, alpha, eps, (int64_t)K, w.plane_ht, K, T2,
                  colsum_state == 2 ? w.row_blocks : 1, true};
     if (int st = plane_gemm<true, false>(h, p.bn_h, Wmn, RTk, K, T2, F, 1, false, e, nullptr, stream)) return st;
   }
@@ -519,42 +527,51 @@ int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, 
   return 0;
 }
 
-// :77-:80; the H rescale of :81 stays pending (applied by the next update_H, or by finish).  Numerator and row
-// sums come from `numer` (F*K + K floats, all-reduced across ranks) when given, else from this rank's partials.
-int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+// :77 in the (U, G) gauge (the normalisation of :79-:81 is applied by finish).  Numerator and row sums come from `numer`
+// (F*K + K floats, all-reduced across ranks) when given, else from this rank's partials.
+int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
+                                const unsigned* arrival_counter, unsigned arrivals_expected, void* workspace, size_t workspace_bytes, void* stream) {
   TMA_CARVE_OR_FAIL(w);
   const Plan p = make_plan(h, F, T2, K);
   const float* partial = numer ? numer : w.partial;
   const float* rowsum = numer ? numer + (int64_t)F * K : w.rowsum_part;
   const dim3 grid((K + kApplyTile - 1) / kApplyTile, w.row_blocks), block(kApplyTile, 8);
-  if (numer_is_multicast) {
-    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, partial, 1, rowsum, 1, F, K,
-                           w.sumsq_part)) return st;
-  } else {
-    if (int st = launch_ex(h, "tma_apply_w1_kernel", tma_apply_w1_kernel<false>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, partial,
-                           numer ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part)) return st;
-  }
-  return launch_ex(h, "tma_apply_w2_kernel", tma_apply_w2_kernel, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.Wnp, w.plane_w,
-                   (const float*)w.sumsq_part, w.row_blocks, F, K, w.norms, w.colsum);
+  if (numer_is_multicast)
+    return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial, 1,
+                     rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected);
+  return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<false>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial,
+                   numer ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part, w.colsum, (const unsigned*)nullptr, 0u);
 }
 
-// Writes the caller's H from H^T, applying a pending H *= norms (:81) when there is one.
+int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  return gccnmf_klnmf_tma_apply_W_mc(h, F, T2, W, K, numer, numer_is_multicast, nullptr, 0u, workspace, workspace_bytes, stream);
+}
+
+// Writes the caller's H from G^T (H = c G, :81) and normalises the caller's W in place (W = U / c, :80) when W was updated.
 int gccnmf_klnmf_tma_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
                             size_t workspace_bytes, void* stream) {
   TMA_CARVE_OR_FAIL(w);
   GCCNMF_LAUNCH(h, tma_finish_h_kernel, dim3((K + 31) / 32, (T2 + 31) / 32), dim3(32, 8), 0, stream, w.HT, T2, K,
-                pending_norms ? w.norms : (const float*)nullptr, H);
+                pending_norms ? w.sumsq_part : (const float*)nullptr, w.row_blocks, H);
+  return 0;
+}
+int gccnmf_klnmf_tma_finish_W(gccnmf_handle* h, int F, int T2, float* W, int K, void* workspace, size_t workspace_bytes, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  GCCNMF_LAUNCH(h, tma_finish_w_kernel, dim3((K + 127) / 128, std::min(F, 64)), 128, 0, stream, W, F, K, w.sumsq_part, w.row_blocks);
   return 0;
 }
 
-int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream) {
+int gccnmf_klnmf_tma_pack_numer_mc(gccnmf_handle* h, int F, int T2, int K, float* numer, unsigned* mc_counter, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
   TMA_CARVE_OR_FAIL(w);
   const Plan p = make_plan(h, F, T2, K);
   const int64_t n = (int64_t)F * K;
-  GCCNMF_LAUNCH(h, tma_pack_numer_kernel, (unsigned)((n + K + 255) / 256), 256, 0, stream, w.partial, p.w.splits, n, w.rowsum_part,
-                p.rowsum_slots, K, numer);
-  return 0;
+  return launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)((n + K + 255) / 256)), dim3(256), 0, stream, h->nmf_pdl, dim3(1, 1, 1),
+                   (const float*)w.partial, p.w.splits, n, (const float*)w.rowsum_part, p.rowsum_slots, K, numer, w.done, mc_counter);
+}
+int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream) {
+  return gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" {

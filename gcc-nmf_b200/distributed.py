@@ -88,14 +88,18 @@ def klnmf_sharded(ops, comm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon,
 
 
 class MultimemNumerator(object):
-    """Two symmetric (F*K + K)-float buffers bound to an NVLink multicast object (torch symmetric memory) for the
-    fused W update: step_numer writes the local partial, a device-side cross-rank barrier follows, and the W-update
-    kernel reads the cross-rank SUM with multimem.ld_reduce (reduction inside the NVSwitch).  Double-buffered so one
-    barrier per iteration is enough.  `create` returns None when the platform has no multicast support (the caller
-    then uses the NCCL all-reduce)."""
+    """Two symmetric buffers of (F*K + K) floats + one uint32 arrival counter each, bound to an NVLink multicast object (torch
+    symmetric memory), for the W update of a frame-sharded run with the exchange fused into the kernels
+    (gccnmf_klnmf_step_multimem): the numerator pack writes the local partial and adds 1 to the counter of EVERY rank through
+    the multicast address, the W-update kernel waits until its own copy of the counter shows one arrival per rank and reads the
+    cross-rank SUM with multimem.ld_reduce (reduction inside the NVSwitch).  No host-launched barrier, no all-reduce.
+    Double-buffered by iteration parity.  `create` returns None when the platform has no multicast support (the caller then
+    uses the NCCL all-reduce)."""
+    COUNTER_PAD = 64        # floats after the numerator: the uint32 arrival counter lives in the first of them
 
-    def __init__(self, buffers, handles):
-        self.buffers, self.handles = buffers, handles
+    def __init__(self, buffers, handles, numel, world):
+        self.buffers, self.handles, self.numel, self.world = buffers, handles, numel, world
+        self.uses = [0, 0]              # how often each buffer has been used (identical on every rank)
 
     @classmethod
     def create(cls, numel, device, group):
@@ -110,33 +114,35 @@ class MultimemNumerator(object):
                 pass
             buffers, handles = [], []
             for _ in range(2):
-                t = symm_mem.empty(numel, dtype=torch.float32, device=device)
+                t = symm_mem.empty(numel + cls.COUNTER_PAD, dtype=torch.float32, device=device)
                 hdl = symm_mem.rendezvous(t, group)
                 if not getattr(hdl, 'has_multicast_support', False) or not int(hdl.multicast_ptr):
                     return None
+                t.zero_()
                 buffers.append(t)
                 handles.append(hdl)
-            return cls(buffers, handles)
+            torch.cuda.synchronize(device)
+            for hdl in handles:
+                hdl.barrier(channel=0, timeout_ms=20000)       # every rank's counters are zero before anyone signals
+            return cls(buffers, handles, numel, dist.get_world_size(group))
         except Exception:
             return None
 
-    def buffer(self, it):
-        return self.buffers[it & 1]
-
-    def barrier(self, it):
-        self.handles[it & 1].barrier(channel=0, timeout_ms=20000)
-
-    def multicast_ptr(self, it):
-        return int(self.handles[it & 1].multicast_ptr)
+    def step_args(self, it):
+        """(numer_local, numer_multicast, counter_local, counter_multicast, arrivals_expected) for iteration `it`."""
+        p = it & 1
+        self.uses[p] += 1
+        local, mc = int(self.buffers[p].data_ptr()), int(self.handles[p].multicast_ptr)
+        off = 4 * self.numel
+        return local, mc, local + off, mc + off, self.world * self.uses[p]
 
 
 def klnmf_sharded_multimem(ops, mm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon):
-    """klnmf_sharded with the all-reduce folded into the W-update kernel (gccnmf_klnmf_step_apply_multimem)."""
+    """klnmf_sharded with the exchange fused into the kernels (gccnmf_klnmf_step_multimem): one C call per iteration, nothing
+    on the host between the numerator and the W update."""
     ops.klnmf_begin(V_s, W, H_s)
     for it in range(numIterations):
-        ops.klnmf_step_numer(V_s, W, H_s, it, mm.buffer(it), sparsityAlpha, epsilon)
-        mm.barrier(it)                 # every rank's partial is written (and every rank is done reading buffer it-2)
-        ops.klnmf_step_apply_multimem(W, H_s, mm.multicast_ptr(it))
+        ops.klnmf_step_multimem(V_s, W, H_s, it, *mm.step_args(it), sparsity_alpha=sparsityAlpha, epsilon=epsilon)
     ops.klnmf_end(W, H_s, numIterations)
     return W, H_s
 
@@ -223,7 +229,8 @@ class ShardedGCCNMFPipeline(object):
             ok = self.torch.tensor([1 if mm is not None else 0], dtype=self.torch.int32, device=self.h.device)
             self.comm.dist.all_reduce(ok, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
             if int(ok.item()) == 1:
-                self.multimem, self.collective = mm, 'multimem.ld_reduce in the W-update kernel (NVLS)'
+                self.multimem, self.collective = mm, ('multimem.red arrival signal in the numerator pack + multimem.ld_reduce in the W-update '
+                                                         'kernel (sum formed in the NVSwitch, no host-launched barrier)')
         self._path_agreed = True
 
     def enhance(self, samples, collect_stage_times=False):

@@ -145,6 +145,16 @@ GCCNMF_API int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W
 GCCNMF_API int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
                                      const float* numer_multicast, void* workspace, size_t workspace_bytes,
                                      void* stream);
+/* One iteration of a frame-sharded run with the cross-rank exchange fused into the kernels: the numerator pack signals "this rank
+ * is complete" to every rank with one multimem.red on an arrival counter, the W-update kernel waits on its own copy of the counter
+ * and reads the sum over ranks with multimem.ld_reduce (formed inside the NVSwitch) -- no host-launched barrier, no all-reduce.
+ * numer_local / counter_local: this rank's addresses inside its symmetric buffer ((F*K + K) floats + one uint32 per buffer);
+ * numer_multicast / counter_multicast: the NVLink multicast addresses of the same offsets; arrivals_expected = world size x the
+ * number of times this buffer has been used so far (including this one).  Double-buffer by iteration parity. */
+GCCNMF_API int gccnmf_klnmf_step_multimem(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K,
+                               float sparsity_alpha, float epsilon, int iteration, float* numer_local,
+                               const float* numer_multicast, const uint32_t* counter_local, uint32_t* counter_multicast,
+                               uint32_t arrivals_expected, void* workspace, size_t workspace_bytes, void* stream);
 GCCNMF_API int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done,
                      void* workspace, size_t workspace_bytes, void* stream);
 
