@@ -85,8 +85,18 @@ class RtConfig(ctypes.Structure):
                 ('epsilon', c_float)]
 
 
+class PipelineConfig(ctypes.Structure):
+    """gccnmf_pipeline_config (include/gccnmf_b200.h)."""
+    _fields_ = [('window_size', c_int), ('hop_size', c_int), ('num_tdoas', c_int), ('num_atoms', c_int), ('num_iterations', c_int),
+                ('num_targets', c_int), ('sparsity_alpha', c_float), ('epsilon', c_float), ('target_window_seconds', c_float)]
+
+
 _C = ctypes.POINTER(RtConfig)
+_PC = ctypes.POINTER(PipelineConfig)
 SIGNATURES.update({
+    'gccnmf_pipeline_workspace_bytes': (c_size_t, [_PC, c_int64]),
+    'gccnmf_pick_targets': (c_int, [_H, _P, c_int, c_int, _P, _P, _S]),
+    'gccnmf_separate': (c_int, [_H, _PC, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _S]),
     'gccnmf_wiener_apply_h': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _S]),
     'gccnmf_rt_state_bytes': (c_size_t, [_C]),
     'gccnmf_rt_init': (c_int, [_H, _C, _P, _P, _P, _P, _P, _P, c_size_t, _S]),
@@ -117,6 +127,12 @@ def load_library():
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def _key_owner(key):
+    while isinstance(key, tuple) and len(key) > 0:
+        key = key[0]
+    return key
 
 
 def _ptr(t):
@@ -194,13 +210,19 @@ class Handle(object):
         return self.torch.empty(shape, dtype=dtype, device=self.device)
 
     def buffer(self, key, shape, dtype):
-        """Persistent device buffer per (key, shape, dtype): allocated once (plan time), reused by every
-        later call, so steady-state pipelines never enter the allocator (a cudaMalloc costs milliseconds)."""
-        full_key = (key, tuple(int(v) for v in shape), dtype)
-        t = self._buffers.get(full_key)
-        if t is None:
-            t = self._buffers[full_key] = self.torch.empty(shape, dtype=dtype, device=self.device)
-        return t
+        """Persistent device buffer per key: allocated once (plan time) and reused by every later call with the same shape, so
+        steady-state pipelines never enter the allocator (a cudaMalloc costs milliseconds).  A call with another shape REPLACES
+        the buffer of that key (clips of varying length do not accumulate one buffer set per length)."""
+        shape = tuple(int(v) for v in shape)
+        entry = self._buffers.get(key)
+        if entry is None or entry[0] != shape or entry[1] != dtype:
+            entry = self._buffers[key] = (shape, dtype, self.torch.empty(shape, dtype=dtype, device=self.device))
+        return entry[2]
+
+    def release(self, owner):
+        """Drops every persistent buffer whose key starts with `owner` (a pipeline's token; called when it is collected)."""
+        for key in [k for k in self._buffers if k == owner or (isinstance(k, tuple) and len(k) > 0 and _key_owner(k) is owner)]:
+            del self._buffers[key]
 
     def _out(self, out_key, name, shape, dtype):
         return self.empty(shape, dtype) if out_key is None else self.buffer((out_key, name), shape, dtype)

@@ -171,6 +171,10 @@ class ShardedGCCNMFPipeline(object):
         self.torch = torch
         self.comm = comm if comm is not None else ShardComm()
         self.h = handle if handle is not None else Handle(device)
+        from .pipeline import _BufferOwner
+        import weakref
+        self._token = _BufferOwner()
+        weakref.finalize(self, self.h.release, self._token)
         self.sr, self.N, self.hop, self.D = sampleRate, int(windowSize), int(hopSize), int(numTDOAs)
         self.micSep, self.K, self.I = microphoneSeparationInMetres, int(dictionarySize), int(numIterations)
         self.alpha, self.eps, self.seed = float(sparsityAlpha), float(epsilon), seedValue
@@ -237,7 +241,7 @@ class ShardedGCCNMFPipeline(object):
         h, torch, comm = self.h, self.torch, self.comm
         self.stage_events = [] if collect_stage_times else None
         self._mark('start')
-        key = id(self)
+        key = self._token
         X, V = h.stft(samples, self.window, self.N, self.hop, conjugate=True, want_V=True, out_key=key)
         Ts = X.shape[2]
         assert Ts == self.t1 - self.t0

@@ -14,18 +14,26 @@ Only two things happen on the host, as in gccNMFFunctions.py: the D-element peak
 (scipy.signal.argrelmax) and the plan-time constants (window, exp(-2 pi i f tau) table in float64,
 seeded numpy draw of the NMF initial values -- a function of shape and seed only, gccNMFFunctions.py:70-73).
 """
+import weakref
+
 import numpy as np
 
 from . import gccNMFFunctions as fn
 from ._lib import Handle
 
 
+class _BufferOwner(object):
+    """Identity token for Handle.buffer keys (an id() can be reused after garbage collection; an object cannot)."""
+
+
 class GCCNMFPipeline(object):
     def __init__(self, sampleRate, windowSize, hopSize, numTDOAs, microphoneSeparationInMetres,
                  dictionarySize, numIterations, sparsityAlpha=0.0, epsilon=1e-16, seedValue=0,
-                 targetTDOAWindowSizePercent=0.05, device=0, handle=None):
+                 targetTDOAWindowSizePercent=0.05, device=0, handle=None, windowFunction=np.hanning):
         self.h = handle if handle is not None else Handle(device)
         self.torch = self.h.torch
+        self._token = _BufferOwner()                    # owner of this pipeline's persistent device buffers (released with it)
+        weakref.finalize(self, self.h.release, self._token)
         self.sampleRate, self.N, self.hop, self.D = sampleRate, int(windowSize), int(hopSize), int(numTDOAs)
         self.micSep = microphoneSeparationInMetres
         self.K, self.I = int(dictionarySize), int(numIterations)
@@ -35,7 +43,10 @@ class GCCNMFPipeline(object):
         self.frequenciesInHz = fn.getFrequenciesInHz(sampleRate, self.F)
         self.hypothesisTDOAs = fn.getTDOAsInSeconds(microphoneSeparationInMetres, self.D)
         self.E_host = np.ascontiguousarray(fn.getExpJOmegaTau(self.frequenciesInHz, self.hypothesisTDOAs))
-        self.window = self.h.to_device(np.hanning(self.N))          # float64, librosaSTFT.py:139
+        self.window = self.h.to_device(np.hanning(self.N))          # float64, librosaSTFT.py:139 (the STFT ignores windowFunction, gccNMFFunctions.py:65)
+        # the iSTFT honours it (gccNMFFunctions.py:161 -> librosaSTFT.py:264-270)
+        synthesis = windowFunction(self.N) if callable(windowFunction) else np.asarray(windowFunction)
+        self.synthesisWindow = self.window if windowFunction is np.hanning else self.h.to_device(np.ascontiguousarray(synthesis, dtype=np.float64))
         self.E = self.h.to_device(self.E_host)
         self._init = {}
         self.stage_events = None
@@ -48,6 +59,8 @@ class GCCNMFPipeline(object):
         """Seeded initial (W0, H0) on the device, drawn once per shape (gccNMFFunctions.py:70-73)."""
         key = (self.F, T2, self.K, self.seed, self.eps)
         if key not in self._init:
+            while len(self._init) >= 2:                 # clips of varying length: keep the two most recent shapes
+                self._init.pop(next(iter(self._init)))
             W0, H0 = fn._seededInit(self.F, T2, self.K, self.eps, self.seed)
             self._init[key] = (self.h.to_device(W0), self.h.to_device(H0))
         return self._init[key]
@@ -68,7 +81,7 @@ class GCCNMFPipeline(object):
         """STFT, coherence + angular spectrogram (+ async copy of its mean), KL-NMF."""
         h, torch = self.h, self.torch
         self._mark('start')
-        key = id(self)
+        key = self._token
         X, V = h.stft(samples, self.window, self.N, self.hop, conjugate=True, want_V=True, out_key=key)
         self._mark('stft')
         coh, ang, mean = h.phat_angspec(X, self.E, out_key=key)
@@ -91,11 +104,11 @@ class GCCNMFPipeline(object):
     def _back(self, r, masks):
         h = self.h
         S = masks.shape[0]
-        est = h.masked_recon_phase(masks, r['X'], r['W'], r['H'], out_key=id(self))
+        est = h.masked_recon_phase(masks, r['X'], r['W'], r['H'], out_key=self._token)
         self._mark('recon')
         F, T = est.shape[2:]
-        y = h.istft_ola(est.reshape(S * 2, F, T), self.window, self.N, self.hop,
-                        gain=np.float32(self.hop / float(self.N) * 2), center=True, conjugate=True, out_key=id(self))
+        y = h.istft_ola(est.reshape(S * 2, F, T), self.synthesisWindow, self.N, self.hop,
+                        gain=np.float32(self.hop / float(self.N) * 2), center=True, conjugate=True, out_key=self._token)
         self._mark('istft')
         r['targetCoefficientMasks'] = masks
         r['targetSpectrogramEstimates'] = est
@@ -115,7 +128,7 @@ class GCCNMFPipeline(object):
         h = self.h
         self.stage_events = [] if collect_stage_times else None
         r = self._front(samples)
-        argmax, refined = h.tdoa_argmax(r['coherence'], self.E, r['W'], out_key=id(self))
+        argmax, refined = h.tdoa_argmax(r['coherence'], self.E, r['W'], out_key=self._token)
         self._mark('gccnmf')
         target = self._pick_targets(r, 1)[0]
         r['refinedDecisions'] = int(refined.item())
@@ -123,7 +136,7 @@ class GCCNMFPipeline(object):
             _, argmax = h.tdoa_gccnmf(r['coherence'], self.E, r['W'], want_values=False, want_argmax=True)   # exact float64 kernel
         window = (self.hypothesisTDOAs[-1] - self.hypothesisTDOAs[0]) * self.windowPercent
         lut = fn.getTargetTDOALookup(self.hypothesisTDOAs, target, window)
-        mask = h.argmax_mask(argmax, h.to_device(lut.astype(np.uint8)), out_key=id(self))
+        mask = h.argmax_mask(argmax, h.to_device(lut.astype(np.uint8)), out_key=self._token)
         self._mark('mask')
         r['argMaxGCCNMF'] = argmax
         return self._back(r, mask[None])
@@ -142,6 +155,44 @@ class GCCNMFPipeline(object):
         r['targetTDOAGCCNMFs'] = values
         r['_all_nan_flag'] = flag
         return self._back(r, masks)
+
+    # ------------------------------------------------------------------ the whole flow as ONE C-ABI call
+    def run_fused(self, samples, numTargets=0):
+        """gccnmf_separate: every stage enqueued by one library call, target picking on the device, no host synchronisation
+        until the caller reads a result.  numTargets = 0: enhancement flow (one target); >= 1: runGCCNMF.py separation.
+        Returns dict(W, H, targetSignalEstimates (S, 2, n_out), targetTDOAIndexes (device i32), status (device i32))."""
+        import ctypes
+        from ._lib import PipelineConfig, _ptr
+        h, torch = self.h, self.torch
+        n = samples.shape[1]
+        T = self.num_frames(n)
+        S = max(1, numTargets)
+        window = (self.hypothesisTDOAs[-1] - self.hypothesisTDOAs[0]) * self.windowPercent
+        cfg = PipelineConfig(self.N, self.hop, self.D, self.K, self.I, int(numTargets), self.alpha, self.eps, float(window))
+        key = (self._token, 'fused', int(numTargets))
+        W0, H0 = self.nmf_init(2 * T)
+        W, H = h.buffer((key, 'W'), W0.shape, W0.dtype), h.buffer((key, 'H'), H0.shape, H0.dtype)
+        W.copy_(W0)
+        H.copy_(H0)
+        if getattr(self, '_tdoas_dev', None) is None:
+            self._tdoas_dev = h.to_device(np.ascontiguousarray(self.hypothesisTDOAs, dtype=np.float64))
+        length = int(h.lib.gccnmf_istft_length(self.N, self.hop, T, 1))
+        y = h.buffer((key, 'y'), (S, 2, length), torch.float32)
+        targets = h.buffer((key, 'targets'), (S,), torch.int32)
+        status = h.buffer((key, 'status'), (1,), torch.int32)
+        ws = h.workspace('pipeline', h.lib.gccnmf_pipeline_workspace_bytes(ctypes.byref(cfg), n))
+        h.check(h.lib.gccnmf_separate(h.h, ctypes.byref(cfg), _ptr(samples), n, _ptr(self.window), _ptr(self.E), _ptr(self._tdoas_dev), _ptr(W), _ptr(H),
+                                      _ptr(y), _ptr(targets), _ptr(status), _ptr(ws), ws.numel(), h.stream))
+        return dict(W=W, H=H, targetSignalEstimates=y, targetTDOAIndexes=targets, status=status)
+
+    @staticmethod
+    def raise_on_status(status):
+        """The conditions the reference turns into exceptions (call after synchronising)."""
+        st = int(status.item())
+        if st & 1:
+            raise ValueError('did not find enough peaks in the angular spectrum')          # gccNMFFunctions.py:102-104
+        if st & 2:
+            raise ValueError('All-NaN slice encountered')                                  # numpy.nanargmax, :138
 
     # ------------------------------------------------------------------ host-buffer entry (what e2e times)
     def enhance_host(self, samples_host, out_host=None):

@@ -16,7 +16,7 @@ def runGCCNMF(mixtureFilePrefix, windowSize, hopSize, numTDOAs, microphoneSepara
     mixtureFileName = fn.getMixtureFileName(mixtureFilePrefix)
     stereoSamples, sampleRate = fn.loadMixtureSignal(mixtureFileName)
     pipe = GCCNMFPipeline(sampleRate, windowSize, hopSize, numTDOAs, microphoneSeparationInMetres, dictionarySize,
-                          numIterations, sparsityAlpha, device=device)
+                          numIterations, sparsityAlpha, device=device, windowFunction=windowFunction)
     targetSignalEstimates = pipe.separate_host(stereoSamples, numTargets).numpy()
     if save:
         fn.saveTargetSignalEstimates(targetSignalEstimates, sampleRate, mixtureFilePrefix)

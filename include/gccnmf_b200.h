@@ -261,6 +261,31 @@ GCCNMF_API int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int
 GCCNMF_API int gccnmf_wiener_apply_h(gccnmf_handle* h, const float* mask, const float* W, const float* H, const float* X, int F,
                           int T, int K, float* Y, float* wiener, void* stream);
 
+/* ---- the whole offline path as one call ------------------------------------------------------------------
+ * runGCCNMF.py:36-52 (num_targets >= 1: separation into num_targets sources) or the enhancement flow of
+ * notebooks/offlineSpeechEnhancement.ipynb cells 12-41 (num_targets == 0: one target, all-TDOA argmax mask), every stage
+ * enqueued on `stream` without a host synchronisation in between: the target TDOAs are picked by a device kernel with the
+ * semantics of scipy.signal.argrelmax + the numSources largest peaks (gccNMFFunctions.py:94-116) and stay on the device. */
+typedef struct gccnmf_pipeline_config {
+  int window_size, hop_size;      /* N (= n_fft), hop                                                               */
+  int num_tdoas, num_atoms;       /* D, K                                                                           */
+  int num_iterations;             /* KL-NMF iterations                                                              */
+  int num_targets;                /* S >= 1: separation; 0: enhancement (one target)                               */
+  float sparsity_alpha, epsilon;  /* gccNMFFunctions.py:69                                                          */
+  float target_window_seconds;    /* enhancement: |tdoa - tdoa[target]| < this (ipynb:468-471)                      */
+} gccnmf_pipeline_config;
+GCCNMF_API size_t gccnmf_pipeline_workspace_bytes(const gccnmf_pipeline_config* cfg, int64_t num_samples);
+/* targets (num_targets) i32 ascending; *status |= 1 when the spectrum has fewer strict local maxima than num_targets. */
+GCCNMF_API int gccnmf_pick_targets(gccnmf_handle* h, const double* mean_angular, int D, int num_targets, int32_t* targets,
+                        int32_t* status, void* stream);
+/* samples (2, n) f32; window (N) f64; E (F, D) c128; tdoas (D) f64; W (F, K), H (K, 2T) f32 in: seeded initial values
+ * (gccNMFFunctions.py:70-73), out: learnt; signals (S, 2, gccnmf_istft_length(N, hop, T, 1)) f32; target_indexes (S) i32 and
+ * status (1) i32 are device outputs: bit 0 too few peaks (the reference aborts), bit 1 all-NaN mask column (numpy raises),
+ * bit 2 more near-tie argmax decisions than the float64 refinement list holds (re-run gccnmf_tdoa_gccnmf). */
+GCCNMF_API int gccnmf_separate(gccnmf_handle* h, const gccnmf_pipeline_config* cfg, const float* samples, int64_t num_samples,
+                    const double* window, const double* E, const double* tdoas, float* W, float* H, float* signals,
+                    int32_t* target_indexes, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a13 + f-2: the real-time block path as one stream-ordered unit ----------------------------------
  * GCCNMFProcessor.processFrames (realtime/gccNMFProcessor.py:201-231 and the Theano graph of :245-270) with the
  * OverlapAddProcessor rings around it (realtime/utils.py:72-116) and, optionally, the per-frame coefficient inference of

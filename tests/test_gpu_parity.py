@@ -333,3 +333,57 @@ def test_masked_reconstruction_tensor_cores_vs_float32_kernel(h, S, F, T, K):
     assert tc.shape == ref.shape == (S, 2, F, T)
     assert relerr(simt, ref) < 2e-6
     assert relerr(tc, ref) < 1e-5 and np.abs(tc - ref).max() < 3e-5 * np.abs(ref).max()
+
+
+def test_fused_separate_call_equals_staged_pipeline(golden):
+    """gccnmf_separate (one C-ABI call, target TDOAs picked by the device kernel with argrelmax semantics) against the staged
+    pipeline (scipy peak picking on the host, like the reference): same targets, bit-identical W, H and signals -- both flows."""
+    import torch
+    from gcc_nmf_b200.pipeline import GCCNMFPipeline
+    from gcc_nmf_b200.synth import synthetic_stereo
+    g = golden('separation_mini')
+    sr, N, hop, D, S, K, I = [int(v) for v in g['params']]
+    pipe = GCCNMFPipeline(sr, N, hop, D, float(g['micSep']), K, I)
+    x = pipe.h.to_device(g['samples'])
+    staged = pipe.separate(x, S)
+    fused = pipe.run_fused(x, S)
+    torch.cuda.synchronize()
+    pipe.raise_on_status(fused['status'])
+    assert fused['targetTDOAIndexes'].cpu().tolist() == staged['targetTDOAIndexes'] == [int(i) for i in g['targetTDOAIndexes']]
+    assert torch.equal(fused['W'], staged['W']) and torch.equal(fused['H'], staged['H'])
+    assert torch.equal(fused['targetSignalEstimates'], staged['targetSignalEstimates'])
+    # enhancement flow at a shape that takes every tensor-core path (KL-NMF planes, argmax GEMM, masked reconstruction)
+    pipe2 = GCCNMFPipeline(16000, 1024, 256, 64, 0.1, 256, 10)
+    x2 = pipe2.h.to_device(synthetic_stereo(6.0, seed=3))
+    staged2 = pipe2.enhance(x2)
+    y_staged = staged2['targetSignalEstimates'].clone()
+    fused2 = pipe2.run_fused(x2, 0)
+    torch.cuda.synchronize()
+    pipe2.raise_on_status(fused2['status'])
+    assert fused2['targetTDOAIndexes'].cpu().tolist() == staged2['targetTDOAIndexes']
+    assert torch.equal(fused2['W'], staged2['W']) and torch.equal(fused2['targetSignalEstimates'], y_staged)
+
+
+def test_device_peak_picking_matches_scipy(h, fn):
+    """gccnmf_pick_targets against scipy.signal.argrelmax + top-S (gccNMFFunctions.py:94-116) on random spectra, plateaus and
+    too-few-peaks cases."""
+    import torch
+    rng = np.random.default_rng(8)
+    for trial in range(40):
+        D = int(rng.choice([8, 16, 64, 128]))
+        x = rng.standard_normal(D)
+        if trial % 5 == 0:
+            x[3:6] = x[3]                                  # a plateau is not a strict maximum
+        S = int(rng.integers(1, 4))
+        peaks = fn.argrelmax(x)[0]
+        xd = h.to_device(x)
+        targets = torch.zeros(S, dtype=torch.int32, device=h.device)
+        status = torch.zeros(1, dtype=torch.int32, device=h.device)
+        h.check(h.lib.gccnmf_pick_targets(h.h, xd.data_ptr(), D, S, targets.data_ptr(), status.data_ptr(), h.stream))
+        if len(peaks) < S:
+            assert int(status.item()) & 1
+            with pytest.raises(ValueError):
+                fn.estimateTargetTDOAIndexesFromAngularSpectrum(x, 0.1, D, S)
+        else:
+            assert int(status.item()) == 0
+            assert targets.cpu().tolist() == [int(i) for i in fn.estimateTargetTDOAIndexesFromAngularSpectrum(x, 0.1, D, S)]
