@@ -217,19 +217,21 @@ __device__ __forceinline__ float multimem_sum_f32(const float* p) {
   return v;
 }
 
-// W update, one fully parallel pass over 32 x 32 tiles (grid: atoms / 32 x rows / 32):
+// W update, one fully parallel pass over tiles of 32 rows x 128 atoms (grid: atoms / 128 x rows / 32 = 8 x 17 = 136 CTAs at the
+// headline shape: one wave): a thread owns 4 consecutive atoms (one 16-byte access per matrix) of 4 rows, with every load of
+// its 4 rows -- 4 x (k-split partials + U) -- in flight before the first use:
 //   U <- U * (sum_z partial[z]) / rowsum(G)  (:77 in the (U, G) gauge); planes of U; per-tile column sums and column sums of
 //   squares -> colsum_part / sumsq_part[row block][atom] (summed by their consumers: colsum(U) and c = ||U[:, k]||)
+constexpr int kApplyAtoms = 128;      // atoms per CTA (32 lanes x 4)
 template <bool MULTIMEM>
-__global__ void __launch_bounds__(kApplyTile * 8)
+__global__ void __launch_bounds__(256)
 tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, const float* __restrict__ partial, int splits,
                    const float* __restrict__ rowsum, int rowsum_slots, int F, int K, float* __restrict__ sumsq_part, float* __restrict__ colsum_part,
                    const unsigned* arrival_counter, unsigned arrivals_expected) {
-  __shared__ float rs_s[kApplyTile];
-  __shared__ float part[2][8][kApplyTile + 1];
+  __shared__ float4 part[2][8][32];
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
-  const int c = threadIdx.x, g = threadIdx.y;
+  const int c = threadIdx.x, g = threadIdx.y;          // c: lane (4 atoms), g: row group 0..7
   if (MULTIMEM && arrival_counter) {
     // every rank's partial numerator is in its symmetric buffer once my copy of the counter has received all arrivals
     if (c == 0 && g == 0) {
@@ -242,57 +244,67 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
     }
     __syncthreads();
   }
-  const int k = blockIdx.x * kApplyTile + c;
+  const int k = blockIdx.x * kApplyAtoms + 4 * c;       // K % 8 == 0 on this path: a thread's 4 atoms are all inside or all outside
   const int64_t slab = (int64_t)F * K;
-  if (g == 0) {
-    float rs = 0.f;
-    if (k < K) {
-      if (MULTIMEM) rs = multimem_sum_f32(rowsum + k);
-      else
-        for (int s = 0; s < rowsum_slots; ++s) rs += rowsum[(int64_t)s * K + k];
+  const bool active = k < K;
+  float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 numer[kApplyTile / 8], u[kApplyTile / 8];
+  if (active) {
+    if (MULTIMEM) {
+      rs = make_float4(multimem_sum_f32(rowsum + k), multimem_sum_f32(rowsum + k + 1), multimem_sum_f32(rowsum + k + 2), multimem_sum_f32(rowsum + k + 3));
+    } else {
+      rs = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < rowsum_slots; ++s) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(rowsum + (int64_t)s * K + k));
+        rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
+      }
     }
-    rs_s[c] = rs;
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {
+      const int f = blockIdx.y * kApplyTile + g + 8 * r;
+      numer[r] = u[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < F) {
+        const int64_t i = (int64_t)f * K + k;
+        u[r] = *reinterpret_cast<const float4*>(U + i);
+        if (MULTIMEM) {
+          numer[r] = make_float4(multimem_sum_f32(partial + i), multimem_sum_f32(partial + i + 1), multimem_sum_f32(partial + i + 2),
+                                 multimem_sum_f32(partial + i + 3));      // sum over ranks, reduced inside the NVSwitch
+        } else {
+          float4 p[kMaxSplits];                       // all split partials in flight at once, then summed in split order
+#pragma unroll
+          for (int z = 0; z < kMaxSplits; ++z)
+            p[z] = z < splits ? __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          numer[r] = p[0];
+#pragma unroll
+          for (int z = 1; z < kMaxSplits; ++z)
+            if (z < splits) { numer[r].x += p[z].x; numer[r].y += p[z].y; numer[r].z += p[z].z; numer[r].w += p[z].w; }
+        }
+      }
+    }
   }
-  __syncthreads();
-  float sumsq = 0.f, csum = 0.f;
-  if (k < K) {
-    const float rs = rs_s[c];
+  float4 sumsq = make_float4(0.f, 0.f, 0.f, 0.f), csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
 #pragma unroll
     for (int r = 0; r < kApplyTile / 8; ++r) {
       const int f = blockIdx.y * kApplyTile + g + 8 * r;
       if (f < F) {
         const int64_t i = (int64_t)f * K + k;
-        float numer;
-        if (MULTIMEM) {
-          numer = multimem_sum_f32(partial + i);      // sum over ranks, reduced inside the NVSwitch
-        } else {
-          float p[kMaxSplits];                       // all split partials in flight at once, then summed in split order
-#pragma unroll
-          for (int z = 0; z < kMaxSplits; ++z) p[z] = z < splits ? __ldg(partial + (int64_t)z * slab + i) : 0.f;
-          numer = p[0];
-#pragma unroll
-          for (int z = 1; z < kMaxSplits; ++z)
-            if (z < splits) numer += p[z];
-        }
-        const float u = U[i] * (numer / rs);
-        U[i] = u;
-        sumsq += u * u;
-        csum += u;
-        bf16 hi, lo;
-        split_bf16(u, hi, lo);
-        Up[i] = hi;
-        Up[plane + i] = lo;
+        const float4 w = make_float4(u[r].x * (numer[r].x / rs.x), u[r].y * (numer[r].y / rs.y), u[r].z * (numer[r].z / rs.z), u[r].w * (numer[r].w / rs.w));
+        *reinterpret_cast<float4*>(U + i) = w;
+        store_planes4(Up + i, plane, w, 4, true);
+        sumsq.x += w.x * w.x; sumsq.y += w.y * w.y; sumsq.z += w.z * w.z; sumsq.w += w.w * w.w;
+        csum.x += w.x; csum.y += w.y; csum.z += w.z; csum.w += w.w;
       }
     }
   }
   part[0][g][c] = sumsq;
   part[1][g][c] = csum;
   __syncthreads();
-  if (g < 2 && k < K) {
-    float s = 0.f;
+  if (g < 2 && active) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += part[g][j][c];
-    (g == 0 ? sumsq_part : colsum_part)[(int64_t)blockIdx.y * K + k] = s;
+    for (int j = 0; j < 8; ++j) { const float4 v = part[g][j][c]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    *reinterpret_cast<float4*>((g == 0 ? sumsq_part : colsum_part) + (int64_t)blockIdx.y * K + k) = s;
   }
 }
 
@@ -535,7 +547,7 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
   const Plan p = make_plan(h, F, T2, K);
   const float* partial = numer ? numer : w.partial;
   const float* rowsum = numer ? numer + (int64_t)F * K : w.rowsum_part;
-  const dim3 grid((K + kApplyTile - 1) / kApplyTile, w.row_blocks), block(kApplyTile, 8);
+  const dim3 grid((K + kApplyAtoms - 1) / kApplyAtoms, w.row_blocks), block(32, 8);
   if (numer_is_multicast)
     return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial, 1,
                      rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected);

@@ -402,6 +402,10 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         else umma::mma_commit(smem_u32(accum_full));
       }
       if (args.timing) args.timing[cta_linear * 8 + 3] = clock64();
+    } else if (PAIR && lane == 0 && args.timing) {
+      // the non-leader CTA of a pair issues no MMA: its slots [2] / [3] record the end of its prologue (diagnostics only)
+      args.timing[cta_linear * 8 + 2] = clock64();
+      args.timing[cta_linear * 8 + 3] = 0;
     }
     __syncwarp();
   } else {

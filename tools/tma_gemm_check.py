@@ -171,6 +171,7 @@ def timing():
         s = stamps.cpu().numpy().reshape(-1, 8)[:, 1:7]
         s = s[s[:, 0] > 0]
         s = s[s[:, 5] > 0]
+        s = s[s[:, 2] > 0]            # (a cta_group::2 pair's non-leader issues no MMA: leaders only)
         d = lambda a, b: float(np.median(s[:, b] - s[:, a]))   # noqa: E731
         print('%s M=%d N=%d K=%d tile %d splits %d: %.1f us per call incl. operand split; CTA medians: start->first full %.0f, '
               'mma issue loop %.0f, last issue->accum done %.0f, epilogue %.0f, total %.0f cycles (%d CTAs)' % (
@@ -213,12 +214,18 @@ def stamps():
             k = k[k[:, 0] > 0]
             t0 = k[:, 0].min()
             st, en = k[:, 0] - t0, k[:, 7] - t0
-            is_tc = k[:, 1] > 0
+            is_tc = (k[:, 1] > 0) & (k[:, 2] > 0) & (k[:, 3] > 0)      # the CTAs that issue MMAs (a pair's leader; every CTA otherwise)
+            follower = (k[:, 1] > 0) & (k[:, 2] > 0) & (k[:, 3] == 0)  # the non-leader CTA of a cta_group::2 pair
             dur = (k[:, 7] - k[:, 0])
             cyc = lambda a, b: np.median((k[is_tc, b] - k[is_tc, a]))   # noqa: E731
             msg = '%s: span %.1f us | CTA start offset p50 %.1f max %.1f us | tc CTA dur p50 %.1f max %.1f us' % (
                 name, en.max() / 1e3, np.median(st) / 1e3, st.max() / 1e3, np.median(dur[is_tc]) / 1e3, dur[is_tc].max() / 1e3)
-            msg += ' | cycles: prologue %.0f, main %.0f, drain %.0f, epilogue %.0f' % (cyc(1, 2), cyc(2, 3), cyc(3, 5), cyc(5, 6))
+            msg += ' | cycles: prologue %.0f, main %.0f, drain %.0f, epilogue %.0f, producer done at %.0f, total %.0f' % (
+                cyc(1, 2), cyc(2, 3), cyc(3, 5), cyc(5, 6), cyc(1, 4), cyc(1, 6))
+            if follower.any():
+                fc = lambda a, b: np.median((k[follower, b] - k[follower, a]))   # noqa: E731
+                msg += ' | pair followers (%d): prologue %.0f, producer done at %.0f, accumulator at %.0f, epilogue %.0f' % (
+                    int(follower.sum()), fc(1, 2), fc(1, 4), fc(1, 5), fc(5, 6))
             if prev_end is not None:
                 msg += ' | gap after previous GEMM %.1f us' % ((t0 - prev_end) / 1e3)
             prev_end = k[:, 7].max()
