@@ -51,6 +51,7 @@ constexpr int kApplyTile = 32;
 struct EpiStoreT {   // DT[z][n][m] = acc.  G4 partials (m = atom, n = f) and the test entry.
   struct State {};
   struct Loaded {};
+  static constexpr bool kDualN = true;       // (takes effect for K-major B tiles of <= 128 columns: the test entry covers the dual-N loop)
   static constexpr bool kRowReduce = false;
   static constexpr int kRowValues = 0;
   static constexpr bool kPrefetch = false;
@@ -75,6 +76,7 @@ struct EpiRatioPlanes {   // RT[n][m] = split(VT[n][m] / acc)     G1 / G3 (m = f
   static constexpr bool kRowReduce = false;
   static constexpr int kRowValues = 0;
   static constexpr bool kPrefetch = false;   // V^T is read twice per iteration and stays in L2 (96 % hit rate measured)
+  static constexpr bool kDualN = true;       // 128 x 128 tiles: 2 MMAs of N = 256 per k-step (all four hi / lo products), see tma_gemm.cuh
   const float* __restrict__ VT; bf16* __restrict__ RT; int64_t ld, plane; int M, N; bool vec;
   __device__ void prefetch(int, int) const {}
   __device__ void row_values(int, float*) const {}
@@ -247,18 +249,17 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
   const int k = blockIdx.x * kApplyAtoms + 4 * c;       // K % 8 == 0 on this path: a thread's 4 atoms are all inside or all outside
   const int64_t slab = (int64_t)F * K;
   const bool active = k < K;
-  float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+  // every global load of the thread is issued before the first one is used: the row-sum slots (spread over the 8 row groups),
+  // the k-split partials and U of its 4 rows
+  float4 rs_part = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 numer[kApplyTile / 8], u[kApplyTile / 8];
+  float4 p[kApplyTile / 8][kMaxSplits];
   if (active) {
-    if (MULTIMEM) {
-      rs = make_float4(multimem_sum_f32(rowsum + k), multimem_sum_f32(rowsum + k + 1), multimem_sum_f32(rowsum + k + 2), multimem_sum_f32(rowsum + k + 3));
-    } else {
-      rs = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < rowsum_slots; ++s) {
+    if (!MULTIMEM)
+      for (int s = g; s < rowsum_slots; s += 8) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(rowsum + (int64_t)s * K + k));
-        rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
+        rs_part.x += v.x; rs_part.y += v.y; rs_part.z += v.z; rs_part.w += v.w;
       }
-    }
 #pragma unroll
     for (int r = 0; r < kApplyTile / 8; ++r) {
       const int f = blockIdx.y * kApplyTile + g + 8 * r;
@@ -270,18 +271,33 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
           numer[r] = make_float4(multimem_sum_f32(partial + i), multimem_sum_f32(partial + i + 1), multimem_sum_f32(partial + i + 2),
                                  multimem_sum_f32(partial + i + 3));      // sum over ranks, reduced inside the NVSwitch
         } else {
-          float4 p[kMaxSplits];                       // all split partials in flight at once, then summed in split order
 #pragma unroll
           for (int z = 0; z < kMaxSplits; ++z)
-            p[z] = z < splits ? __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          numer[r] = p[0];
-#pragma unroll
-          for (int z = 1; z < kMaxSplits; ++z)
-            if (z < splits) { numer[r].x += p[z].x; numer[r].y += p[z].y; numer[r].z += p[z].z; numer[r].w += p[z].w; }
+            p[r][z] = z < splits ? __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
   }
+  part[0][g][c] = rs_part;
+  __syncthreads();
+  float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (active) {
+    if (MULTIMEM) {
+      rs = make_float4(multimem_sum_f32(rowsum + k), multimem_sum_f32(rowsum + k + 1), multimem_sum_f32(rowsum + k + 2), multimem_sum_f32(rowsum + k + 3));
+    } else {
+      rs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 v = part[0][j][c]; rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w; }
+#pragma unroll
+      for (int r = 0; r < kApplyTile / 8; ++r) {        // split partials summed in split order
+        numer[r] = p[r][0];
+#pragma unroll
+        for (int z = 1; z < kMaxSplits; ++z)
+          if (z < splits) { numer[r].x += p[r][z].x; numer[r].y += p[r][z].y; numer[r].z += p[r][z].z; numer[r].w += p[r][z].w; }
+      }
+    }
+  }
+  __syncthreads();                                       // part[] is reused below
   float4 sumsq = make_float4(0.f, 0.f, 0.f, 0.f), csum = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
 #pragma unroll

@@ -174,8 +174,8 @@ struct PlaneGemmArgs {
                                 // [1..6] clock64: start, first stage full, last MMA issued, producer done, accumulator complete, epilogue end
 };
 
-template <int BN, int KB, bool A_MN, bool B_MN, int BDIV = 1>     // BDIV = 2: CTA pair (cta_group::2), each CTA holds half of the B tile
-struct Config {
+template <int BN, int KB, bool A_MN, bool B_MN, int BDIV = 1, int NACC = 1>     // BDIV = 2: CTA pair (cta_group::2), each CTA holds half of the B tile;
+struct Config {                                                                  // NACC = 2: dual-N mode, two BN-column accumulators
   static_assert(KB == 32 || KB == 64, "k-block of 32 (SWIZZLE_64B K-major rows) or 64 (SWIZZLE_128B)");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
   static constexpr int kAAtoms = kBM / 64;
@@ -189,7 +189,9 @@ struct Config {
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static_assert(kStages >= 2, "tile too large for a 2-stage pipeline");
-  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kAccCols = BN * NACC;
+  static_assert(kAccCols <= 256, "accumulator columns");
+  static constexpr int kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : 256;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kScratchBytes = kMaxRowValues * kBM * 4 + (kThreads / 32) * 32 * 16;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kScratchBytes + 1024;   // + alignment slack
@@ -216,6 +218,18 @@ struct has_tile_epilogue { static constexpr bool value = false; };
 template <class E>
 struct has_tile_epilogue<E, decltype((void)E::kTileEpilogue)> { static constexpr bool value = E::kTileEpilogue; };
 
+// Epilogues with `static constexpr bool kDualN = true` ask for the dual-N main loop where the shape allows it (K-major B, 2 BN <= 256,
+// no CTA pair).  Measured (profiles/r02_cta_phase_stamps.md): a tcgen05.mma with M = 128 costs ~128 cycles however narrow N is
+// (391 / 388 / 378 cycles per 3-MMA k-step at N = 128 / 208 / 176, and no change at all with cta_group::2, which halves the B bytes
+// read per CTA) -- the instruction is bound by its 128 x 16 A slab, so it only reaches the tensor-pipe floor of N / 2 cycles at
+// N = 256.  The hi and lo planes of a K-major B tile are adjacent in the stage, so ONE MMA with N = 2 BN multiplies an A plane with
+// [B_hi ; B_lo] into two accumulators: 2 MMAs per k-step (A_hi, then A_lo) compute all FOUR products hi.hi + lo.hi | hi.lo + lo.lo in
+// 2 x 128 cycles instead of three products in 3 x 128, and the epilogue adds the two accumulator halves.
+template <class E, class = void>
+struct wants_dual_n { static constexpr bool value = false; };
+template <class E>
+struct wants_dual_n<E, decltype((void)E::kDualN)> { static constexpr bool value = E::kDualN; };
+
 // Epilogue concept (functors in klnmf_tma.cu).  The kernel stages the accumulator tile in shared memory and hands it out by
 // columns: a warp owns column n, lane l rows m .. m + 3 with m = m0 + 4 l (contiguous in every output of the KL-NMF loop).
 //   static constexpr int kRowValues (<= kMaxRowValues);  __device__ void row_values(int m, float* v) const;
@@ -229,7 +243,8 @@ struct has_tile_epilogue<E, decltype((void)E::kTileEpilogue)> { static constexpr
 template <int BN, int KB, bool A_MN, bool B_MN, int CN, int CM, bool PAIR, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
 plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, PlaneGemmArgs args, Epilogue epi) {
-  using C = Config<BN, KB, A_MN, B_MN, PAIR ? 2 : 1>;
+  constexpr bool DUAL = wants_dual_n<Epilogue>::value && !B_MN && !PAIR && 2 * BN <= 256;
+  using C = Config<BN, KB, A_MN, B_MN, PAIR ? 2 : 1, DUAL ? 2 : 1>;
   constexpr int kCluster = CN * CM;
   static_assert(!PAIR || (CN == 1 && CM == 2), "a CTA pair is a 1 x 2 cluster (two m tiles)");
   static_assert((CN == 1 || CN == 2) && (CM == 1 || CM == 2), "cluster of CN n-tiles x CM m-tiles");
@@ -359,7 +374,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && (!PAIR || cy == 0)) {      // pair: the leader issues for both CTAs
-      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN) + (PAIR ? ((uint32_t)(kBM >> 4) << 24) : 0u);   // pair: M = 256
+      constexpr uint32_t idesc = make_idesc(DUAL ? 2 * BN : BN, A_MN, B_MN) + (PAIR ? ((uint32_t)(kBM >> 4) << 24) : 0u);   // pair: M = 256
       // plane offsets inside an operand block and the per-k16 start-address advance
       constexpr uint32_t a_lo_off = A_MN ? KB * 128 : kBM * KB * 2;
       constexpr uint32_t b_lo_off = B_MN ? KB * 128 : (BN / (PAIR ? 2 : 1)) * KB * 2;
@@ -385,6 +400,11 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               mma_bf16_pair(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
               mma_bf16_pair(tmem_base, a_hi, b_lo, idesc, 1);
               mma_bf16_pair(tmem_base, a_hi, b_hi, idesc, 1);
+            } else if constexpr (DUAL) {
+              // N = 2 BN: the descriptor at b_hi walks the BN rows of the hi plane and on into the lo plane behind it
+              umma::mma_bf16(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
+              umma::mma_bf16(tmem_base, a_hi, b_hi, idesc, 1);
+              (void)b_lo;
             } else {
               umma::mma_bf16(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
               umma::mma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
@@ -481,6 +501,12 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (; c + 32 <= ncols; c += 32) {
       if (num_kb > 0) {
         umma::tmem_ld_32x32(taddr + (uint32_t)c, v);
+        if constexpr (DUAL) {      // + the [hi ; lo] . B_lo half: columns BN .. 2 BN - 1
+          float v2[32];
+          umma::tmem_ld_32x32(taddr + (uint32_t)(BN + c), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -491,6 +517,12 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (c < ncols) {   // 16-column remainder (BN = 176, 208)
       if (num_kb > 0) {
         tmem_ld_32x16(taddr + (uint32_t)c, v);
+        if constexpr (DUAL) {
+          float v2[32];
+          tmem_ld_32x16(taddr + (uint32_t)(BN + c), v2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += v2[j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
