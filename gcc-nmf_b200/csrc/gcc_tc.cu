@@ -102,7 +102,7 @@ struct EpiArgmaxTile {
   struct Loaded {};
   int32_t* __restrict__ argmax;        // (K, T)
   const float* __restrict__ colsumW;   // (K) sum_f |W[f,k]|
-  int2* __restrict__ list; int* __restrict__ count; int capacity;
+  int2* __restrict__ list; uint4* __restrict__ candidates; int* __restrict__ count; int capacity;
   int K, T, D; float margin_factor;
   __device__ void prefetch(int, int) const {}
   __device__ void row_values(int, float*) const {}
@@ -125,9 +125,19 @@ struct EpiArgmaxTile {
       }
       const int t = n0 / D + j;
       argmax[(int64_t)m * T + t] = idx;
-      if (nan || !(best - second > margin_factor * colsumW[m])) {
+      const float margin = margin_factor * colsumW[m];
+      if (nan || !(best - second > margin)) {
+        // the TDOAs that can still be the float64 maximum: every value within the margin of the best (all of them after a NaN)
+        uint32_t bits[4] = {0u, 0u, 0u, 0u};
+        for (int d = 0; d < D; ++d) {
+          const float x = col[(size_t)d * tgemm::kBM];
+          if (nan || !(best - x > margin)) bits[d >> 5] |= 1u << (d & 31);
+        }
         const int slot = atomicAdd(count, 1);
-        if (slot < capacity) list[slot] = make_int2(m, t);
+        if (slot < capacity) {
+          list[slot] = make_int2(m, t);
+          candidates[slot] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+        }
       }
     }
   }
@@ -259,12 +269,88 @@ __global__ void abs_colsum_kernel(const float* __restrict__ W, int F, int K, flo
   colsum[k] = s;
 }
 
+// Candidate refinement (the default): the GEMM epilogue leaves, per flagged (atom, frame), the set of TDOAs whose value lies within
+// the margin of the best -- 2 or 3 of D as a rule -- and only those are recomputed in float64.  One warp per pair; lanes stride
+// the bins over TRANSPOSED copies of the coherence (T, F), W (K, F) and E (D, F), so every load of a warp is one contiguous row
+// segment (the first version gathered: 700 MB of 32-byte sectors at the headline shape); each lane accumulates its bins in order
+// (one fma per bin, as the float64 kernel), then a shuffle tree adds the 32 partial sums.
+constexpr int kRefineGroup = 8;        // candidates per pass over the bins
+__global__ void __launch_bounds__(256)
+refine_candidates_kernel(const int2* __restrict__ list, const uint4* __restrict__ candidates, const int* __restrict__ count, int capacity,
+                         const float2* __restrict__ cohT, const float* __restrict__ WT, const double2* __restrict__ ET, int F, int64_t Fp, int D,
+                         int T, int32_t* __restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int n = min(*count, capacity);
+  for (int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n; p += warps) {
+    const int k = list[p].x, t = list[p].y;
+    const uint4 c4 = candidates[p];
+    uint32_t bits[4] = {c4.x, c4.y, c4.z, c4.w};
+    const float2* crow = cohT + (int64_t)t * Fp;
+    const float* wrow = WT + (int64_t)k * Fp;
+    double bv = 0.0;
+    int bi = -1;
+    int word = 0;
+    while (true) {
+      int ds[kRefineGroup], nd = 0;                       // the next <= 8 candidate TDOAs, ascending (warp-uniform)
+      while (nd < kRefineGroup && word < 4) {
+        if (bits[word] == 0u) { ++word; continue; }
+        const int b = __ffs(bits[word]) - 1;
+        bits[word] &= bits[word] - 1;
+        ds[nd++] = word * 32 + b;
+      }
+      if (nd == 0) break;
+      double acc[kRefineGroup];
+#pragma unroll
+      for (int j = 0; j < kRefineGroup; ++j) acc[j] = 0.0;
+      for (int f = lane; f < F; f += 32) {
+        const float2 c = crow[f];
+        const double w = (double)wrow[f];
+#pragma unroll
+        for (int j = 0; j < kRefineGroup; ++j)
+          if (j < nd) {
+            const double2 e = ET[(int64_t)ds[j] * Fp + f];
+            acc[j] = fma((double)c.x * e.x - (double)c.y * e.y, w, acc[j]);
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < kRefineGroup; ++j) {
+        if (j < nd) {
+          double v = acc[j];
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (bi < 0 || argmax_better64(v, ds[j], bv, bi)) { bv = v; bi = ds[j]; }
+        }
+      }
+    }
+    if (lane == 0 && bi >= 0) argmax[(int64_t)k * T + t] = bi;
+  }
+}
+
+// dst (cols, ld) = src (rows, cols)^T for 4-, 8- and 16-byte elements (zero in the pad columns [rows, ld))
+template <typename E>
+__global__ void transpose_pad_kernel(const E* __restrict__ src, int rows, int cols, E* __restrict__ dst, int64_t ld) {
+  __shared__ E tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(int64_t)r * cols + c] : E{};
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < ld) dst[(int64_t)c * ld + r] = tile[threadIdx.x][i];
+  }
+}
+
 constexpr int kArgmaxTile = 256;       // columns (frame, TDOA) per tile: 256 / D whole frames
 
 struct ArgmaxWorkspace {
   bf16 *Gp, *Wp;
-  float* colsum;
+  float *colsum, *WT;
+  float2* cohT;
+  double2* ET;
   int2* list;
+  uint4* cand;
   int* count;
   int64_t Fp, plane_g, plane_w;
   int capacity;
@@ -283,6 +369,10 @@ ArgmaxWorkspace carve_argmax(void* ws, size_t bytes, int F, int T, int D, int K)
   w.Gp = c.take<bf16>((size_t)2 * w.plane_g);
   w.Wp = c.take<bf16>((size_t)2 * w.plane_w);
   w.colsum = c.take<float>(K);
+  w.ET = c.take<double2>((size_t)D * w.Fp);
+  w.cand = c.take<uint4>(w.capacity);
+  w.cohT = c.take<float2>((size_t)T * w.Fp);
+  w.WT = c.take<float>((size_t)K * w.Fp);
   w.list = c.take<int2>(w.capacity);
   w.count = c.take<int>(4);
   w.ok = ws != nullptr && c.ok();
@@ -292,7 +382,8 @@ ArgmaxWorkspace carve_argmax(void* ws, size_t bytes, int F, int T, int D, int K)
 size_t argmax_workspace_bytes(int F, int T, int D, int K) {
   WorkspaceCarver c(reinterpret_cast<void*>(256), ~size_t(0) >> 1);
   const size_t Fp = (F + 7) & ~7;
-  c.take<bf16>((size_t)2 * T * D * Fp); c.take<bf16>((size_t)2 * F * K); c.take<float>(K); c.take<int2>(list_capacity(K, T)); c.take<int>(4);
+  c.take<bf16>((size_t)2 * T * D * Fp); c.take<bf16>((size_t)2 * F * K); c.take<float>(K); c.take<double2>((size_t)D * Fp);
+  c.take<uint4>(list_capacity(K, T)); c.take<float2>((size_t)T * Fp); c.take<float>((size_t)K * Fp); c.take<int2>(list_capacity(K, T)); c.take<int>(4);
   return align_up(c.used, 256);
 }
 
@@ -434,9 +525,19 @@ int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, c
   const int N = T * D;
   const Operand Wmn{w.Wp, (int64_t)K, w.plane_w, true};          // A(m = atom, k = f): (F, K) as it lies
   const Operand Gk{w.Gp, w.Fp, w.plane_g, false};                // B(n = (t, tau), k = f)
-  EpiArgmaxTile epi{argmax, w.colsum, w.list, w.count, w.capacity, K, T, D, margin_factor(F)};
+  EpiArgmaxTile epi{argmax, w.colsum, w.list, w.cand, w.count, w.capacity, K, T, D, margin_factor(F)};
   if (int st = plane_gemm<true, false>(h, kArgmaxTile, Wmn, Gk, K, N, F, 1, false, epi, nullptr, stream, true)) return st;
-  if (h->argmax_refine_shared && D <= 64) {
+  if (h->argmax_refine_shared) {
+    // candidate refinement over transposed copies (contiguous loads); argmax_refine_shared = 0 selects the all-TDOA kernels below
+    const dim3 tb(32, 8);
+    GCCNMF_LAUNCH(h, transpose_pad_kernel<float2>, dim3((T + 31) / 32, (int)((w.Fp + 31) / 32)), tb, 0, stream, reinterpret_cast<const float2*>(coherence), F,
+                  T, w.cohT, w.Fp);
+    GCCNMF_LAUNCH(h, transpose_pad_kernel<float>, dim3((K + 31) / 32, (int)((w.Fp + 31) / 32)), tb, 0, stream, W, F, K, w.WT, w.Fp);
+    GCCNMF_LAUNCH(h, transpose_pad_kernel<double2>, dim3((D + 31) / 32, (int)((w.Fp + 31) / 32)), tb, 0, stream, reinterpret_cast<const double2*>(E), F, D,
+                  w.ET, w.Fp);
+    GCCNMF_LAUNCH(h, refine_candidates_kernel, h->sm_count * 8, 256, 0, stream, w.list, w.cand, w.count, w.capacity, w.cohT, w.WT, w.ET, F, w.Fp, D, T,
+                  argmax);
+  } else if (D <= 64) {
     GCCNMF_LAUNCH(h, refine_argmax_shared_kernel, h->sm_count * 4, 256, 0, stream, w.list, w.count, w.capacity,
                   reinterpret_cast<const float2*>(coherence), F, T, reinterpret_cast<const double2*>(E), D, W, K, argmax);
   } else {

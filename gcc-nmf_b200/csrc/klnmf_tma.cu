@@ -520,7 +520,7 @@ int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, c
   const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
   {  // G1: RT = split(VT / (U . G^T))
     EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2, true};
-    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream)) return st;
+    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream, false, true)) return st;
   }
   if (colsum_state == 0) GCCNMF_LAUNCH(h, tma_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
   {  // G2: HT32, HTp = G * (U^T . R) / denom
@@ -544,7 +544,7 @@ int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, 
     const Operand Wk{w.Wp, (int64_t)K, w.plane_w, false};
     const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
     EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2, true};
-    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream)) return st;
+    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream, false, true)) return st;
   }
   {  // G4: partial[z][f][atom] = sum_t H^T[t][atom] R^T[t][f]
     const Operand HTmn{w.HTp, (int64_t)K, w.plane_ht, true};

@@ -223,8 +223,10 @@ struct has_tile_epilogue<E, decltype((void)E::kTileEpilogue)> { static constexpr
 // (391 / 388 / 378 cycles per 3-MMA k-step at N = 128 / 208 / 176, and no change at all with cta_group::2, which halves the B bytes
 // read per CTA) -- the instruction is bound by its 128 x 16 A slab, so it only reaches the tensor-pipe floor of N / 2 cycles at
 // N = 256.  The hi and lo planes of a K-major B tile are adjacent in the stage, so ONE MMA with N = 2 BN multiplies an A plane with
-// [B_hi ; B_lo] into two accumulators: 2 MMAs per k-step (A_hi, then A_lo) compute all FOUR products hi.hi + lo.hi | hi.lo + lo.lo in
-// 2 x 128 cycles instead of three products in 3 x 128, and the epilogue adds the two accumulator halves.
+// [B_hi ; B_lo] into two accumulators: 2 MMAs per k-step (A_hi, then A_lo) compute all FOUR products hi.hi + lo.hi | hi.lo + lo.lo
+// instead of three products in three MMAs, and the epilogue adds the two accumulator halves (measured: 391 -> 334 cycles per k-step,
+// now at the shared-memory port: 24 KB of operand reads + 16 KB of TMA writes).  With a CTA pair (cta_group::2, M = 256) on top, the
+// N = 2 BN operand is split between the two CTAs by plane, which halves the B bytes each CTA reads and writes.
 template <class E, class = void>
 struct wants_dual_n { static constexpr bool value = false; };
 template <class E>
@@ -243,7 +245,7 @@ struct wants_dual_n<E, decltype((void)E::kDualN)> { static constexpr bool value 
 template <int BN, int KB, bool A_MN, bool B_MN, int CN, int CM, bool PAIR, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
 plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, PlaneGemmArgs args, Epilogue epi) {
-  constexpr bool DUAL = wants_dual_n<Epilogue>::value && !B_MN && !PAIR && 2 * BN <= 256;
+  constexpr bool DUAL = wants_dual_n<Epilogue>::value && !B_MN && 2 * BN <= 256;
   using C = Config<BN, KB, A_MN, B_MN, PAIR ? 2 : 1, DUAL ? 2 : 1>;
   constexpr int kCluster = CN * CM;
   static_assert(!PAIR || (CN == 1 && CM == 2), "a CTA pair is a 1 x 2 cluster (two m tiles)");
@@ -339,6 +341,10 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int a = 0; a < kHalfAtoms; ++a)
               tma_load_3d_pair(b_dst + a * C::kAtomBytes, &map_b, leader_bar, n0 + 64 * (cy * kHalfAtoms + a), k0, 0);
+          } else if constexpr (DUAL) {
+            // pair + dual-N: the N = 2 BN operand [B_hi ; B_lo] is split between the CTAs by PLANE -- the leader holds all BN rows of
+            // the hi plane, its peer those of the lo plane (same bytes per CTA as half of both planes)
+            tma_load_3d_pair(b_dst, &map_b, leader_bar, k0, n0, cy);
           } else {
             constexpr int kRows = BN / 2;
 #pragma unroll
@@ -396,7 +402,12 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint64_t a_lo = A_MN ? make_desc(a_addr + a_lo_off, C::kAtomBytes, 1024, 2) : make_desc(a_addr + a_lo_off, 16, C::kKSbo, C::kKLayout);
             const uint64_t b_hi = B_MN ? make_desc(b_addr, C::kAtomBytes, 1024, 2) : make_desc(b_addr, 16, C::kKSbo, C::kKLayout);
             const uint64_t b_lo = B_MN ? make_desc(b_addr + b_lo_off, C::kAtomBytes, 1024, 2) : make_desc(b_addr + b_lo_off, 16, C::kKSbo, C::kKLayout);
-            if constexpr (PAIR) {
+            if constexpr (PAIR && DUAL) {
+              // M = 256 (both m tiles), N = 2 BN ([leader: B_hi ; peer: B_lo]): all four products of both tiles in two MMAs
+              mma_bf16_pair(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
+              mma_bf16_pair(tmem_base, a_hi, b_hi, idesc, 1);
+              (void)b_lo;
+            } else if constexpr (PAIR) {
               mma_bf16_pair(tmem_base, a_lo, b_hi, idesc, (i | kk) != 0);
               mma_bf16_pair(tmem_base, a_hi, b_lo, idesc, 1);
               mma_bf16_pair(tmem_base, a_hi, b_hi, idesc, 1);

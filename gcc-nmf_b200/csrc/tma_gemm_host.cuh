@@ -216,8 +216,10 @@ struct PlaneGemmInstance {
     CUtensorMap map_a, map_b;
     if (int st = A_MN ? tmap_mnmajor(h, A.planes, g.M, g.Kc, A.pitch, A.plane, &map_a)
                       : tmap_kmajor(h, A.planes, g.M, g.Kc, A.pitch, A.plane, tgemm::kBM / CN, &map_a)) return st;
+    // (pair + dual-N: each CTA of the pair loads all BN rows of ONE plane of B, see the kernel)
+    constexpr bool kPairDual = PAIR && tgemm::wants_dual_n<Epi>::value && !B_MN && 2 * BN <= 256;
     if (int st = B_MN ? tmap_mnmajor(h, B.planes, g.N, g.Kc, B.pitch, B.plane, &map_b)
-                      : tmap_kmajor(h, B.planes, g.N, g.Kc, B.pitch, B.plane, BN / CM, &map_b)) return st;
+                      : tmap_kmajor(h, B.planes, g.N, g.Kc, B.pitch, B.plane, kPairDual ? BN : BN / CM, &map_b)) return st;
     PlaneGemmArgs args{};
     args.M = g.M; args.N = g.N; args.Kc = g.Kc;
     args.m_tiles = g.m_tiles;
@@ -246,7 +248,7 @@ struct PlaneGemmInstance {
 // single-CTA grid is); h->gemm_cluster (diagnostics) forces 10 CN + CM.
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, bool simt_tail,
-                      const Epi& epi, unsigned long long* timing, void* stream, bool m_fastest = false) {
+                      const Epi& epi, unsigned long long* timing, void* stream, bool m_fastest = false, bool prefer_pair = false) {
   GemmShape g{};
   g.M = M; g.N = N; g.Kc = Kc; g.splits = splits; g.m_fastest = m_fastest;
   const int tail = M % tgemm::kBM;
@@ -256,9 +258,9 @@ int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int 
   g.tail_rows = use_tail ? tail : 0;
   g.n_tiles = (N + BN - 1) / BN;
   const int ctas = g.n_tiles * g.m_tiles * splits;
-  if (h->gemm_pair) {
-    // cta_group::2 CTA pairs (two m tiles issue one 256 x BN MMA, each holding half of B): compiled, NOT yet validated on
-    // hardware -- reachable only through set_option("gemm_pair", 1), never chosen automatically.
+  if (h->gemm_pair > 0 || (h->gemm_pair < 0 && prefer_pair)) {
+    // cta_group::2 CTA pairs (two m tiles issue one 256-row MMA).  Option gemm_pair: -1 (default) where the call site asks for it --
+    // the W.H contractions, which combine it with the dual-N loop --, 1 wherever the shape allows, 0 never.
     constexpr bool kPairOk = B_MN ? (BN % 128 == 0) : ((BN / 2) % 8 == 0);
     if constexpr (kPairOk) {
       if (g.m_tiles % 2 == 0) {
@@ -298,12 +300,12 @@ int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int 
 
 template <bool A_MN, bool B_MN, class Epi>
 int plane_gemm(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, bool simt_tail, const Epi& epi,
-               unsigned long long* timing, void* stream, bool m_fastest = false) {
+               unsigned long long* timing, void* stream, bool m_fastest = false, bool prefer_pair = false) {
   switch (bn) {
-    case 128: return launch_plane_gemm<128, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest);
-    case 176: return launch_plane_gemm<176, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest);
-    case 208: return launch_plane_gemm<208, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest);
-    case 256: return launch_plane_gemm<256, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest);
+    case 128: return launch_plane_gemm<128, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
+    case 176: return launch_plane_gemm<176, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
+    case 208: return launch_plane_gemm<208, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
+    case 256: return launch_plane_gemm<256, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
   }
   return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: tile width %d (supported: 128, 176, 208, 256)", bn);
 }

@@ -15,6 +15,7 @@ def h():
     hd = default_handle()
     yield hd
     hd.set_option('gemm_cluster', -1)
+    hd.set_option('gemm_pair', -1)
     hd.set_option('nmf_tma', 1)
     hd.set_option('nmf_pdl', 1)
 
@@ -142,11 +143,11 @@ def test_debug_timing_records_every_cta(h):
     assert h.lib.gccnmf_debug_timing(h.h, None, 1) == 0                 # disarmed and rewound
 
 
-@pytest.mark.skipif(os.environ.get('GCCNMF_TEST_EXPERIMENTAL') != '1',
-                    reason='cta_group::2 CTA-pair kernel: compiled, not yet validated on hardware (set GCCNMF_TEST_EXPERIMENTAL=1)')
 @pytest.mark.parametrize('layout', [(False, False), (True, False), (True, True)])
-def test_plane_gemm_cta_pairs_experimental(h, layout):
-    """set_option('gemm_pair', 1): two m tiles issue one 256 x BN tcgen05.mma.cta_group::2, each CTA holding half of B."""
+def test_plane_gemm_cta_pairs(h, layout):
+    """set_option('gemm_pair', 1): two m tiles issue one 256-row tcgen05.mma.cta_group::2.  With K-major B tiles of <= 128 columns the
+    pair also runs the dual-N loop (N = 2 BN = [leader: B_hi ; peer: B_lo], two MMAs per k-step); wider tiles split both planes of B
+    in halves (three MMAs per k-step)."""
     a_mn, b_mn = layout
     h.set_option('gemm_pair', 1)
     try:
@@ -155,4 +156,26 @@ def test_plane_gemm_cta_pairs_experimental(h, layout):
                 err = _gemm_error(h, M, N, Kc, a_mn, b_mn, tile_n, 1)
                 assert err < 8e-6 + 4e-8 * (3 * Kc / 16), (layout, (M, N, Kc), tile_n, err)
     finally:
-        h.set_option('gemm_pair', 0)
+        h.set_option('gemm_pair', -1)
+
+
+def test_klnmf_pairs_on_and_off_agree(h):
+    """The W.H contractions run on CTA pairs + dual-N by default (gemm_pair = -1); gemm_pair = 0 runs the same four products per
+    k-step on single CTAs: identical arithmetic, so identical results."""
+    import torch
+    from oracle import gccnmf_oracle as orc
+    F, T2, K = 513, 640, 128
+    rng = np.random.default_rng(12)
+    V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
+    W0, H0 = orc.initKLNMF(F, T2, K)
+    out = {}
+    try:
+        for pair in (-1, 0):
+            h.set_option('gemm_pair', pair)
+            W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
+            h.klnmf(V, W, H, 10)
+            torch.cuda.synchronize()
+            out[pair] = (W.cpu().numpy(), H.cpu().numpy())
+    finally:
+        h.set_option('gemm_pair', -1)
+    assert np.array_equal(out[-1][0], out[0][0]) and np.array_equal(out[-1][1], out[0][1])
