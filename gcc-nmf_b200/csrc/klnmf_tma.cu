@@ -66,7 +66,7 @@ struct EpiStoreT {   // DT[z][n][m] = acc.  G4 partials (m = atom, n = f) and th
   __device__ void store(int m, int n, const float4& acc, const Loaded&, int z, State&) const {
     const int valid = min(4, M - m);
     if (valid <= 0) return;
-    store4(DT + (int64_t)z * slab + (int64_t)n * ld + m, acc, valid, vec);
+    store4_streaming(DT + (int64_t)z * slab + (int64_t)n * ld + m, acc, valid, vec);
   }
 };
 
@@ -273,7 +273,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
         } else {
 #pragma unroll
           for (int z = 0; z < kMaxSplits; ++z)
-            p[r][z] = z < splits ? __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            p[r][z] = z < splits ? __ldcs(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
@@ -392,9 +392,11 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------ tile plan
-// Cycles per 16-deep k-step of one CTA: the three UMMAs read 3 x 32 (128 + BN) bytes of shared memory and TMA writes
-// 2 x 32 (128 + BN) through the same 128 B/clk port; the tensor pipe needs 3 BN / 2.
-double kstep_cycles(int bn) { return std::max(160.0 * (128 + bn) / 128.0, 1.5 * bn); }
+// Cycles per 16-deep k-step of one CTA, from the CTA stamps (profiles/r02_cta_phase_stamps.md): a tcgen05.mma with M = 128 costs
+// max(128, 0.65 N) cycles -- below N ~ 200 the 128 x 16 A slab bounds it, above it the tensor pipe at the rate cuBLAS reaches
+// (0.745 of nominal); the dual-N loop issues 2 MMAs of N = 2 bn per k-step, the plain loop 3 of N = bn.
+double mma_cycles(int n) { return std::max(128.0, 0.65 * n); }
+double kstep_cycles(int bn, bool dual) { return (dual && 2 * bn <= 256) ? 2.0 * mma_cycles(2 * bn) : 3.0 * mma_cycles(bn); }
 double epilogue_cycles(int bn) { return 1500.0 + 20.0 * bn; }
 
 int m_tiles_of(int M, bool simt_tail) {
@@ -405,7 +407,7 @@ int m_tiles_of(int M, bool simt_tail) {
 struct TilePlan { int bn, splits; };
 
 // Picks the tile width (and k-split count when `allow_split`) with the smallest estimated time.
-TilePlan plan_tiles(int sm_count, int m_tiles, int N, int Kc, bool allow_split, const int* widths, int n_widths) {
+TilePlan plan_tiles(int sm_count, int m_tiles, int N, int Kc, bool allow_split, const int* widths, int n_widths, bool dual = false) {
   TilePlan best{128, 1};
   double best_cost = 1e300;
   const int total_kb = (Kc + kKB - 1) / kKB;
@@ -416,13 +418,13 @@ TilePlan plan_tiles(int sm_count, int m_tiles, int N, int Kc, bool allow_split, 
     if (allow_split) splits = std::max(1, std::min(std::min(kMaxSplits, sm_count / std::max(1, tiles)), total_kb / 4));
     const int kb = (total_kb + splits - 1) / splits;
     const int waves = (tiles * splits + sm_count - 1) / sm_count;
-    const double cost = waves * (kb * (kKB / 16) * kstep_cycles(bn) + epilogue_cycles(bn) + 3000.0);
+    const double cost = waves * (kb * (kKB / 16) * kstep_cycles(bn, dual) + epilogue_cycles(bn) + 3000.0);
     if (cost < best_cost) { best_cost = cost; best = TilePlan{bn, splits}; }
   }
   return best;
 }
 
-const int kWidthsWH[] = {128, 256};
+const int kWidthsWH[] = {112, 128, 256};          // K-major B: the dual-N loop applies up to 128 columns
 const int kWidthsAll[] = {128, 176, 208, 256};
 
 struct Plan {
@@ -434,7 +436,7 @@ struct Plan {
 
 Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
   Plan p;
-  p.bn_wh = h->wh_tile ? h->wh_tile : plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 2).bn;
+  p.bn_wh = h->wh_tile ? h->wh_tile : plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 3, true).bn;
   p.bn_h = plan_tiles(h->sm_count, m_tiles_of(K, false), T2, F, false, kWidthsAll, 4).bn;
   p.w = plan_tiles(h->sm_count, m_tiles_of(K, false), F, T2, true, kWidthsAll, 4);
   p.rowsum_slots = (T2 + p.bn_h - 1) / p.bn_h;

@@ -157,6 +157,15 @@ __device__ __forceinline__ float4 load4(const float* p, int valid, bool vec, flo
   if (valid > 3) r.w = p[3];
   return r;
 }
+// streaming variant (st.global.cs): data that is written once and read once by the next kernel (the k-split partials of the
+// W-update numerator, 12.6 MB per iteration) should not push the H^T master and planes out of the L2
+__device__ __forceinline__ void store4_streaming(float* p, const float4& v, int valid, bool vec) {
+  if (vec && valid == 4) { __stcs(reinterpret_cast<float4*>(p), v); return; }
+  if (valid > 0) __stcs(p, v.x);
+  if (valid > 1) __stcs(p + 1, v.y);
+  if (valid > 2) __stcs(p + 2, v.z);
+  if (valid > 3) __stcs(p + 3, v.w);
+}
 __device__ __forceinline__ void store4(float* p, const float4& v, int valid, bool vec) {
   if (vec && valid == 4) { *reinterpret_cast<float4*>(p) = v; return; }
   if (valid > 0) p[0] = v.x;
@@ -302,12 +311,13 @@ template <bool A_MN, bool B_MN, class Epi>
 int plane_gemm(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, bool simt_tail, const Epi& epi,
                unsigned long long* timing, void* stream, bool m_fastest = false, bool prefer_pair = false) {
   switch (bn) {
+    case 112: return launch_plane_gemm<112, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 128: return launch_plane_gemm<128, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 176: return launch_plane_gemm<176, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 208: return launch_plane_gemm<208, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 256: return launch_plane_gemm<256, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
   }
-  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: tile width %d (supported: 128, 176, 208, 256)", bn);
+  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: tile width %d (supported: 112, 128, 176, 208, 256)", bn);
 }
 
 }  // namespace tgemm_host

@@ -71,15 +71,15 @@ def test_klnmf_tile_plan_fills_the_chip(lib):
     out = (ctypes.c_int * 8)()
     assert lib.gccnmf_klnmf_tile_plan(148, 513, 3744, 1024, out) == 0            # config 2
     bn_wh, bn_h, bn_w, splits_w, slots, c_wh, c_h, c_w = list(out)
-    assert (bn_wh, bn_h, bn_w, splits_w) == (128, 208, 176, 6)
-    assert slots == 18 and (c_wh, c_h, c_w) == (120, 144, 144)                    # every launch is one wave of <= 148 CTAs
+    assert (bn_wh, bn_h, bn_w, splits_w) == (112, 208, 176, 6)                    # W.H: dual-N loop, 2 MMAs of N = 224 per k-step
+    assert slots == 18 and (c_wh, c_h, c_w) == (136, 144, 144)                    # every launch is one wave of <= 148 CTAs
     assert lib.gccnmf_klnmf_tile_plan(148, 513, 622, 128, out) == 0               # config 1: few tiles -> k-splits for the numerator
     assert out[3] >= 2 and max(out[5], out[6], out[7]) <= 148
     assert lib.gccnmf_klnmf_tile_plan(148, 1025, 37494, 4096, out) == 0           # config 4: many waves, widest tiles
     assert out[0] == 256 and out[1] in (208, 256) and out[3] == 1
     for bn in (out[0], out[1], out[2]):
-        assert bn in (128, 176, 208, 256)
-    assert lib.gccnmf_klnmf_tile_plan(148, 513, 3744, 1020, out) < 0              # K % 8 != 0: loader-based path
+        assert bn in (112, 128, 176, 208, 256)
+    assert lib.gccnmf_klnmf_tile_plan(148, 513, 3744, 1020, out) < 0              # K % 8 != 0: float32 SIMT path
     assert lib.gccnmf_klnmf_tile_plan(0, 513, 3744, 1024, out) < 0
     # fewer SMs -> the planner may not use more CTAs than a wave when a single-wave choice exists
     assert lib.gccnmf_klnmf_tile_plan(132, 513, 3744, 1024, out) == 0
