@@ -212,10 +212,12 @@ __global__ void tma_colsum_kernel(const float* W, int F, int K, float* colsum) {
   colsum[k] = s;
 }
 
-// Cross-rank sum read straight from the NVSwitch (see klnmf_tc.cu).
-__device__ __forceinline__ float multimem_sum_f32(const float* p) {
-  float v;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+// Cross-rank sum read straight from the NVSwitch: p is the multicast address of a symmetric buffer, every rank's copy of the
+// 16 bytes is fetched and added inside the switch (SASS LDGMC.E.ADD.F32x4).
+__device__ __forceinline__ float4 multimem_sum_f32x4(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
 
@@ -268,8 +270,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
         const int64_t i = (int64_t)f * K + k;
         u[r] = *reinterpret_cast<const float4*>(U + i);
         if (MULTIMEM) {
-          numer[r] = make_float4(multimem_sum_f32(partial + i), multimem_sum_f32(partial + i + 1), multimem_sum_f32(partial + i + 2),
-                                 multimem_sum_f32(partial + i + 3));      // sum over ranks, reduced inside the NVSwitch
+          numer[r] = multimem_sum_f32x4(partial + i);      // sum over ranks, reduced inside the NVSwitch
         } else {
 #pragma unroll
           for (int z = 0; z < kMaxSplits; ++z)
@@ -283,7 +284,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
   float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
   if (active) {
     if (MULTIMEM) {
-      rs = make_float4(multimem_sum_f32(rowsum + k), multimem_sum_f32(rowsum + k + 1), multimem_sum_f32(rowsum + k + 2), multimem_sum_f32(rowsum + k + 3));
+      rs = multimem_sum_f32x4(rowsum + k);
     } else {
       rs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -424,7 +425,7 @@ TilePlan plan_tiles(int sm_count, int m_tiles, int N, int Kc, bool allow_split, 
   return best;
 }
 
-const int kWidthsWH[] = {112, 128, 256};          // K-major B: the dual-N loop applies up to 128 columns
+const int kWidthsWH[] = {128, 256};               // K-major B: the dual-N loop applies up to 128 columns (104 / 112: wh_tile option)
 const int kWidthsAll[] = {128, 176, 208, 256};
 
 struct Plan {
@@ -436,7 +437,7 @@ struct Plan {
 
 Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
   Plan p;
-  p.bn_wh = h->wh_tile ? h->wh_tile : plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 3, true).bn;
+  p.bn_wh = h->wh_tile ? h->wh_tile : plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 2, true).bn;
   p.bn_h = plan_tiles(h->sm_count, m_tiles_of(K, false), T2, F, false, kWidthsAll, 4).bn;
   p.w = plan_tiles(h->sm_count, m_tiles_of(K, false), F, T2, true, kWidthsAll, 4);
   p.rowsum_slots = (T2 + p.bn_h - 1) / p.bn_h;

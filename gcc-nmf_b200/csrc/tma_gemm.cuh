@@ -140,6 +140,19 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 8 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // barrier 1: the 8 epilogue warps only
 __device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
@@ -166,6 +179,7 @@ struct PlaneGemmArgs {
   int tail_rows;           // rows [128 m_tiles, M) computed in float32 SIMT by the epilogue warps while the main loop runs (K-major operands)
   int tail_cols;           // columns of the n tile each m tile's CTA takes for those rows (multiple of 2)
   int kblocks_per_split;   // k-blocks of KB handled by one blockIdx.z
+  int preload;             // 1: the by-column epilogue's global operands are fetched into registers while the main loop runs
   int m_fastest;           // 0: grid (n tiles, m tiles, splits); 1: grid (m tiles, n tiles, splits) -- the CTAs that share a B tile are
                            // launched together, so a large B operand is read from HBM once (cluster shapes with CN == 1 only)
   // SIMT tail rows (both operands K-major only): element (r, k) of plane p at ptr[p * plane + r * ld + k]
@@ -178,7 +192,7 @@ struct PlaneGemmArgs {
 template <int BN, int KB, bool A_MN, bool B_MN, int BDIV = 1, int NACC = 1>     // BDIV = 2: CTA pair (cta_group::2), each CTA holds half of the B tile;
 struct Config {                                                                  // NACC = 2: dual-N mode, two BN-column accumulators
   static_assert(KB == 32 || KB == 64, "k-block of 32 (SWIZZLE_64B K-major rows) or 64 (SWIZZLE_128B)");
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
+  static_assert(BN % 8 == 0 && (BN * NACC) % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N (= BN, or 2 BN in the dual-N loop) for M = 128");
   static constexpr int kAAtoms = kBM / 64;
   static constexpr int kBAtoms = (BN + 63) / 64;
   static constexpr int kAtomBytes = 2 * KB * 128;                 // one MN-major atom: 64 elements x KB k-rows x 2 planes
@@ -328,6 +342,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   typename Epilogue::Loaded pre[kPre > 0 ? kPre : 1];
   auto preload = [&]() {
     if constexpr (kPre > 0) {
+      if (!args.preload) return;
       const int n_valid = min(BN, args.N - n0);
 #pragma unroll
       for (int u = 0; u < kPre; ++u) {
@@ -550,7 +565,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
       for (int j = 0; j < 32; ++j) dst[(size_t)(c + j) * kBM] = v[j];
     }
-    if (c < ncols) {   // 16-column remainder (BN = 176, 208)
+    if (c + 16 <= ncols) {   // 16-column remainder (BN = 176, 208)
       if (num_kb > 0) {
         tmem_ld_32x16(taddr + (uint32_t)c, v);
         if constexpr (DUAL) {
@@ -565,6 +580,23 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) dst[(size_t)(c + j) * kBM] = v[j];
+      c += 16;
+    }
+    if (c < ncols) {   // 8-column remainder (BN = 104: halves of 64 and 40 columns)
+      if (num_kb > 0) {
+        tmem_ld_32x8(taddr + (uint32_t)c, v);
+        if constexpr (DUAL) {
+          float v2[32];
+          tmem_ld_32x8(taddr + (uint32_t)(BN + c), v2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += v2[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[(size_t)(c + j) * kBM] = v[j];
     }
   }
   // ------------------------------------------------------------------ epilogue, phase 2 (all 10 warps)
@@ -585,18 +617,22 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     epi.init(st, m_first, rowvals + 4 * lane);
     const int n_valid = min(BN, args.N - n0);
     constexpr int U = kColumnsInFlight;
+    int c_first = warp;
     if constexpr (kPre > 0) {
+      if (args.preload) {
 #pragma unroll
-      for (int u = 0; u < kPre; ++u) {
-        const int cc = warp + kWarps * u;
-        if (cc < n_valid) {
-          const float4 acc = *reinterpret_cast<const float4*>(tile + (size_t)cc * kBM + 4 * lane);
-          epi.store(m_first, n0 + cc, acc, pre[u], z, st);
+        for (int u = 0; u < kPre; ++u) {
+          const int cc = warp + kWarps * u;
+          if (cc < n_valid) {
+            const float4 acc = *reinterpret_cast<const float4*>(tile + (size_t)cc * kBM + 4 * lane);
+            epi.store(m_first, n0 + cc, acc, pre[u], z, st);
+          }
         }
+        c_first = warp + kWarps * kPre;
       }
     }
 #pragma unroll 1
-    for (int c = warp + kWarps * kPre; c < n_valid; c += kWarps * U) {
+    for (int c = c_first; c < n_valid; c += kWarps * U) {
       typename Epilogue::Loaded loaded[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {

@@ -189,7 +189,8 @@ struct GemmShape {
 // One instantiation: kernel attributes + how many of its clusters can be resident at once (queried once).
 template <int BN, bool A_MN, bool B_MN, int CN, int CM, class Epi, bool PAIR = false>
 struct PlaneGemmInstance {
-  using C = tgemm::Config<BN, kKB, A_MN, B_MN, PAIR ? 2 : 1>;
+  static constexpr bool kDual = tgemm::wants_dual_n<Epi>::value && !B_MN && 2 * BN <= 256;
+  using C = tgemm::Config<BN, kKB, A_MN, B_MN, PAIR ? 2 : 1, kDual ? 2 : 1>;
   static int max_clusters(gccnmf_handle* h, int* out) {
     static int cached_per_device[kGccnmfMaxDevices];     // 0 = not queried yet, else value + 1 (per device: attribute + occupancy)
     int& slot = cached_per_device[h->device % kGccnmfMaxDevices];
@@ -239,6 +240,7 @@ struct PlaneGemmInstance {
     args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
     args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
     args.timing = timing;
+    args.preload = (h->gemm_preload >> (Epi::kRowReduce ? 1 : 0)) & 1;     // bit 0: epilogues without a row reduction (the ratio), bit 1: the H update
     // m-fastest (always for a cta_group::2 pair, whose two m tiles must sit next to each other along x): grid (m, n, splits)
     const bool mf = PAIR || g.m_fastest;
     args.m_fastest = mf ? 1 : 0;
@@ -270,7 +272,7 @@ int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int 
   if (h->gemm_pair > 0 || (h->gemm_pair < 0 && prefer_pair)) {
     // cta_group::2 CTA pairs (two m tiles issue one 256-row MMA).  Option gemm_pair: -1 (default) where the call site asks for it --
     // the W.H contractions, which combine it with the dual-N loop --, 1 wherever the shape allows, 0 never.
-    constexpr bool kPairOk = B_MN ? (BN % 128 == 0) : ((BN / 2) % 8 == 0);
+    constexpr bool kPairOk = B_MN ? (BN % 128 == 0) : ((BN / 2) % 8 == 0 && BN % 16 == 0);
     if constexpr (kPairOk) {
       if (g.m_tiles % 2 == 0) {
         int resident = 0;
@@ -292,6 +294,7 @@ int launch_plane_gemm(gccnmf_handle* h, const Operand& A, const Operand& B, int 
     if (m_fastest && cn != 1) continue;
     int resident = 0;
 #define GCCNMF_TRY_CLUSTER(CN_, CM_)                                                                                         \
+    if constexpr (B_MN || (BN / CM_) % 8 == 0) /* the B row slices of a CM-row cluster keep whole swizzle atoms */              \
     if (cn == CN_ && cm == CM_) {                                                                                            \
       if (int st = PlaneGemmInstance<BN, A_MN, B_MN, CN_, CM_, Epi>::max_clusters(h, &resident)) return st;                  \
       /* a single-wave grid must keep all its clusters resident at once; a multi-wave grid only needs one to fit */            \
@@ -311,13 +314,17 @@ template <bool A_MN, bool B_MN, class Epi>
 int plane_gemm(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, bool simt_tail, const Epi& epi,
                unsigned long long* timing, void* stream, bool m_fastest = false, bool prefer_pair = false) {
   switch (bn) {
+    case 104:      // only as a dual-N tile (2 x 104 = 208 columns per MMA; 104 alone is not a multiple of 16)
+      if constexpr (tgemm::wants_dual_n<Epi>::value && !B_MN)
+        return launch_plane_gemm<104, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
+      break;
     case 112: return launch_plane_gemm<112, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 128: return launch_plane_gemm<128, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 176: return launch_plane_gemm<176, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 208: return launch_plane_gemm<208, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
     case 256: return launch_plane_gemm<256, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
   }
-  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: tile width %d (supported: 112, 128, 176, 208, 256)", bn);
+  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: tile width %d (supported: 104, 112, 128, 176, 208, 256)", bn);
 }
 
 }  // namespace tgemm_host

@@ -179,3 +179,13 @@ def test_klnmf_pairs_on_and_off_agree(h):
     finally:
         h.set_option('gemm_pair', -1)
     assert np.array_equal(out[-1][0], out[0][0]) and np.array_equal(out[-1][1], out[0][1])
+
+
+def test_plane_gemm_dual_n_narrow_tiles(h):
+    """104- and 112-column tiles of the dual-N loop (2 x 104 = 208 / 224 columns per MMA): K-major B only; the 40-column
+    half of a 104-column tile exercises the 8-column tcgen05.ld remainder of the epilogue."""
+    for tile_n in (104, 112):
+        for (M, N, Kc) in [(128, 104, 64), (513, 640, 256), (256, 416, 513)]:
+            for a_mn in (False, True):
+                err = _gemm_error(h, M, N, Kc, a_mn, False, tile_n, 1)
+                assert err < 8e-6 + 4e-8 * (3 * Kc / 16), (tile_n, (M, N, Kc), a_mn, err)

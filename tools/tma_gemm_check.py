@@ -179,6 +179,44 @@ def timing():
     return 0
 
 
+def variants():
+    """KL-NMF stage time at config 2 over the runtime switches of the plane GEMM: tile width of the W.H contractions (dual-N loop),
+    epilogue operand preload (bit 0 ratio, bit 1 H update), CTA pairs; plus the result's distance from the default build."""
+    import torch
+    from oracle import gccnmf_oracle as orc
+    h = handle()
+    F, T2, K, iters = 513, 3744, 1024, 100
+    rng = np.random.default_rng(5)
+    V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
+    W0, H0 = orc.initKLNMF(F, T2, K)
+    W0d, H0d = h.to_device(W0), h.to_device(H0)
+    ref = None
+    for wh in (128, 112, 104):
+        for pre in (0, 1, 3):
+            for pair in (-1, 0):
+                h.set_option('wh_tile', wh)
+                h.set_option('gemm_preload', pre)
+                h.set_option('gemm_pair', pair)
+                ms = []
+                for rep in range(3):
+                    W, H = W0d.clone(), H0d.clone()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    h.klnmf(V, W, H, iters)
+                    e1.record()
+                    e1.synchronize()
+                    ms.append(e0.elapsed_time(e1))
+                Wn = W.cpu().numpy()
+                if ref is None:
+                    ref = Wn
+                print('wh_tile %3d preload %d pair %2d: %s ms per 100 iterations | rel W vs first variant %.2e finite %s' % (
+                    wh, pre, pair, ['%.2f' % m for m in ms], _rel(Wn, ref), bool(np.isfinite(Wn).all())), flush=True)
+    h.set_option('wh_tile', 0)
+    h.set_option('gemm_preload', 1)
+    h.set_option('gemm_pair', -1)
+    return 0
+
+
 def stamps():
     """%globaltimer / clock64 stamps of every CTA of the plane GEMMs inside the live KL-NMF loop (config 2)."""
     import ctypes
@@ -264,4 +302,4 @@ if __name__ == '__main__':
                 print('TIMEOUT in %s' % part)
                 rc |= 1
         sys.exit(rc)
-    sys.exit({'gemm': gemm, 'nmf': nmf, 'time': timing, 'prof': prof, 'stamps': stamps}[what]())
+    sys.exit({'gemm': gemm, 'nmf': nmf, 'time': timing, 'prof': prof, 'stamps': stamps, 'variants': variants}[what]())
