@@ -89,6 +89,8 @@ int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
   if (strcmp(name, "wh_tile") == 0) { h->wh_tile = value; return GCCNMF_OK; }
   if (strcmp(name, "argmax_refine_shared") == 0) { h->argmax_refine_shared = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "gemm_pair") == 0) { h->gemm_pair = value; return GCCNMF_OK; }
+  if (strcmp(name, "gemm_streaming") == 0) { h->gemm_streaming = value; return GCCNMF_OK; }
+  if (strcmp(name, "argmax_persistent") == 0) { h->argmax_persistent = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "gemm_preload") == 0) { h->gemm_preload = value; return GCCNMF_OK; }
   if (strcmp(name, "gemm_cluster") == 0) { h->gemm_cluster = value; return GCCNMF_OK; }
   return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);

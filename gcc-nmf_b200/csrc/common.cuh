@@ -19,6 +19,8 @@ struct gccnmf_handle {
   bool nmf_pdl = true;           // programmatic dependent launch between the kernels of a KL-NMF iteration
   int wh_tile = 0;               // diagnostics: tile width of the W.H contractions (0 = planned)
   bool argmax_refine_shared = true;   // exact float64 refinement of near-tie argmax decisions: E staged in shared memory (0 = one warp per pair from L2)
+  int gemm_streaming = 0;        // st.global.cs for the k-split partials of the W-update numerator (diagnostics)
+  bool argmax_persistent = true; // all-TDOA argmax GEMM as one persistent CTA per SM with double-buffered TMEM accumulators (0: one CTA per tile)
   int gemm_preload = 1;          // plane GEMM epilogues that fetch their global operands during the main loop: bit 0 ratio (W.H), bit 1 H update
   int gemm_pair = -1;            // plane GEMM on cta_group::2 CTA pairs (256-row MMAs): -1 where the call site prefers it, 0 never, 1 wherever possible
   int gemm_cluster = -1;         // diagnostics: force the plane GEMM cluster shape 10 CN + CM (11 = no cluster); -1 = automatic

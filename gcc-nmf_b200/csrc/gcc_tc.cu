@@ -143,6 +143,164 @@ struct EpiArgmaxTile {
   }
 };
 
+// ------------------------------------------------------------------ step 2, persistent form
+// The argmax GEMM has many tiles per SM (8 m tiles x T D / 256 n tiles = 3744 at the headline shape = 25 per SM) and no dependency
+// between them, so it runs as ONE persistent CTA per SM that walks the tiles m-fastest (the 8 CTAs working on the same B tile are
+// neighbours: it is read from HBM once and from the L2 seven times), with the shared-memory pipeline running across tile
+// boundaries and TWO 256-column TMEM accumulators: the epilogue of tile j -- straight from TMEM to registers, one thread per atom,
+// no shared-memory staging -- runs under the main loop of tile j + 1, and the per-CTA prologue (barrier init, TMEM allocation,
+// descriptor prefetch) is paid once instead of 25 times.  Same arithmetic as plane_gemm_kernel<256, 32, true, false> + EpiArgmaxTile
+// (three bf16 products per k-step into one float32 accumulator, k tail included): identical values, identical decisions.
+constexpr int kPersBN = 256, kPersKB = 32, kPersStages = 4;
+constexpr int kPersABytes = 2 * tgemm::kBM * kPersKB * 2;            // MN-major A: 2 atoms of 64 atoms x 32 k-rows x 2 planes = 16 KB
+constexpr int kPersBBytes = 2 * kPersBN * kPersKB * 2;               // K-major B: 2 planes x 256 rows x 64 B = 32 KB
+constexpr int kPersStageBytes = kPersABytes + kPersBBytes;
+constexpr int kPersSmem = kPersStages * kPersStageBytes + 256 + 1024;
+constexpr int kPersAtomBytes = 2 * kPersKB * 128;
+
+__global__ void __launch_bounds__(tgemm::kThreads, 1)
+argmax_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int K, int N, int Kc, int m_tiles,
+                              int n_tiles, EpiArgmaxTile epi) {
+  using namespace tgemm;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPersStages * kPersStageBytes);
+  uint64_t* full = bars;                         // [stages]  TMA -> MMA
+  uint64_t* empty = bars + kPersStages;          // [stages]  tcgen05.commit -> TMA
+  uint64_t* acc_full = bars + 2 * kPersStages;   // [2]       tcgen05.commit -> epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2]       epilogue (8 warps) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  if (tid == 0) {
+    for (int s = 0; s < kPersStages; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc_full[b]), 1); mbar_init(smem_u32(&acc_empty[b]), kEpiWarps); }
+    umma::fence_barrier_init();
+    tma_prefetch_descriptor(&map_a);
+    tma_prefetch_descriptor(&map_b);
+  }
+  if (warp == 1) umma::tmem_alloc(smem_u32(tmem_slot), 512);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = (Kc + kPersKB - 1) / kPersKB;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;                                                  // k-blocks produced so far (all tiles)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * kBM, n0 = (tile / m_tiles) * kPersBN;
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int s = g % kPersStages;
+          const uint32_t use = g / kPersStages;
+          if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);
+          const uint32_t bar = smem_u32(&full[s]);
+          const uint32_t a_dst = smem_u32(smem + (size_t)s * kPersStageBytes), b_dst = a_dst + kPersABytes;
+          mbar_arrive_expect_tx(bar, kPersStageBytes);
+          const int k0 = i * kPersKB;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) tma_load_3d(a_dst + a * kPersAtomBytes, &map_a, bar, m0 + 64 * a, k0, 0);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) tma_load_3d(b_dst + p * (kPersBN * kPersKB * 2), &map_b, bar, k0, n0, p);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kPersBN, true, false);
+      uint32_t g = 0, j = 0;                                           // k-blocks consumed, tiles done by this CTA
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+        const uint32_t buf = j & 1u;
+        if (j >= 2) mbar_wait(smem_u32(&acc_empty[buf]), ((j >> 1) - 1) & 1);      // the epilogue has drained this accumulator
+        umma::tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + buf * kPersBN;
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int s = g % kPersStages;
+          mbar_wait(smem_u32(&full[s]), (g / kPersStages) & 1);
+          umma::tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(smem + (size_t)s * kPersStageBytes), b_base = a_base + kPersABytes;
+          const int steps = min(kPersKB / 16, (Kc - i * kPersKB + 15) / 16);
+#pragma unroll
+          for (int kk = 0; kk < kPersKB / 16; ++kk) {
+            if (kk < steps) {
+              const uint32_t a_addr = a_base + kk * 2048u, b_addr = b_base + kk * 32u;
+              const uint64_t a_hi = make_desc(a_addr, kPersAtomBytes, 1024, 2), a_lo = make_desc(a_addr + kPersKB * 128, kPersAtomBytes, 1024, 2);
+              const uint64_t b_hi = make_desc(b_addr, 16, 512, 4), b_lo = make_desc(b_addr + kPersBN * kPersKB * 2, 16, 512, 4);
+              umma::mma_bf16(tmem_d, a_lo, b_hi, idesc, (i | kk) != 0);
+              umma::mma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
+              umma::mma_bf16(tmem_d, a_hi, b_hi, idesc, 1);
+            }
+          }
+          umma::mma_commit(smem_u32(&empty[s]));
+        }
+        umma::mma_commit(smem_u32(&acc_full[buf]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue warps: TMEM -> registers -> argmax per (atom, frame)
+    const int quarter = warp & 3, half = (warp - 2) >> 2;               // TMEM lanes 32 quarter .. + 31; the two warps of a quarter split the frames
+    const int D = epi.D, frames_per_tile = kPersBN / D;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const uint32_t buf = j & 1u;
+      const int m0 = (tile % m_tiles) * kBM, n0 = (tile / m_tiles) * kPersBN;
+      mbar_wait(smem_u32(&acc_full[buf]), (j >> 1) & 1);
+      umma::tc_fence_after_sync();
+      const int m = m0 + quarter * 32 + lane;
+      const int n_valid = min(kPersBN, N - n0);
+      const int frames = n_valid / D;
+      const uint32_t taddr = tmem_base + buf * kPersBN + ((uint32_t)(quarter * 32) << 16);
+      for (int fr = half; fr < frames_per_tile; fr += 2) {
+        if (fr >= frames) break;
+        float best = -INFINITY, second = -INFINITY;
+        int idx = 0, nan = 0;
+        float v[32];
+        for (int c = 0; c < D; c += 32) {
+          umma::tmem_ld_32x32(taddr + (uint32_t)(fr * D + c), v);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float x = v[q];
+            if (x != x) nan = 1;
+            if (x > best) { second = best; best = x; idx = c + q; }
+            else if (x > second) second = x;
+          }
+        }
+        if (m < K) {
+          const int t = n0 / D + fr;
+          epi.argmax[(int64_t)m * epi.T + t] = idx;
+          const float margin = epi.margin_factor * epi.colsumW[m];
+          if (nan || !(best - second > margin)) {
+            uint32_t bits[4] = {0u, 0u, 0u, 0u};
+            for (int c = 0; c < D; c += 32) {              // second pass over the accumulator row: the candidates within the margin
+              umma::tmem_ld_32x32(taddr + (uint32_t)(fr * D + c), v);
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (nan || !(best - v[q] > margin)) bits[c >> 5] |= 1u << q;
+            }
+            const int slot = atomicAdd(epi.count, 1);
+            if (slot < epi.capacity) {
+              epi.list[slot] = make_int2(m, t);
+              epi.candidates[slot] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+            }
+          }
+        }
+      }
+      umma::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(smem_u32(&acc_empty[buf]));      // one arrival per epilogue warp
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    umma::tc_fence_after_sync();
+    umma::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ step 3: exact float64 recomputation of flagged (atom, frame) pairs
 __device__ __forceinline__ bool argmax_better64(double v, int i, double bv, int bi) {   // numpy.argmax: NaN is a maximum, first wins
   const bool vn = v != v, bn = bv != bv;
@@ -526,7 +684,22 @@ int gccnmf_tdoa_argmax(gccnmf_handle* h, const float* coherence, int F, int T, c
   const Operand Wmn{w.Wp, (int64_t)K, w.plane_w, true};          // A(m = atom, k = f): (F, K) as it lies
   const Operand Gk{w.Gp, w.Fp, w.plane_g, false};                // B(n = (t, tau), k = f)
   EpiArgmaxTile epi{argmax, w.colsum, w.list, w.cand, w.count, w.capacity, K, T, D, margin_factor(F)};
-  if (int st = plane_gemm<true, false>(h, kArgmaxTile, Wmn, Gk, K, N, F, 1, false, epi, nullptr, stream, true)) return st;
+  if (h->argmax_persistent && D >= 32) {
+    static DeviceFlags configured;
+    if (!configured(h)) {
+      GCCNMF_CHECK_CUDA(h, cudaFuncSetAttribute(argmax_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersSmem));
+      configured(h) = true;
+    }
+    CUtensorMap map_a, map_b;
+    if (int st = tmap_mnmajor(h, Wmn.planes, K, F, Wmn.pitch, Wmn.plane, &map_a)) return st;
+    if (int st = tmap_kmajor(h, Gk.planes, N, F, Gk.pitch, Gk.plane, kPersBN, &map_b)) return st;
+    const int m_tiles = (K + tgemm::kBM - 1) / tgemm::kBM, n_tiles = (N + kPersBN - 1) / kPersBN;
+    const int ctas = std::min(h->sm_count, m_tiles * n_tiles);
+    if (int st = launch_ex(h, "argmax_gemm_persistent_kernel", argmax_gemm_persistent_kernel, dim3(ctas), dim3(tgemm::kThreads), (size_t)kPersSmem, stream,
+                           false, dim3(1, 1, 1), map_a, map_b, K, N, F, m_tiles, n_tiles, epi)) return st;
+  } else if (int st = plane_gemm<true, false>(h, kArgmaxTile, Wmn, Gk, K, N, F, 1, false, epi, nullptr, stream, true)) {
+    return st;
+  }
   if (h->argmax_refine_shared) {
     // candidate refinement over transposed copies (contiguous loads); argmax_refine_shared = 0 selects the all-TDOA kernels below
     const dim3 tb(32, 8);

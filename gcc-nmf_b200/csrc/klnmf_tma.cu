@@ -55,7 +55,7 @@ struct EpiStoreT {   // DT[z][n][m] = acc.  G4 partials (m = atom, n = f) and th
   static constexpr bool kRowReduce = false;
   static constexpr int kRowValues = 0;
   static constexpr bool kPrefetch = false;
-  float* __restrict__ DT; int64_t ld, slab; int M, N; bool vec;
+  float* __restrict__ DT; int64_t ld, slab; int M, N; bool vec; bool streaming;
   __device__ void prefetch(int, int) const {}
   __device__ void row_values(int, float*) const {}
   __device__ void init(State&, int, const float*) const {}
@@ -66,7 +66,8 @@ struct EpiStoreT {   // DT[z][n][m] = acc.  G4 partials (m = atom, n = f) and th
   __device__ void store(int m, int n, const float4& acc, const Loaded&, int z, State&) const {
     const int valid = min(4, M - m);
     if (valid <= 0) return;
-    store4_streaming(DT + (int64_t)z * slab + (int64_t)n * ld + m, acc, valid, vec);
+    if (streaming) store4_streaming(DT + (int64_t)z * slab + (int64_t)n * ld + m, acc, valid, vec);
+    else store4(DT + (int64_t)z * slab + (int64_t)n * ld + m, acc, valid, vec);
   }
 };
 
@@ -76,7 +77,8 @@ struct EpiRatioPlanes {   // RT[n][m] = split(VT[n][m] / acc)     G1 / G3 (m = f
   static constexpr bool kRowReduce = false;
   static constexpr int kRowValues = 0;
   static constexpr bool kPrefetch = false;   // V^T is read twice per iteration and stays in L2 (96 % hit rate measured)
-  static constexpr bool kDualN = true;       // 128 x 128 tiles: 2 MMAs of N = 256 per k-step (all four hi / lo products), see tma_gemm.cuh
+  static constexpr bool kDualN = true;       // 2 MMAs of N = 2 BN per k-step (all four hi / lo products), see tma_gemm.cuh
+  static constexpr bool kPreloadOperands = true;   // V^T of the thread's columns is fetched while the main loop runs
   const float* __restrict__ VT; bf16* __restrict__ RT; int64_t ld, plane; int M, N; bool vec;
   __device__ void prefetch(int, int) const {}
   __device__ void row_values(int, float*) const {}
@@ -274,7 +276,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
         } else {
 #pragma unroll
           for (int z = 0; z < kMaxSplits; ++z)
-            p[r][z] = z < splits ? __ldcs(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            p[r][z] = z < splits ? __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
@@ -394,9 +396,9 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
 
 // ------------------------------------------------------------------------------------------------ tile plan
 // Cycles per 16-deep k-step of one CTA, from the CTA stamps (profiles/r02_cta_phase_stamps.md): a tcgen05.mma with M = 128 costs
-// max(128, 0.65 N) cycles -- below N ~ 200 the 128 x 16 A slab bounds it, above it the tensor pipe at the rate cuBLAS reaches
-// (0.745 of nominal); the dual-N loop issues 2 MMAs of N = 2 bn per k-step, the plain loop 3 of N = bn.
-double mma_cycles(int n) { return std::max(128.0, 0.65 * n); }
+// ~128 cycles up to N = 208 (131 / 126 / 129 at N = 128 / 176 / 208) and ~168 at N = 224 / 256 (the rate cuBLAS reaches: 0.745 of
+// nominal); the dual-N loop issues 2 MMAs of N = 2 bn per k-step, the plain loop 3 of N = bn.
+double mma_cycles(int n) { return n <= 208 ? 128.0 : 168.0; }
 double kstep_cycles(int bn, bool dual) { return (dual && 2 * bn <= 256) ? 2.0 * mma_cycles(2 * bn) : 3.0 * mma_cycles(bn); }
 double epilogue_cycles(int bn) { return 1500.0 + 20.0 * bn; }
 
@@ -425,7 +427,7 @@ TilePlan plan_tiles(int sm_count, int m_tiles, int N, int Kc, bool allow_split, 
   return best;
 }
 
-const int kWidthsWH[] = {128, 256};               // K-major B: the dual-N loop applies up to 128 columns (104 / 112: wh_tile option)
+const int kWidthsWH[] = {104, 128, 256};          // K-major B: the dual-N loop applies up to 128 columns (112: wh_tile option)
 const int kWidthsAll[] = {128, 176, 208, 256};
 
 struct Plan {
@@ -437,7 +439,7 @@ struct Plan {
 
 Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
   Plan p;
-  p.bn_wh = h->wh_tile ? h->wh_tile : plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 2, true).bn;
+  p.bn_wh = h->wh_tile ? h->wh_tile : plan_tiles(h->sm_count, m_tiles_of(F, true), T2, K, false, kWidthsWH, 3, true).bn;
   p.bn_h = plan_tiles(h->sm_count, m_tiles_of(K, false), T2, F, false, kWidthsAll, 4).bn;
   p.w = plan_tiles(h->sm_count, m_tiles_of(K, false), F, T2, true, kWidthsAll, 4);
   p.rowsum_slots = (T2 + p.bn_h - 1) / p.bn_h;
@@ -552,7 +554,7 @@ int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, 
   {  // G4: partial[z][f][atom] = sum_t H^T[t][atom] R^T[t][f]
     const Operand HTmn{w.HTp, (int64_t)K, w.plane_ht, true};
     const Operand RTmn{w.RTp, w.Fp, w.plane_rt, true};
-    EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F, true};
+    EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F, true, h->gemm_streaming != 0};
     if (int st = plane_gemm<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, false, e, nullptr, stream)) return st;
   }
   return 0;
@@ -665,7 +667,7 @@ int gccnmf_gemm_planes(gccnmf_handle* h, const float* A, int a_mn_major, const f
   GCCNMF_LAUNCH(h, tma_split_rows_kernel, (unsigned)((nb + 255) / 256), 256, 0, stream, B, b_rows, b_inner, Bp, b_pitch, (int64_t)b_rows * b_pitch);
   const Operand Ao{Ap, a_pitch, (int64_t)a_rows * a_pitch, a_mn_major != 0};
   const Operand Bo{Bp, b_pitch, (int64_t)b_rows * b_pitch, b_mn_major != 0};
-  EpiStoreT e{DT, (int64_t)M, (int64_t)N * M, M, N, M % 4 == 0 && (reinterpret_cast<uintptr_t>(DT) & 15) == 0};
+  EpiStoreT e{DT, (int64_t)M, (int64_t)N * M, M, N, M % 4 == 0 && (reinterpret_cast<uintptr_t>(DT) & 15) == 0, false};
   if (!a_mn_major && !b_mn_major) return plane_gemm<false, false>(h, tile_n, Ao, Bo, M, N, Kc, splits, true, e, timing, stream);
   if (a_mn_major && !b_mn_major) return plane_gemm<true, false>(h, tile_n, Ao, Bo, M, N, Kc, splits, false, e, timing, stream);
   if (a_mn_major && b_mn_major) return plane_gemm<true, true>(h, tile_n, Ao, Bo, M, N, Kc, splits, false, e, timing, stream);

@@ -242,6 +242,13 @@ struct has_tile_epilogue<E, decltype((void)E::kTileEpilogue)> { static constexpr
 // instead of three products in three MMAs, and the epilogue adds the two accumulator halves (measured: 391 -> 334 cycles per k-step,
 // now at the shared-memory port: 24 KB of operand reads + 16 KB of TMA writes).  With a CTA pair (cta_group::2, M = 256) on top, the
 // N = 2 BN operand is split between the two CTAs by plane, which halves the B bytes each CTA reads and writes.
+// Epilogues with `static constexpr bool kPreloadOperands = true` have their by-column global operands fetched into registers while
+// the main loop runs (opt-in: measured to pay for the ratio epilogue of the W.H contractions, to cost for the H update).
+template <class E, class = void>
+struct wants_preload { static constexpr bool value = false; };
+template <class E>
+struct wants_preload<E, decltype((void)E::kPreloadOperands)> { static constexpr bool value = E::kPreloadOperands; };
+
 template <class E, class = void>
 struct wants_dual_n { static constexpr bool value = false; };
 template <class E>
@@ -336,7 +343,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // critical path: 6.2 k of a 31 k-cycle CTA for the ratio, 12 k of 29 k for the H update).
   constexpr int kWarpsAll = kThreads / 32;
   constexpr int kLoadedWords = (int)((sizeof(typename Epilogue::Loaded) + 3) / 4);
-  constexpr bool kPreloads = !has_tile_epilogue<Epilogue>::value && !std::is_empty<typename Epilogue::Loaded>::value;
+  constexpr bool kPreloads = wants_preload<Epilogue>::value && !has_tile_epilogue<Epilogue>::value && !std::is_empty<typename Epilogue::Loaded>::value;
   constexpr int kPreCap = 64 / (kLoadedWords > 0 ? kLoadedWords : 1);                      // register budget: 64 words per thread
   constexpr int kPre = kPreloads ? ((BN + kWarpsAll - 1) / kWarpsAll < kPreCap ? (BN + kWarpsAll - 1) / kWarpsAll : kPreCap) : 0;
   typename Epilogue::Loaded pre[kPre > 0 ? kPre : 1];

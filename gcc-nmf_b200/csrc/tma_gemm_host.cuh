@@ -240,7 +240,7 @@ struct PlaneGemmInstance {
     args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
     args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
     args.timing = timing;
-    args.preload = (h->gemm_preload >> (Epi::kRowReduce ? 1 : 0)) & 1;     // bit 0: epilogues without a row reduction (the ratio), bit 1: the H update
+    args.preload = h->gemm_preload & 1;     // (only epilogues that opt in with kPreloadOperands have the code)
     // m-fastest (always for a cta_group::2 pair, whose two m tiles must sit next to each other along x): grid (m, n, splits)
     const bool mf = PAIR || g.m_fastest;
     args.m_fastest = mf ? 1 : 0;

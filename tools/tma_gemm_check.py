@@ -192,8 +192,10 @@ def variants():
     W0d, H0d = h.to_device(W0), h.to_device(H0)
     ref = None
     for wh in (128, 112, 104):
-        for pre in (0, 1, 3):
+        for pre in (0, 1):
+          for stream in (0, 1):
             for pair in (-1, 0):
+                h.set_option('gemm_streaming', stream)
                 h.set_option('wh_tile', wh)
                 h.set_option('gemm_preload', pre)
                 h.set_option('gemm_pair', pair)
@@ -209,10 +211,11 @@ def variants():
                 Wn = W.cpu().numpy()
                 if ref is None:
                     ref = Wn
-                print('wh_tile %3d preload %d pair %2d: %s ms per 100 iterations | rel W vs first variant %.2e finite %s' % (
-                    wh, pre, pair, ['%.2f' % m for m in ms], _rel(Wn, ref), bool(np.isfinite(Wn).all())), flush=True)
+                print('wh_tile %3d preload %d streaming %d pair %2d: %s ms per 100 iterations | rel W vs first variant %.2e finite %s' % (
+                    wh, pre, stream, pair, ['%.2f' % m for m in ms], _rel(Wn, ref), bool(np.isfinite(Wn).all())), flush=True)
     h.set_option('wh_tile', 0)
     h.set_option('gemm_preload', 1)
+    h.set_option('gemm_streaming', 0)
     h.set_option('gemm_pair', -1)
     return 0
 
