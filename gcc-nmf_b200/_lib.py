@@ -68,12 +68,10 @@ SIGNATURES = {
     'gccnmf_wiener_apply': (c_int, [_H, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _S]),
     'gccnmf_masked_recon_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'gccnmf_masked_recon_phase': (c_int, [_H, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _S]),
-    'gccnmf_gemm_tn_3xtf32': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _S]),
     'gccnmf_debug_timing': (c_int64, [_H, _P, c_int]),
     'gccnmf_klnmf_tile_plan': (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int)]),
     'gccnmf_gemm_planes_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_gemm_planes': (c_int, [_H, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P, _S]),
-    'gccnmf_gemm_tn_3xtf32_timed': (c_int, [_H, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _S]),
 }
 
 
@@ -424,16 +422,6 @@ class Handle(object):
                                                       _ptr(out), _ptr(ws), ws.numel() if ws is not None else 0, self.stream))
         return out
 
-
-    def gemm_tn_3xtf32(self, A, B, Kc=None, tile_n=128):
-        """D = A[:, :Kc] . B[:, :Kc]^T on the tensor cores (3xTF32).  A (M, lda), B (N, ldb) f32 cuda."""
-        torch = self.torch
-        M, N = A.shape[0], B.shape[0]
-        Kc = A.shape[1] if Kc is None else Kc
-        D = self.empty((M, N), torch.float32)
-        self.check(self.lib.gccnmf_gemm_tn_3xtf32(self.h, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(D), D.stride(0),
-                                                  M, N, Kc, tile_n, self.stream))
-        return D
 
     def gemm_planes(self, A, B, a_mn_major=False, b_mn_major=False, tile_n=128, splits=1, timing=None):
         """(A . B^T)^T on the TMA-fed plane GEMM.  A: (M, Kc) or, MN-major, (Kc, M); B likewise with N.

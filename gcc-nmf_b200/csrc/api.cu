@@ -43,10 +43,6 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   h->last_error = "no error";
   const char* path = getenv("GCCNMF_NMF_PATH");
   h->force_simt_nmf = path && strcmp(path, "simt") == 0;
-  const char* split = getenv("GCCNMF_NMF_SPLIT");
-  h->nmf_split_bf16 = !(split && strcmp(split, "tf32") == 0);   // default: 3xBF16 (same measured parity, 12 % faster)
-  const char* tma = getenv("GCCNMF_NMF_TMA");
-  h->nmf_tma = !(tma && strcmp(tma, "0") == 0);
   const char* pdl = getenv("GCCNMF_NMF_PDL");
   h->nmf_pdl = !(pdl && strcmp(pdl, "0") == 0);
   *out = h;
@@ -83,8 +79,6 @@ int64_t gccnmf_launch_count(const gccnmf_handle* h) { return h ? h->launches : 0
 int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
   if (!h || !name) return GCCNMF_ERR_INVALID_ARGUMENT;
   if (strcmp(name, "force_simt_nmf") == 0) { h->force_simt_nmf = value != 0; return GCCNMF_OK; }
-  if (strcmp(name, "nmf_split_bf16") == 0) { h->nmf_split_bf16 = value != 0; return GCCNMF_OK; }
-  if (strcmp(name, "nmf_tma") == 0) { h->nmf_tma = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "nmf_pdl") == 0) { h->nmf_pdl = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "wh_tile") == 0) { h->wh_tile = value; return GCCNMF_OK; }
   if (strcmp(name, "argmax_refine_shared") == 0) { h->argmax_refine_shared = value != 0; return GCCNMF_OK; }

@@ -13,9 +13,7 @@ struct gccnmf_handle {
   int device = 0;
   int sm_count = 148;
   int64_t launches = 0;
-  bool nmf_split_bf16 = true;    // KL-NMF contractions: 0 = 3xTF32 (hi/lo tf32), 1 = 3xBF16 (hi/lo bf16)
-  bool force_simt_nmf = false;   // GCCNMF_NMF_PATH=simt: float32 SIMT contractions instead of tcgen05 3xTF32
-  bool nmf_tma = true;           // KL-NMF contractions on the TMA-fed plane GEMM (klnmf_tma.cu); 0 = loader-based kernel (klnmf_tc.cu)
+  bool force_simt_nmf = false;   // GCCNMF_NMF_PATH=simt: float32 SIMT contractions instead of the tcgen05 plane GEMM
   bool nmf_pdl = true;           // programmatic dependent launch between the kernels of a KL-NMF iteration
   int wh_tile = 0;               // diagnostics: tile width of the W.H contractions (0 = planned)
   bool argmax_refine_shared = true;   // exact float64 refinement of near-tie argmax decisions: E staged in shared memory (0 = one warp per pair from L2)

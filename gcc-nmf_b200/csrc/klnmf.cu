@@ -121,8 +121,7 @@ apply_w_kernel(float* W, const float* numer, const float* rowsumH, int F, int K,
   __shared__ float norm_s[kApplyCols];
   const int c = threadIdx.x % kApplyCols, g = threadIdx.x / kApplyCols;
   const int k = blockIdx.x * kApplyCols + c;
-  // rows f = g, g + 32, ... (the same partition and reduction order as tc_apply_w_kernel: a rank on the SIMT
-  // path and a rank on the tensor-core path produce bit-identical W from the same all-reduced numerator)
+  // rows f = g, g + 32, ... (one column per thread, 32 row groups per CTA)
   float sumsq = 0.f;
   if (k < K) {
     const float rs = rowsumH[k];
@@ -230,22 +229,7 @@ int apply_W_impl(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, con
 
 }  // namespace
 
-// tensor-core path (klnmf_tc.cu)
-bool gccnmf_klnmf_tc_supported(int F, int T2, int K);
-size_t gccnmf_klnmf_tc_workspace_bytes(int F, int T2, int K);
-int gccnmf_klnmf_tc_prepare(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
-                            size_t workspace_bytes, bool need_vt, bool need_wt, bool need_ht, void* stream);
-int gccnmf_klnmf_tc_update_H(gccnmf_handle* h, const float* V, int F, int T2, const float* W, float* H, int K, float alpha, float eps,
-                             void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream);
-int gccnmf_klnmf_tc_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
-                              size_t workspace_bytes, bool have_rowsum, void* stream);
-int gccnmf_klnmf_tc_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
-                            void* workspace, size_t workspace_bytes, void* stream);
-int gccnmf_klnmf_tc_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
-                           size_t workspace_bytes, void* stream);
-int gccnmf_klnmf_tc_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream);
-
-// TMA-fed plane GEMM path (klnmf_tma.cu): same protocol
+// tensor-core path: TMA-fed plane GEMM (klnmf_tma.cu)
 bool gccnmf_klnmf_tma_supported(int F, int T2, int K);
 size_t gccnmf_klnmf_tma_workspace_bytes(int F, int T2, int K);
 int gccnmf_klnmf_tma_prepare(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
@@ -267,25 +251,8 @@ int gccnmf_klnmf_tma_pack_numer_mc(gccnmf_handle* h, int F, int T2, int K, float
 int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
                                 const unsigned* arrival_counter, unsigned arrivals_expected, void* workspace, size_t workspace_bytes, void* stream);
 
-static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tc_supported(F, T2, K); }
-// The TMA path is the 3xBF16 split over pre-split planes; the 3xTF32 option and shapes it does not cover use the loader-based kernel.
-static bool use_tma(const gccnmf_handle* h, int F, int T2, int K) {
-  return use_tc(h, F, T2, K) && h->nmf_tma && h->nmf_split_bf16 && gccnmf_klnmf_tma_supported(F, T2, K);
-}
-// The two tensor-core implementations expose the same protocol; every call site below goes through this table.
-struct TensorCoreOps {
-  decltype(&gccnmf_klnmf_tc_prepare) prepare;
-  decltype(&gccnmf_klnmf_tc_update_H) update_H;
-  decltype(&gccnmf_klnmf_tc_partial_W) partial_W;
-  decltype(&gccnmf_klnmf_tc_apply_W) apply_W;
-  decltype(&gccnmf_klnmf_tc_finish) finish;
-  decltype(&gccnmf_klnmf_tc_pack_numer) pack_numer;
-};
-static const TensorCoreOps kLoaderOps = {gccnmf_klnmf_tc_prepare, gccnmf_klnmf_tc_update_H, gccnmf_klnmf_tc_partial_W,
-                                         gccnmf_klnmf_tc_apply_W, gccnmf_klnmf_tc_finish, gccnmf_klnmf_tc_pack_numer};
-static const TensorCoreOps kTmaOps = {gccnmf_klnmf_tma_prepare, gccnmf_klnmf_tma_update_H, gccnmf_klnmf_tma_partial_W,
-                                      gccnmf_klnmf_tma_apply_W, gccnmf_klnmf_tma_finish, gccnmf_klnmf_tma_pack_numer};
-static const TensorCoreOps& tc_ops(const gccnmf_handle* h, int F, int T2, int K) { return use_tma(h, F, T2, K) ? kTmaOps : kLoaderOps; }
+// Shapes the plane GEMM does not cover (K % 8 != 0, tiny problems) and the force_simt_nmf option run the float32 SIMT kernels above.
+static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tma_supported(F, T2, K); }
 
 extern "C" {
 
@@ -301,7 +268,6 @@ size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K) {
   add(K);
   add(K);
   n = align_up(n, 256);
-  if (gccnmf_klnmf_tc_supported(F, T2, K)) n = std::max(n, gccnmf_klnmf_tc_workspace_bytes(F, T2, K));
   if (gccnmf_klnmf_tma_supported(F, T2, K)) n = std::max(n, gccnmf_klnmf_tma_workspace_bytes(F, T2, K));
   return n;
 }
@@ -312,7 +278,7 @@ int gccnmf_klnmf_begin(gccnmf_handle* h, const float* V, int F, int T2, const fl
   if (int st = check_dims(h, F, T2, K)) return st;
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  if (use_tc(h, F, T2, K)) return tc_ops(h, F, T2, K).prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream);
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tma_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream);
   return GCCNMF_OK;
 }
 
@@ -325,10 +291,10 @@ int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, int T2, con
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (use_tc(h, F, T2, K)) {
-    if (int st = tc_ops(h, F, T2, K).update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0,
+    if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0,
                                           iteration > 0, stream)) return st;
-    if (int st = tc_ops(h, F, T2, K).partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
-    return tc_ops(h, F, T2, K).pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
+    if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+    return gccnmf_klnmf_tma_pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   if (int st = update_H_impl(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, w, false, stream)) return st;
@@ -342,7 +308,7 @@ int gccnmf_klnmf_step_apply(gccnmf_handle* h, int F, int T2, float* W, float* H,
   GCCNMF_REQUIRE(h, numer != nullptr, "klnmf_step_apply: NULL numerator");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  if (use_tc(h, F, T2, K)) return tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, numer, false, workspace, workspace_bytes, stream);
+  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tma_apply_W(h, F, T2, W, K, numer, false, workspace, workspace_bytes, stream);
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
   return apply_W_impl(h, F, T2, W, H, K, numer, w, stream);
 }
@@ -356,7 +322,7 @@ int gccnmf_klnmf_step_apply_multimem(gccnmf_handle* h, int F, int T2, float* W, 
   if (!use_tc(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_apply_multimem: only the tensor-core path reads the numerator through multimem");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  return tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, numer_multicast, true, workspace, workspace_bytes, stream);
+  return gccnmf_klnmf_tma_apply_W(h, F, T2, W, K, numer_multicast, true, workspace, workspace_bytes, stream);
 }
 
 // One KL-NMF iteration of a frame-sharded run with the cross-rank sum of the W-update numerator formed INSIDE the NVSwitch and no
@@ -370,7 +336,7 @@ int gccnmf_klnmf_step_multimem(gccnmf_handle* h, const float* V, int F, int T2, 
   GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   GCCNMF_REQUIRE(h, numer_local && numer_multicast && counter_local && counter_multicast && iteration >= 0, "klnmf_step_multimem: bad arguments");
-  if (!use_tma(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_multimem: shape not covered by the TMA tensor-core path");
+  if (!use_tc(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_multimem: shape not covered by the tensor-core path");
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0,
@@ -385,8 +351,8 @@ int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
   GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   if (use_tc(h, F, T2, K)) {
-    if (int st = tc_ops(h, F, T2, K).finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream)) return st;
-    if (use_tma(h, F, T2, K) && iterations_done > 0) return gccnmf_klnmf_tma_finish_W(h, F, T2, W, K, workspace, workspace_bytes, stream);
+    if (int st = gccnmf_klnmf_tma_finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream)) return st;
+    if (iterations_done > 0) return gccnmf_klnmf_tma_finish_W(h, F, T2, W, K, workspace, workspace_bytes, stream);
   }
   return GCCNMF_OK;
 }
@@ -400,18 +366,18 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (iterations == 0) return GCCNMF_OK;
   if (use_tc(h, F, T2, K)) {
-    if (int st = tc_ops(h, F, T2, K).prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
+    if (int st = gccnmf_klnmf_tma_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
     for (int it = 0; it < iterations; ++it) {
       // colsum(W) comes out of the previous W update; with a fixed dictionary it is computed once
       // and the H *= norms of :81 stays pending: the next iteration's G1 loader and G2 epilogue apply it
-      if (int st = tc_ops(h, F, T2, K).update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes,
+      if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes,
                                             it == 0 ? 0 : (update_W ? 2 : 1), update_W && it > 0, stream)) return st;
       if (!update_W) continue;
-      if (int st = tc_ops(h, F, T2, K).partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
-      if (int st = tc_ops(h, F, T2, K).apply_W(h, F, T2, W, K, nullptr, false, workspace, workspace_bytes, stream)) return st;
+      if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+      if (int st = gccnmf_klnmf_tma_apply_W(h, F, T2, W, K, nullptr, false, workspace, workspace_bytes, stream)) return st;
     }
-    if (int st = tc_ops(h, F, T2, K).finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream)) return st;
-    if (use_tma(h, F, T2, K) && update_W) return gccnmf_klnmf_tma_finish_W(h, F, T2, W, K, workspace, workspace_bytes, stream);
+    if (int st = gccnmf_klnmf_tma_finish(h, F, T2, H, K, update_W != 0, workspace, workspace_bytes, stream)) return st;
+    if (update_W) return gccnmf_klnmf_tma_finish_W(h, F, T2, W, K, workspace, workspace_bytes, stream);
     return GCCNMF_OK;
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);

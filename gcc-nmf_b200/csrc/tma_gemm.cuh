@@ -6,9 +6,12 @@
 // (the KL-NMF epilogues / the W update), in ONE orientation; the contraction picks the matching shared-memory layout:
 //   K-major  : element (r, k) at rows r, k contiguous        TMA boxes {KB, rows / cluster extent, 1 plane}, SWIZZLE_64B rows
 //   MN-major : element (r, k) at rows k, r contiguous        TMA boxes {64, KB, 2 planes} = 64-wide atoms, SWIZZLE_128B
-// so no matrix is ever transposed or re-split inside the loop (the loader-based kernel in umma_gemm.cuh converted
-// float32 operands on the fly: 32 KB of L2->SM traffic and 32 KB of shared-memory stores per k-block per CTA, its limiter).
-// Three tcgen05.mma.kind::f16 products per 16-deep k-step (lo.hi + hi.lo + hi.hi) accumulate in float32 TMEM.
+// so no matrix is ever transposed or re-split inside the loop (round 1's kernel converted float32 operands on the fly:
+// 32 KB of L2->SM traffic and 32 KB of shared-memory stores per k-block per CTA, its limiter).
+// Per 16-deep k-step the products lo.hi + hi.lo + hi.hi accumulate in float32 TMEM: three tcgen05.mma.kind::f16 of width BN,
+// or -- dual-N loop, K-major B with 2 BN <= 256 -- two of width 2 BN against the adjacent [B_hi; B_lo] planes of the stage,
+// which also yields lo.lo; the epilogue adds the two accumulator halves.  (Measured: an M = 128 MMA costs ~128 cycles for
+// any N <= 208 and ~168 at N = 224 / 256, so two wide MMAs beat three narrow ones.)
 //
 // CTA = one 128 x BN accumulator tile, 10 warps:
 //   warp 0     lane 0 is the TMA producer: waits empty[s], arms full[s] with the stage's byte count, issues the boxes
@@ -17,8 +20,9 @@
 // Rows past the last full 128-row tile (F = 513 = 4 x 128 + 1) are computed in float32 SIMT by the epilogue warps while
 // they wait for the accumulator.  A cluster of CN x CM CTAs (n tiles x m tiles) shares operand tiles: each CTA loads 1 / CN
 // of its A tile and 1 / CM of its B tile and TMA-multicasts the slice to the CTAs of its cluster row / column.  Measured
-// (DESIGN.md 4.1): that pays for the 128 x 208 tiles of the H update (1 x 2), not for the 128 x 128 tiles, whose loop sits at
-// the shared-memory port.  PAIR: compile-time cta_group::2 mode (256-row MMAs), not yet validated on hardware.
+// (DESIGN.md 4.1): that pays for the 128 x 208 tiles of the H update (1 x 2), not for the 128 x 128 tiles.
+// PAIR: compile-time cta_group::2 mode (256-row MMAs over a CTA pair, B split between the two CTAs); validated on hardware,
+// bit-identical to the single-CTA kernel, and measured no faster (the MMA rate, not operand staging, bounds the loop).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -27,7 +31,7 @@
 #include <cstdint>
 #include <type_traits>
 
-#include "umma_gemm.cuh"
+#include "umma_ptx.cuh"
 
 namespace tgemm {
 

@@ -59,14 +59,16 @@ GCCNMF_API const char* gccnmf_status_string(int status);
 GCCNMF_API int64_t gccnmf_launch_count(const gccnmf_handle* h);
 /* Options (A/B switches between sm_100a code paths of this library; all ranks of a sharded run must use the same ones so
  * that W stays bit-identical).  Defaults in brackets.
- *   "force_simt_nmf" [0]        KL-NMF contractions on the float32 SIMT kernels even where the tcgen05 paths apply
- *   "nmf_tma" [1]               KL-NMF on the TMA-fed plane GEMM (bf16 hi/lo operand planes); 0 = loader-based tcgen05 kernel
- *   "nmf_split_bf16" [1]        3xBF16 operand split; 0 = 3xTF32 (loader-based kernel only)
+ *   "force_simt_nmf" [0]        KL-NMF contractions on the float32 SIMT kernels even where the tcgen05 plane GEMM applies
  *   "nmf_pdl" [1]               programmatic dependent launch between the kernels of a KL-NMF iteration
  *   "gemm_cluster" [-1]         plane GEMM cluster shape 10 CN + CM (11, 12, 21, 22) instead of the automatic choice
  *   "argmax_refine_shared" [1]  float64 refinement of near-tie argmax decisions with E staged in shared memory
- *   "wh_tile" [0]               tile width of the W.H contractions (128 / 256) instead of the planned one
- *   "gemm_pair" [0]             EXPERIMENTAL (not validated on hardware): plane GEMM on cta_group::2 CTA pairs */
+ *   "argmax_persistent" [1]     all-TDOA argmax GEMM as one persistent CTA per SM (double-buffered TMEM); 0 = one CTA per tile
+ *   "wh_tile" [0]               tile width of the W.H contractions (104 / 112 / 128 / 256) instead of the planned one
+ *   "gemm_pair" [-1]            plane GEMM on cta_group::2 CTA pairs: -1 where a call site prefers it, 0 never, 1 wherever possible
+ *                               (bit-identical results either way; measured no faster)
+ *   "gemm_preload" [1]          bit 0: the W.H ratio epilogue fetches V during the main loop
+ *   "gemm_streaming" [0]        st.global.cs / ld.global.cs for the k-split partials of the W-update numerator */
 GCCNMF_API int gccnmf_set_option(gccnmf_handle* h, const char* name, int value);
 
 /* ---- a1: STFT  (gccNMF/librosaSTFT.py:20-181 via gccNMFFunctions.py:61-67) ------------------ */
@@ -238,22 +240,6 @@ GCCNMF_API size_t gccnmf_masked_recon_workspace_bytes(int S, int F, int T, int K
 GCCNMF_API int gccnmf_masked_recon_phase(gccnmf_handle* h, const float* masks, const float* X, const float* W,
                               const float* H, int S, int F, int T, int K, float* out, void* workspace,
                               size_t workspace_bytes, void* stream);
-
-/* ---- tensor-core building block of a2 (the four contractions of gccNMFFunctions.py:76-77) ------ */
-/*
- * D (M, N) row-major (ldd) = A (M, Kc; lda) . B (N, Kc; ldb)^T, float32 in / float32 out, computed with
- * 3-pass error-compensated TF32 on tcgen05 (hi.hi + hi.lo + lo.hi, float32 TMEM accumulator): the accuracy
- * class of the reference's float32 numpy.dot, which plain TF32 is not.
- * lda, ldb: multiples of 4 floats, rows 16-byte aligned, zero padding in [Kc, round_up(Kc, 4)).
- * tile_n selects the 128 x 128 or 128 x 256 CTA tile.
- */
-GCCNMF_API int gccnmf_gemm_tn_3xtf32(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb,
-                          float* D, int64_t ldd, int M, int N, int Kc, int tile_n, void* stream);
-/* Diagnostics: the same product; `timing` (device uint64[6 x CTAs] or NULL) receives per-CTA clock64 stamps:
- * kernel start, first stage full, last MMA issued, loaders finished, accumulator complete, epilogue end. */
-GCCNMF_API int gccnmf_gemm_tn_3xtf32_timed(gccnmf_handle* h, const float* A, int64_t lda, const float* B, int64_t ldb,
-                                float* D, int64_t ldd, int M, int N, int Kc, int tile_n,
-                                unsigned long long* timing, void* stream);
 
 /* The numInferenceIterations > 0 branch of the notebooks' frame loop (onlineSpeechEnhancement.ipynb:433-440): with
  * H (K, 2T) f32 the inferred coefficients (channel c in columns [c T, (c + 1) T)),

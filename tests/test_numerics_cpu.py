@@ -60,9 +60,9 @@ def test_workspace_sizes_cover_the_buffers():
     lib = _lib.load_library()
     F, T2, K = 513, 3744, 1024
     ws = lib.gccnmf_klnmf_workspace_bytes(F, T2, K)
-    # H^T float32 + planes, V^T, R^T planes, W planes x 2, 8 k-split slabs: DESIGN.md section 3
-    need = T2 * K * 4 + 2 * T2 * K * 2 + T2 * 520 * 4 + 2 * T2 * 520 * 2 + 2 * (2 * F * K * 2) + 8 * F * K * 4
-    assert need <= ws <= need * 1.2
+    # H^T float32 + planes, V^T, R^T planes, W planes, 8 k-split slabs: DESIGN.md section 3
+    need = T2 * K * 4 + 2 * T2 * K * 2 + T2 * 520 * 4 + 2 * T2 * 520 * 2 + 2 * F * K * 2 + 8 * F * K * 4
+    assert need <= ws <= need * 1.05
     assert lib.gccnmf_klnmf_workspace_bytes(F, 2 * T2, K) > ws
     assert lib.gccnmf_gemm_planes_workspace_bytes(513, 3744, 1024) >= 2 * 2 * (513 + 3744) * 1024
     assert lib.gccnmf_klnmf_workspace_bytes(0, 10, 10) == 0

@@ -1,8 +1,8 @@
 """GPU diagnostics for the TMA-fed plane GEMM (gcc-nmf_b200/csrc/tma_gemm.cuh) and the KL-NMF path built on it.
 
   python tools/tma_gemm_check.py gemm      every operand-layout combination against a float64 product
-  python tools/tma_gemm_check.py nmf       KL-NMF, TMA path vs oracle and vs the loader-based path (small + config 2)
-  python tools/tma_gemm_check.py time      KL-NMF stage time at config 2: loader path, TMA path, TMA + PDL
+  python tools/tma_gemm_check.py nmf       KL-NMF, TMA path vs oracle and vs the float32 SIMT path (small + config 2)
+  python tools/tma_gemm_check.py time      KL-NMF stage time at config 2: float32 SIMT path, TMA path, TMA + PDL
   python tools/tma_gemm_check.py all       each of the above in its own process (a trap in one does not hide the others)
 """
 import os
@@ -84,8 +84,8 @@ def nmf():
         t0 = time.time()
         Wo, Ho = orc.performKLNMF(V, K, iters, 0, W0=W0, H0=H0)
         res = {}
-        for name, tma in (('loader', 0), ('tma', 1)):
-            h.set_option('nmf_tma', tma)
+        for name, tma in (('simt', 0), ('tma', 1)):
+            h.set_option('force_simt_nmf', 1 - tma)
             W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
             h.klnmf(h.to_device(V), W, H, iters)
             torch.cuda.synchronize()
@@ -96,14 +96,14 @@ def nmf():
             print('KL-NMF %s F=%d T2=%d K=%d %d it: rel W %.2e rel H %.2e %s (oracle %.1fs)' % (name, F, T2, K, iters, eW, eH, 'ok' if ok else 'BAD', time.time() - t0), flush=True)
         # 1 iteration: tight comparison of the two paths
         out = {}
-        for name, tma in (('loader', 0), ('tma', 1)):
-            h.set_option('nmf_tma', tma)
+        for name, tma in (('simt', 0), ('tma', 1)):
+            h.set_option('force_simt_nmf', 1 - tma)
             W, H = h.to_device(W0.copy()), h.to_device(H0.copy())
             h.klnmf(h.to_device(V), W, H, 1)
             out[name] = (W.cpu().numpy(), H.cpu().numpy())
-        print('  1 iteration tma vs loader: rel W %.2e rel H %.2e' % (_rel(out['tma'][0], out['loader'][0]), _rel(out['tma'][1], out['loader'][1])))
+        print('  1 iteration tma vs simt: rel W %.2e rel H %.2e' % (_rel(out['tma'][0], out['simt'][0]), _rel(out['tma'][1], out['simt'][1])))
         # fixed dictionary
-        h.set_option('nmf_tma', 1)
+        h.set_option('force_simt_nmf', 0)
         Hi = h.to_device(H0.copy())
         h.klnmf(h.to_device(V), h.to_device(Wo), Hi, 5, update_W=False)
         Href = H0.copy()
@@ -125,12 +125,12 @@ def timing():
     V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
     W0, H0 = orc.initKLNMF(F, T2, K)
     W0d, H0d = h.to_device(W0), h.to_device(H0)
-    variants = (('loader', 0, 0, -1), ('tma no pdl, auto clusters', 1, 0, -1), ('tma+pdl, no clusters', 1, 1, 11), ('tma+pdl, clusters 1x2', 1, 1, 12),
+    variants = (('float32 simt', 0, 0, -1), ('tma no pdl, auto clusters', 1, 0, -1), ('tma+pdl, no clusters', 1, 1, 11), ('tma+pdl, clusters 1x2', 1, 1, 12),
                 ('tma+pdl, clusters 2x1', 1, 1, 21), ('tma+pdl, clusters 2x2', 1, 1, 22), ('tma+pdl, auto clusters', 1, 1, -1))
     if os.environ.get('TIME_VARIANTS') == 'short':
         variants = (('tma+pdl, auto clusters', 1, 1, -1),)
     for name, tma, pdl, cl in variants:
-        h.set_option('nmf_tma', tma)
+        h.set_option('force_simt_nmf', 1 - tma)
         h.set_option('nmf_pdl', pdl)
         h.set_option('gemm_cluster', cl)
         t_cpu = 0.0
@@ -230,7 +230,7 @@ def stamps():
     rng = np.random.default_rng(5)
     V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
     W0, H0 = orc.initKLNMF(F, T2, K)
-    h.set_option('nmf_tma', 1)
+    h.set_option('force_simt_nmf', 0)
     WH = int(os.environ.get('WH_TILE', '128'))
     h.set_option('wh_tile', WH)
     h.set_option('gemm_cluster', int(os.environ.get('GEMM_CLUSTER', '-1')))
@@ -284,7 +284,7 @@ def prof():
     rng = np.random.default_rng(5)
     V = h.to_device((rng.random((F, T2)) ** 3 + 1e-3).astype(np.float32))
     W0, H0 = orc.initKLNMF(F, T2, K)
-    h.set_option('nmf_tma', 1)
+    h.set_option('force_simt_nmf', 0)
     h.set_option('nmf_pdl', int(os.environ.get('PROF_PDL', '0')))
     W, H = h.to_device(W0), h.to_device(H0)
     h.klnmf(V, W, H, int(os.environ.get('PROF_ITERS', '6')))
