@@ -53,6 +53,8 @@ SIGNATURES = {
     'gccnmf_klnmf_step_apply': (c_int, [_H, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
     'gccnmf_klnmf_step_apply_multimem': (c_int, [_H, c_int, c_int, _P, _P, c_int, _P, _P, c_size_t, _S]),
     'gccnmf_klnmf_step_multimem': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, c_int, _P, _P, _P, _P, ctypes.c_uint32, _P, c_size_t, _S]),
+    'gccnmf_klnmf_step_multimem2': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P,
+                                            ctypes.c_uint32, _P, c_size_t, _S]),
     'gccnmf_klnmf_end': (c_int, [_H, c_int, c_int, _P, _P, c_int, c_int, _P, c_size_t, _S]),
     'gccnmf_phat_angspec_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gccnmf_phat_angspec': (c_int, [_H, _P, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_size_t, _S]),
@@ -310,6 +312,19 @@ class Handle(object):
         self.check(self.lib.gccnmf_klnmf_step_multimem(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, float(sparsity_alpha), float(epsilon),
                                                        int(iteration), int(numer_local_ptr), int(numer_multicast_ptr), int(counter_local_ptr),
                                                        int(counter_multicast_ptr), int(arrivals_expected) & 0xFFFFFFFF, _ptr(ws), ws.numel(), self.stream))
+
+    def klnmf_step_multimem2(self, V, W, H, iteration, rank, world, numer_local_ptr, numer_multicast_ptr, reduced_local_ptr,
+                             reduced_multicast_ptr, counters_local_ptr, counters_multicast_ptr, arrivals_expected, sparsity_alpha=0.0,
+                             epsilon=1e-16):
+        """One sharded iteration with the two-shot in-switch exchange (see gccnmf_klnmf_step_multimem2); pointers are ints."""
+        F, T2 = V.shape
+        K = W.shape[1]
+        ws = self._klnmf_ws(F, T2, K)
+        self.check(self.lib.gccnmf_klnmf_step_multimem2(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, float(sparsity_alpha), float(epsilon),
+                                                        int(iteration), int(rank), int(world), int(numer_local_ptr), int(numer_multicast_ptr),
+                                                        int(reduced_local_ptr), int(reduced_multicast_ptr), int(counters_local_ptr),
+                                                        int(counters_multicast_ptr), int(arrivals_expected) & 0xFFFFFFFF, _ptr(ws), ws.numel(),
+                                                        self.stream))
 
     def klnmf_end(self, W, H, iterations_done):
         F, K = W.shape

@@ -45,6 +45,8 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   h->force_simt_nmf = path && strcmp(path, "simt") == 0;
   const char* pdl = getenv("GCCNMF_NMF_PDL");
   h->nmf_pdl = !(pdl && strcmp(pdl, "0") == 0);
+  const char* pers = getenv("GCCNMF_ARGMAX_PERSISTENT");
+  if (pers) h->argmax_persistent = strcmp(pers, "0") != 0;
   *out = h;
   return GCCNMF_OK;
 }

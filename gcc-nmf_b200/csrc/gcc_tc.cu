@@ -268,18 +268,20 @@ argmax_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const _
             else if (x > second) second = x;
           }
         }
-        if (m < K) {
-          const int t = n0 / D + fr;
-          epi.argmax[(int64_t)m * epi.T + t] = idx;
-          const float margin = epi.margin_factor * epi.colsumW[m];
-          if (nan || !(best - second > margin)) {
-            uint32_t bits[4] = {0u, 0u, 0u, 0u};
-            for (int c = 0; c < D; c += 32) {              // second pass over the accumulator row: the candidates within the margin
-              umma::tmem_ld_32x32(taddr + (uint32_t)(fr * D + c), v);
+        const int t = n0 / D + fr;
+        const float margin = m < K ? epi.margin_factor * epi.colsumW[m] : 0.f;
+        const bool near_tie = m < K && (nan || !(best - second > margin));
+        if (m < K) epi.argmax[(int64_t)m * epi.T + t] = idx;
+        // tcgen05.ld is .sync.aligned: the second pass over the accumulator rows is taken by the whole warp or not at all
+        if (__any_sync(0xffffffffu, near_tie)) {
+          uint32_t bits[4] = {0u, 0u, 0u, 0u};
+          for (int c = 0; c < D; c += 32) {                // the candidates within the margin
+            umma::tmem_ld_32x32(taddr + (uint32_t)(fr * D + c), v);
 #pragma unroll
-              for (int q = 0; q < 32; ++q)
-                if (nan || !(best - v[q] > margin)) bits[c >> 5] |= 1u << q;
-            }
+            for (int q = 0; q < 32; ++q)
+              if (nan || !(best - v[q] > margin)) bits[c >> 5] |= 1u << q;
+          }
+          if (near_tie) {
             const int slot = atomicAdd(epi.count, 1);
             if (slot < epi.capacity) {
               epi.list[slot] = make_int2(m, t);

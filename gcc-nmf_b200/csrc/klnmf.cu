@@ -252,6 +252,10 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
                                 const unsigned* arrival_counter, unsigned arrivals_expected, void* workspace, size_t workspace_bytes, void* stream);
 
 // Shapes the plane GEMM does not cover (K % 8 != 0, tiny problems) and the force_simt_nmf option run the float32 SIMT kernels above.
+int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const float* numer_multicast, float* reduced_multicast, int rank, int world,
+                                  const unsigned* arrivals_in, unsigned arrivals_expected, unsigned* arrivals_out_mc, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tma_supported(F, T2, K); }
 
 extern "C" {
@@ -344,6 +348,30 @@ int gccnmf_klnmf_step_multimem(gccnmf_handle* h, const float* V, int F, int T2, 
   if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
   if (int st = gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer_local, counter_multicast, workspace, workspace_bytes, stream)) return st;
   return gccnmf_klnmf_tma_apply_W_mc(h, F, T2, W, K, numer_multicast, true, counter_local, arrivals_expected, workspace, workspace_bytes, stream);
+}
+
+// The same iteration with a TWO-SHOT exchange (reduce-scatter + all-gather inside the switch): after the pack every rank sums only its
+// 1 / world slice of the numerator with multimem.ld_reduce and multicasts the result into the `reduced` buffer of every rank
+// (multimem.st); the W update then reads plain local memory once the second arrival counter is complete.  Link traffic per GPU and
+// iteration is one numerator in each direction for any world size.  counters_*: two uint32 (pack arrivals, slice arrivals).
+int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float sparsity_alpha, float epsilon,
+                                int iteration, int rank, int world, float* numer_local, const float* numer_multicast, const float* reduced_local,
+                                float* reduced_multicast, const uint32_t* counters_local, uint32_t* counters_multicast, uint32_t arrivals_expected,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  GCCNMF_ENTER(h);
+  if (int st = check_dims(h, F, T2, K)) return st;
+  GCCNMF_REQUIRE(h, numer_local && numer_multicast && reduced_local && reduced_multicast && counters_local && counters_multicast && iteration >= 0 &&
+                        world >= 1 && rank >= 0 && rank < world, "klnmf_step_multimem2: bad arguments");
+  if (!use_tc(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_multimem2: shape not covered by the tensor-core path");
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0,
+                                         stream)) return st;
+  if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+  if (int st = gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer_local, counters_multicast, workspace, workspace_bytes, stream)) return st;
+  if (int st = gccnmf_klnmf_tma_reduce_bcast(h, F, T2, K, numer_multicast, reduced_multicast, rank, world, counters_local, arrivals_expected,
+                                             counters_multicast + 1, workspace, workspace_bytes, stream)) return st;
+  return gccnmf_klnmf_tma_apply_W_mc(h, F, T2, W, K, reduced_local, false, counters_local + 1, arrivals_expected, workspace, workspace_bytes, stream);
 }
 
 int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,

@@ -238,14 +238,14 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
   const int c = threadIdx.x, g = threadIdx.y;          // c: lane (4 atoms), g: row group 0..7
-  if (MULTIMEM && arrival_counter) {
-    // every rank's partial numerator is in its symmetric buffer once my copy of the counter has received all arrivals
+  if (arrival_counter) {
+    // every rank's contribution is in place once my copy of the counter has received all arrivals
     if (c == 0 && g == 0) {
       unsigned seen;
       unsigned long long spins = 0;
       do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrival_counter) : "memory");
-        if (++spins > (1ull << 31)) __trap();   // a lost peer must not hang the box
+        if (++spins > (1ull << 25)) __trap();   // a lost peer must not hang the box
       } while ((int)(seen - arrivals_expected) < 0);
     }
     __syncthreads();
@@ -261,7 +261,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
   if (active) {
     if (!MULTIMEM)
       for (int s = g; s < rowsum_slots; s += 8) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(rowsum + (int64_t)s * K + k));
+        const float4 v = arrival_counter ? __ldcg(reinterpret_cast<const float4*>(rowsum + (int64_t)s * K + k)) : __ldg(reinterpret_cast<const float4*>(rowsum + (int64_t)s * K + k));
         rs_part.x += v.x; rs_part.y += v.y; rs_part.z += v.z; rs_part.w += v.w;
       }
 #pragma unroll
@@ -276,7 +276,9 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
         } else {
 #pragma unroll
           for (int z = 0; z < kMaxSplits; ++z)
-            p[r][z] = z < splits ? __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            p[r][z] = z < splits ? (arrival_counter ? __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i))      // written by peers: not through L1
+                                                   : __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
@@ -390,6 +392,42 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
         __threadfence_system();
         asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
       }
+    }
+  }
+}
+
+// Two-shot all-reduce of the packed numerator inside the NVSwitch (frame-sharded runs, gccnmf_klnmf_step_multimem2): rank r owns the
+// r-th slice of the (F*K + K) floats; once every rank's pack has arrived it reads the cross-rank SUM of its slice with
+// multimem.ld_reduce and writes it to EVERY rank's `reduced` buffer with multimem.st, then counts itself in on the second arrival
+// counter.  Per GPU and iteration the links carry one numerator out and one in, whatever the world size (the one-shot form, every rank
+// pulling the whole sum, makes each GPU serve `world` numerators: 16.8 MB per iteration at 8 ranks).
+__global__ void tma_reduce_bcast_kernel(const float* numer_mc, float* reduced_mc, int64_t n4, int rank, int world, const unsigned* arrivals_in,
+                                        unsigned arrivals_expected, unsigned* done_counter, unsigned* arrivals_out_mc) {
+  tgemm::pdl_launch_dependents();
+  tgemm::pdl_wait_prior_grids();
+  if (threadIdx.x == 0) {
+    unsigned seen;
+    unsigned long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrivals_in) : "memory");
+      if (++spins > (1ull << 25)) __trap();     // a lost peer must not hang the box
+    } while ((int)(seen - arrivals_expected) < 0);
+  }
+  __syncthreads();
+  const int64_t chunk = (n4 + world - 1) / world, begin = rank * chunk, end = begin + chunk < n4 ? begin + chunk : n4;
+  for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = multimem_sum_f32x4(numer_mc + 4 * i);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reduced_mc + 4 * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *done_counter = 0;
+      __threadfence_system();
+      asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(arrivals_out_mc), "r"(1u) : "memory");
     }
   }
 }
@@ -573,7 +611,18 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
     return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial, 1,
                      rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected);
   return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<false>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial,
-                   numer ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part, w.colsum, (const unsigned*)nullptr, 0u);
+                   numer ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected);
+}
+
+int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const float* numer_multicast, float* reduced_multicast, int rank, int world,
+                                  const unsigned* arrivals_in, unsigned arrivals_expected, unsigned* arrivals_out_mc, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  const int64_t n4 = ((int64_t)F * K + K) / 4;                       // K % 8 == 0 on this path
+  const int64_t chunk = (n4 + world - 1) / world;
+  const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (chunk + 255) / 256));
+  return launch_ex(h, "tma_reduce_bcast_kernel", tma_reduce_bcast_kernel, dim3(ctas), dim3(256), 0, stream, h->nmf_pdl, dim3(1, 1, 1), numer_multicast,
+                   reduced_multicast, n4, rank, world, arrivals_in, arrivals_expected, w.done + 1, arrivals_out_mc);
 }
 
 int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,

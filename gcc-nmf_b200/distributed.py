@@ -137,12 +137,54 @@ class MultimemNumerator(object):
         return local, mc, local + off, mc + off, self.world * self.uses[p]
 
 
+class MultimemTwoShot(object):
+    """One symmetric allocation [numerator (F*K + K) | reduced (F*K + K) | 2 uint32 arrival counters], bound to an NVLink multicast
+    object, for gccnmf_klnmf_step_multimem2: pack -> every rank sums its 1 / world slice inside the NVSwitch (multimem.ld_reduce) and
+    multicasts it to all ranks (multimem.st) -> W update from the local `reduced` copy.  Per GPU and iteration the links carry one
+    numerator each way whatever the world size.  `create` returns None without multicast support."""
+    COUNTER_PAD = 64
+
+    def __init__(self, buffer, handle, numel, rank, world):
+        self.buffer, self.handle, self.numel, self.rank, self.world = buffer, handle, numel, rank, world
+        self.iterations = 0             # arrivals so far / world (identical on every rank)
+
+    @classmethod
+    def create(cls, numel, device, group):
+        try:
+            import torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group if group is not None else dist.group.WORLD
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+            t = symm_mem.empty(2 * numel + cls.COUNTER_PAD, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(t, group)
+            if not getattr(hdl, 'has_multicast_support', False) or not int(hdl.multicast_ptr):
+                return None
+            t.zero_()
+            torch.cuda.synchronize(device)
+            hdl.barrier(channel=0, timeout_ms=20000)           # every rank's counters are zero before anyone signals
+            return cls(t, hdl, numel, dist.get_rank(group), dist.get_world_size(group))
+        except Exception:
+            return None
+
+    def step_args(self, it):
+        """(rank, world, numer_local, numer_mc, reduced_local, reduced_mc, counters_local, counters_mc, arrivals_expected)."""
+        self.iterations += 1
+        local, mc = int(self.buffer.data_ptr()), int(self.handle.multicast_ptr)
+        red, cnt = 4 * self.numel, 8 * self.numel
+        return (self.rank, self.world, local, mc, local + red, mc + red, local + cnt, mc + cnt, self.world * self.iterations)
+
+
 def klnmf_sharded_multimem(ops, mm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon):
-    """klnmf_sharded with the exchange fused into the kernels (gccnmf_klnmf_step_multimem): one C call per iteration, nothing
-    on the host between the numerator and the W update."""
+    """klnmf_sharded with the exchange fused into the kernels: one C call per iteration, nothing on the host between the numerator
+    and the W update (gccnmf_klnmf_step_multimem: one-shot; gccnmf_klnmf_step_multimem2: two-shot)."""
+    step = ops.klnmf_step_multimem2 if isinstance(mm, MultimemTwoShot) else ops.klnmf_step_multimem
     ops.klnmf_begin(V_s, W, H_s)
     for it in range(numIterations):
-        ops.klnmf_step_multimem(V_s, W, H_s, it, *mm.step_args(it), sparsity_alpha=sparsityAlpha, epsilon=epsilon)
+        step(V_s, W, H_s, it, *mm.step_args(it), sparsity_alpha=sparsityAlpha, epsilon=epsilon)
     ops.klnmf_end(W, H_s, numIterations)
     return W, H_s
 
@@ -227,14 +269,20 @@ class ShardedGCCNMFPipeline(object):
             self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
         if int(flag.item()) == 0:
             self.h.set_option('force_simt_nmf', 1)
-        elif self.comm.world > 1 and os.environ.get('GCCNMF_COLLECTIVE', 'multimem') == 'multimem':
-            # fused W update over the NVSwitch multicast (all ranks must agree that it is available)
-            mm = MultimemNumerator.create(self.F * self.K + self.K, self.h.device, self.comm.group)
+        elif self.comm.world > 1 and os.environ.get('GCCNMF_COLLECTIVE', 'multimem').startswith('multimem'):
+            # exchange fused into the kernels over the NVSwitch multicast (all ranks must agree that it is available);
+            # GCCNMF_COLLECTIVE=multimem1 selects the one-shot form (every rank pulls the whole sum)
+            one_shot = os.environ.get('GCCNMF_COLLECTIVE', 'multimem') == 'multimem1'
+            mm = (MultimemNumerator if one_shot else MultimemTwoShot).create(self.F * self.K + self.K, self.h.device, self.comm.group)
             ok = self.torch.tensor([1 if mm is not None else 0], dtype=self.torch.int32, device=self.h.device)
             self.comm.dist.all_reduce(ok, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
             if int(ok.item()) == 1:
-                self.multimem, self.collective = mm, ('multimem.red arrival signal in the numerator pack + multimem.ld_reduce in the W-update '
-                                                         'kernel (sum formed in the NVSwitch, no host-launched barrier)')
+                self.multimem = mm
+                self.collective = ('one-shot: multimem.red arrival signal in the numerator pack + multimem.ld_reduce of the whole sum in the '
+                                   'W-update kernel (no host-launched barrier)') if one_shot else (
+                                   'two-shot inside the NVSwitch: multimem.red arrival signal in the numerator pack, each rank '
+                                   'multimem.ld_reduce-s its 1/world slice and multimem.st-s it to every rank, second arrival counter, '
+                                   'W update from local memory (no host-launched barrier, no NCCL call in the loop)')
         self._path_agreed = True
 
     def enhance(self, samples, collect_stage_times=False):

@@ -157,6 +157,18 @@ GCCNMF_API int gccnmf_klnmf_step_multimem(gccnmf_handle* h, const float* V, int 
                                float sparsity_alpha, float epsilon, int iteration, float* numer_local,
                                const float* numer_multicast, const uint32_t* counter_local, uint32_t* counter_multicast,
                                uint32_t arrivals_expected, void* workspace, size_t workspace_bytes, void* stream);
+/* The same iteration with a TWO-SHOT exchange: after the pack every rank sums only its 1 / world slice of the numerator with
+ * multimem.ld_reduce and multicasts the sum into the `reduced` buffer of every rank (multimem.st); the W update reads its local
+ * `reduced` copy once the second arrival counter is complete.  Link traffic per GPU and iteration: one numerator out, one in, for any
+ * world size (the one-shot form above makes every GPU serve `world` numerators).  numer_* / reduced_*: two symmetric buffers of
+ * (F*K + K) floats (local and multicast addresses); counters_*: two consecutive uint32 in symmetric memory (pack arrivals, slice
+ * arrivals), zero before the first iteration; arrivals_expected = world x (iteration + 1).  No double buffering needed: a rank
+ * re-packs only after its own W update, which waits for every rank's slice. */
+GCCNMF_API int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K,
+                                float sparsity_alpha, float epsilon, int iteration, int rank, int world, float* numer_local,
+                                const float* numer_multicast, const float* reduced_local, float* reduced_multicast,
+                                const uint32_t* counters_local, uint32_t* counters_multicast, uint32_t arrivals_expected,
+                                void* workspace, size_t workspace_bytes, void* stream);
 GCCNMF_API int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done,
                      void* workspace, size_t workspace_bytes, void* stream);
 
