@@ -12,9 +12,9 @@
 namespace {
 
 // ------------------------------------------------------------------ a3 + a4: coherence + angular spectrogram
-constexpr int kAngT = 32;     // frames per block (one per lane)
-constexpr int kAngGroups = 8; // TDOA groups (one per warp)
-constexpr int kAngBF = 8;     // frequency bins staged per step
+constexpr int kAngT = 16;     // frames per CTA
+constexpr int kAngWarps = 4;  // warps per CTA: each takes a quarter of the staged bins (partial sums added in warp order at the end)
+constexpr int kAngBF = 16;    // frequency bins staged per step
 constexpr int kAngMaxD = 128;
 
 // numpy's complex64 arithmetic for  X0 * conj(X1) / |X0| / |X1|  (runGCCNMF.py:44): float32 products,
@@ -31,26 +31,25 @@ __device__ __forceinline__ float2 phat_coherence(float2 a, float2 b) {
   return float2{re, im};
 }
 
-// grid = (frame tiles, TDOA chunks): blockIdx.y takes the TDOAs [y * d_chunk, (y + 1) * d_chunk) (d_chunk a multiple of the
-// 8 warp groups).  With one chunk the grid is T / 32 = 59 CTAs at the headline shape, i.e. 59 of the 148 SMs; splitting the
-// TDOAs replicates the coherence staging, keeps every accumulation in its bin order and fills the chip -- measured
-// 0.267 -> 0.249 ms only: the stage is bound by the float64 pipe (2 F D T = 123 M DFMA + the float64 square roots of the
-// PHAT normalisation), not by occupancy.  Chunk 0 writes the coherence.
-__global__ void __launch_bounds__(kAngT * kAngGroups)
-phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coherence, const double2* __restrict__ E, int D, int d_chunk,
+// CTA = 16 frames x all TDOAs, 4 warps.  A lane owns the TDOAs lane, lane + 32, ... (DPL of them) for ALL 16 frames of the tile:
+// per staged bin it reads its DPL steering values once and then one broadcast coherence value per frame, i.e. 2 DPL float64 FMAs
+// per shared-memory wavefront -- the previous layout (lane = frame, one broadcast E value per FMA pair) spent 6 wavefronts per 4 FMA
+// instructions and ran at 2.6 % of the float64 pipe.  The four warps split the bins of every staged chunk; their partial sums are
+// added in warp order at the end (deterministic).  Every CTA also writes the coherence of its frames.
+template <int DPL>
+__global__ void __launch_bounds__(kAngWarps * 32)
+phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coherence, const double2* __restrict__ E, int D,
                     float2* __restrict__ coherence, double* __restrict__ angular, double* __restrict__ tile_sums) {
   __shared__ double2 Cs[kAngBF][kAngT];
-  __shared__ double2 Es[kAngBF][kAngMaxD];
-  const int lane = threadIdx.x % kAngT, group = threadIdx.x / kAngT;
+  __shared__ double2 Es[kAngBF][kAngMaxD];          // reused as the reduction buffer red[kAngT][kAngMaxD] (doubles) at the end
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int t0 = blockIdx.x * kAngT;
-  const int t = t0 + lane;
-  const int d_begin = blockIdx.y * d_chunk, d_count = max(0, min(d_chunk, D - d_begin));
-  const bool write_coherence = coherence != nullptr && blockIdx.y == 0;
-  constexpr int kMaxPerThread = kAngMaxD / kAngGroups;
-  double acc[kMaxPerThread];
+  const bool accumulate = angular != nullptr || tile_sums != nullptr;
+  double acc[kAngT][DPL];
 #pragma unroll
-  for (int j = 0; j < kMaxPerThread; ++j) acc[j] = 0.0;
-  const int per_thread = (d_count + kAngGroups - 1) / kAngGroups;
+  for (int tt = 0; tt < kAngT; ++tt)
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) acc[tt][j] = 0.0;
 
   for (int f0 = 0; f0 < F; f0 += kAngBF) {
     for (int e = threadIdx.x; e < kAngBF * kAngT; e += blockDim.x) {
@@ -60,48 +59,60 @@ phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coheren
       if (f < F && t0 + tt < T) {
         const float2 coh = x_is_coherence ? X[(int64_t)f * T + t0 + tt]
                                           : phat_coherence(X[(int64_t)f * T + t0 + tt], X[((int64_t)F + f) * T + t0 + tt]);
-        if (write_coherence) coherence[(int64_t)f * T + t0 + tt] = coh;
+        if (coherence) coherence[(int64_t)f * T + t0 + tt] = coh;
         c = double2{(double)coh.x, (double)coh.y};
       }
       Cs[ff][tt] = c;
     }
-    for (int e = threadIdx.x; e < kAngBF * d_count; e += blockDim.x) {
-      const int ff = e / d_count, d = e % d_count;
-      Es[ff][d] = (f0 + ff < F) ? E[(int64_t)(f0 + ff) * D + d_begin + d] : double2{0.0, 0.0};
-    }
+    if (accumulate)
+      for (int e = threadIdx.x; e < kAngBF * D; e += blockDim.x) {
+        const int ff = e / D, d = e % D;
+        Es[ff][d] = (f0 + ff < F) ? E[(int64_t)(f0 + ff) * D + d] : double2{0.0, 0.0};
+      }
     __syncthreads();
-    if (angular || tile_sums) {
-#pragma unroll 4
-      for (int ff = 0; ff < kAngBF; ++ff) {
-        const double2 c = Cs[ff][lane];
+    if (accumulate) {
 #pragma unroll
-        for (int j = 0; j < kMaxPerThread; ++j) {
-          if (j < per_thread) {
-            const int d = group + j * kAngGroups;
-            if (d < d_count) {
-              const double2 e = Es[ff][d];
-              acc[j] += c.x * e.x - c.y * e.y;   // Re(C * E)
-            }
-          }
+      for (int i = 0; i < kAngBF / kAngWarps; ++i) {
+        const int ff = w + kAngWarps * i;
+        double2 e[DPL];
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) e[j] = (lane + 32 * j < D) ? Es[ff][lane + 32 * j] : double2{0.0, 0.0};
+#pragma unroll
+        for (int tt = 0; tt < kAngT; ++tt) {
+          const double2 c = Cs[ff][tt];
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) acc[tt][j] += c.x * e[j].x - c.y * e[j].y;   // Re(C * E)
         }
       }
     }
     __syncthreads();
   }
+  if (!accumulate) return;
+  double (*red)[kAngMaxD] = reinterpret_cast<double (*)[kAngMaxD]>(&Es[0][0]);
+  for (int r = 0; r < kAngWarps; ++r) {
+    if (w == r) {
 #pragma unroll
-  for (int j = 0; j < kMaxPerThread; ++j) {
-    if (j >= per_thread) break;
-    const int dl = group + j * kAngGroups;
-    if (dl >= d_count) continue;
-    const int d = d_begin + dl;
-    const double v = (t < T) ? acc[j] : 0.0;
-    if (angular && t < T) angular[(int64_t)d * T + t] = v;
-    if (tile_sums) {
-      double s = v;
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) tile_sums[(int64_t)blockIdx.x * D + d] = s;
+      for (int tt = 0; tt < kAngT; ++tt)
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+          const int d = lane + 32 * j;
+          if (d < D) red[tt][d] = r == 0 ? acc[tt][j] : red[tt][d] + acc[tt][j];
+        }
     }
+    __syncthreads();
   }
+  const int t_valid = min(kAngT, T - t0);
+  if (angular)
+    for (int e = threadIdx.x; e < kAngT * D; e += blockDim.x) {
+      const int d = e / kAngT, tt = e % kAngT;
+      if (tt < t_valid) angular[(int64_t)d * T + t0 + tt] = red[tt][d];
+    }
+  if (tile_sums)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      double sum = 0.0;
+      for (int tt = 0; tt < t_valid; ++tt) sum += red[tt][d];
+      tile_sums[(int64_t)blockIdx.x * D + d] = sum;
+    }
 }
 
 __global__ void mean_tiles_kernel(const double* __restrict__ tile_sums, int tiles, int D, int T, double* __restrict__ mean) {
@@ -434,14 +445,13 @@ int gccnmf_phat_angspec(gccnmf_handle* h, const float* X, int F, int T, int x_is
       return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "phat_angspec workspace too small");
     tile_sums = static_cast<double*>(workspace);
   }
-  // TDOA chunks of 16 (two per warp group) while that keeps at least ~2 CTAs per SM busy
   const int Dk = need_ang ? D : 0;
-  int chunks = 1;
-  while (chunks * 2 * 16 <= Dk && tiles * chunks < 4 * h->sm_count) chunks *= 2;
-  const int d_chunk = Dk > 0 ? (((Dk + chunks - 1) / chunks) + kAngGroups - 1) / kAngGroups * kAngGroups : kAngGroups;
-  GCCNMF_LAUNCH(h, phat_angspec_kernel, dim3(tiles, Dk > 0 ? (Dk + d_chunk - 1) / d_chunk : 1), kAngT * kAngGroups, 0, stream,
-                reinterpret_cast<const float2*>(X), F, T, x_is_coherence, reinterpret_cast<const double2*>(expJOmegaTau), Dk, d_chunk,
-                reinterpret_cast<float2*>(coherence), angular, tile_sums);
+  const float2* Xc = reinterpret_cast<const float2*>(X);
+  const double2* Ec = reinterpret_cast<const double2*>(expJOmegaTau);
+  float2* Cc = reinterpret_cast<float2*>(coherence);
+  if (Dk <= 32) GCCNMF_LAUNCH(h, phat_angspec_kernel<1>, tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
+  else if (Dk <= 64) GCCNMF_LAUNCH(h, phat_angspec_kernel<2>, tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
+  else GCCNMF_LAUNCH(h, phat_angspec_kernel<4>, tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
   if (mean_angular) GCCNMF_LAUNCH(h, mean_tiles_kernel, (D + 63) / 64, 64, 0, stream, tile_sums, tiles, D, T, mean_angular);
   return GCCNMF_OK;
 }

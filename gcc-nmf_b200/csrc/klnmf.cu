@@ -256,6 +256,8 @@ int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const 
                                   const unsigned* arrivals_in, unsigned arrivals_expected, unsigned* arrivals_out_mc, void* workspace,
                                   size_t workspace_bytes, void* stream);
 
+int gccnmf_klnmf_tma_l2_window(gccnmf_handle* h, int F, int T2, int K, bool enable, void* workspace, size_t workspace_bytes);
+
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tma_supported(F, T2, K); }
 
 extern "C" {
@@ -282,7 +284,10 @@ int gccnmf_klnmf_begin(gccnmf_handle* h, const float* V, int F, int T2, const fl
   if (int st = check_dims(h, F, T2, K)) return st;
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
-  if (use_tc(h, F, T2, K)) return gccnmf_klnmf_tma_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream);
+  if (use_tc(h, F, T2, K)) {
+    if (int st = gccnmf_klnmf_tma_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
+    return gccnmf_klnmf_tma_l2_window(h, F, T2, K, true, workspace, workspace_bytes);      // cleared by gccnmf_klnmf_end
+  }
   return GCCNMF_OK;
 }
 
@@ -378,6 +383,8 @@ int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K,
                      size_t workspace_bytes, void* stream) {
   GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
+  h->l2_window_base = nullptr;
+  h->l2_window_bytes = 0;
   if (use_tc(h, F, T2, K)) {
     if (int st = gccnmf_klnmf_tma_finish(h, F, T2, H, K, iterations_done > 0, workspace, workspace_bytes, stream)) return st;
     if (iterations_done > 0) return gccnmf_klnmf_tma_finish_W(h, F, T2, W, K, workspace, workspace_bytes, stream);
@@ -395,6 +402,8 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
   if (iterations == 0) return GCCNMF_OK;
   if (use_tc(h, F, T2, K)) {
     if (int st = gccnmf_klnmf_tma_prepare(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, true, true, stream)) return st;
+    if (int st = gccnmf_klnmf_tma_l2_window(h, F, T2, K, true, workspace, workspace_bytes)) return st;
+    struct WindowGuard { gccnmf_handle* h; ~WindowGuard() { h->l2_window_base = nullptr; h->l2_window_bytes = 0; } } guard{h};
     for (int it = 0; it < iterations; ++it) {
       // colsum(W) comes out of the previous W update; with a fixed dictionary it is computed once
       // and the H *= norms of :81 stays pending: the next iteration's G1 loader and G2 epilogue apply it

@@ -383,11 +383,14 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
     numer[i] = s;
   }
   if (mc_counter) {
-    __threadfence_system();                     // my stores are visible system-wide before the CTA is counted as done
+    // One device-scope fence per CTA (cumulative over the CTA's stores through the barrier) and ONE system-scope release by the
+    // last CTA: a __threadfence_system() per thread (MEMBAR.SC.SYS x 500 k) cost ~20 us per iteration at 2 ranks.
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence();
       const unsigned prev = atomicAdd(done_counter, 1u);
       if (prev == gridDim.x - 1) {
+        __threadfence();                        // acquire side of the CTA count
         *done_counter = 0;                      // ready for the next iteration (this kernel is never concurrent with itself)
         __threadfence_system();
         asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
@@ -420,13 +423,15 @@ __global__ void tma_reduce_bcast_kernel(const float* numer_mc, float* reduced_mc
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reduced_mc + 4 * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
   }
-  __threadfence_system();
+  // this CTA's multicast stores travel over the links: one system-scope fence per CTA (thread 0, after the barrier -- cumulative over
+  // the CTA's stores) before the CTA is counted; the last CTA signals every rank
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned prev = atomicAdd(done_counter, 1u);
     if (prev == gridDim.x - 1) {
+      __threadfence();
       *done_counter = 0;
-      __threadfence_system();
       asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(arrivals_out_mc), "r"(1u) : "memory");
     }
   }
@@ -506,13 +511,13 @@ TmaWorkspace tma_carve(void* ws, size_t bytes, int F, int T2, int K) {
   w.plane_rt = (int64_t)T2 * w.Fp;
   w.row_blocks = (F + kApplyTile - 1) / kApplyTile;
   w.HT = c.take<float>((size_t)T2 * K);
+  w.HTp = c.take<bf16>((size_t)2 * w.plane_ht);       // right after the float32 master: one L2 access-policy window covers both
   w.VT = c.take<float>((size_t)T2 * w.Fp);
   w.partial = c.take<float>((size_t)kMaxSplits * F * K);
   w.colsum = c.take<float>((size_t)w.row_blocks * K);
   w.sumsq_part = c.take<float>((size_t)w.row_blocks * K);
   w.rowsum_part = c.take<float>((size_t)max_rowsum_slots(T2) * K);
   w.done = c.take<unsigned>(4);
-  w.HTp = c.take<bf16>((size_t)2 * w.plane_ht);
   w.Wp = c.take<bf16>((size_t)2 * w.plane_w);
   w.RTp = c.take<bf16>((size_t)2 * w.plane_rt);
   w.bytes = align_up(c.used, 256);
@@ -641,6 +646,32 @@ int gccnmf_klnmf_tma_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bo
 int gccnmf_klnmf_tma_finish_W(gccnmf_handle* h, int F, int T2, float* W, int K, void* workspace, size_t workspace_bytes, void* stream) {
   TMA_CARVE_OR_FAIL(w);
   GCCNMF_LAUNCH(h, tma_finish_w_kernel, dim3((K + 127) / 128, std::min(F, 64)), 128, 0, stream, W, F, K, w.sumsq_part, w.row_blocks);
+  return 0;
+}
+
+// Option l2_persist: while the loop runs, every launch through launch_ex carries an access-policy window (persisting) over the
+// float32 master of G^T (1) or the master and its planes (2) -- the H update re-reads and rewrites the master every iteration and
+// the ncu capture shows those 30 MB going to DRAM and back although the working set of an iteration is ~65 MB.  enable = false
+// clears the window (the persisting lines decay as other data replaces them).
+int gccnmf_klnmf_tma_l2_window(gccnmf_handle* h, int F, int T2, int K, bool enable, void* workspace, size_t workspace_bytes) {
+  h->l2_window_base = nullptr;
+  h->l2_window_bytes = 0;
+  if (!enable || h->l2_persist <= 0) return 0;
+  TMA_CARVE_OR_FAIL(w);
+  int dev = 0, max_window = 0, max_persist = 0;
+  GCCNMF_CHECK_CUDA(h, cudaGetDevice(&dev));
+  GCCNMF_CHECK_CUDA(h, cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  GCCNMF_CHECK_CUDA(h, cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  size_t bytes = (size_t)T2 * K * 4;
+  if (h->l2_persist >= 2) bytes = (size_t)((const char*)(w.HTp + 2 * w.plane_ht) - (const char*)w.HT);
+  bytes = std::min(bytes, std::min((size_t)max_window, (size_t)max_persist));
+  if (bytes == 0) return 0;
+  if (!h->l2_limit_set) {
+    GCCNMF_CHECK_CUDA(h, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, (size_t)48 << 20)));
+    h->l2_limit_set = true;
+  }
+  h->l2_window_base = w.HT;
+  h->l2_window_bytes = bytes;
   return 0;
 }
 

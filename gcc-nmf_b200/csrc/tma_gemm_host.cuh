@@ -101,8 +101,17 @@ int launch_ex(gccnmf_handle* h, const char* name, void (*kernel)(KArgs...), dim3
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  if (h->l2_window_bytes > 0) {          // KL-NMF loop: keep G^T resident in L2 (set by gccnmf_klnmf_tma_l2_window)
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = const_cast<void*>(h->l2_window_base);
+    attr[n].val.accessPolicyWindow.num_bytes = h->l2_window_bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    ++n;
+  }
   if (pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;

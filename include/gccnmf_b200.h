@@ -67,6 +67,7 @@ GCCNMF_API int64_t gccnmf_launch_count(const gccnmf_handle* h);
  *   "wh_tile" [0]               tile width of the W.H contractions (104 / 112 / 128 / 256) instead of the planned one
  *   "gemm_pair" [-1]            plane GEMM on cta_group::2 CTA pairs: -1 where a call site prefers it, 0 never, 1 wherever possible
  *                               (bit-identical results either way; measured no faster)
+ *   "l2_persist" [0]            KL-NMF loop: persisting L2 access-policy window over G^T (1 = float32 master, 2 = master + planes)
  *   "gemm_preload" [1]          bit 0: the W.H ratio epilogue fetches V during the main loop
  *   "gemm_streaming" [0]        st.global.cs / ld.global.cs for the k-split partials of the W-update numerator */
 GCCNMF_API int gccnmf_set_option(gccnmf_handle* h, const char* name, int value);
