@@ -238,6 +238,8 @@ int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, c
                               void* workspace, size_t workspace_bytes, int colsum_state, bool pending_norms, void* stream);
 int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
                                size_t workspace_bytes, bool have_rowsum, void* stream);
+int gccnmf_klnmf_tma_partial_W_to(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K, void* workspace,
+                                  size_t workspace_bytes, bool have_rowsum, float* numer_out, void* stream);
 int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
                              void* workspace, size_t workspace_bytes, void* stream);
 int gccnmf_klnmf_tma_finish(gccnmf_handle* h, int F, int T2, float* H, int K, bool pending_norms, void* workspace,
@@ -302,7 +304,7 @@ int gccnmf_klnmf_step_numer(gccnmf_handle* h, const float* V, int F, int T2, con
   if (use_tc(h, F, T2, K)) {
     if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0,
                                           iteration > 0, stream)) return st;
-    if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+    if (int st = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, numer, stream)) return st;
     return gccnmf_klnmf_tma_pack_numer(h, F, T2, K, numer, workspace, workspace_bytes, stream);
   }
   Workspace w = carve(workspace, workspace_bytes, F, T2, K);
@@ -350,7 +352,7 @@ int gccnmf_klnmf_step_multimem(gccnmf_handle* h, const float* V, int F, int T2, 
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0,
                                          stream)) return st;
-  if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+  if (int st = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, numer_local, stream)) return st;
   if (int st = gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer_local, counter_multicast, workspace, workspace_bytes, stream)) return st;
   return gccnmf_klnmf_tma_apply_W_mc(h, F, T2, W, K, numer_multicast, true, counter_local, arrivals_expected, workspace, workspace_bytes, stream);
 }
@@ -372,7 +374,7 @@ int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int F, int T2,
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0,
                                          stream)) return st;
-  if (int st = gccnmf_klnmf_tma_partial_W(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, stream)) return st;
+  if (int st = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, numer_local, stream)) return st;
   if (int st = gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer_local, counters_multicast, workspace, workspace_bytes, stream)) return st;
   if (int st = gccnmf_klnmf_tma_reduce_bcast(h, F, T2, K, numer_multicast, reduced_multicast, rank, world, counters_local, arrivals_expected,
                                              counters_multicast + 1, workspace, workspace_bytes, stream)) return st;

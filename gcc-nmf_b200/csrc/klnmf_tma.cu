@@ -372,7 +372,8 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
                                       unsigned* done_counter, unsigned* mc_counter) {
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // partial == NULL: the numerator itself is already in place (k-splits summed inside clusters by the contraction): row sums only
+  const int64_t i = (partial ? 0 : n) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float s = partial[i];
     for (int z = 1; z < splits; ++z) s += partial[(int64_t)z * n + i];
@@ -527,6 +528,17 @@ TmaWorkspace tma_carve(void* ws, size_t bytes, int F, int T2, int K) {
 
 size_t tma_workspace_bytes(int F, int T2, int K) { return tma_carve(nullptr, 0, F, T2, K).bytes; }
 
+// Whether the W-update numerator contraction sums its k-splits inside (1, 1, splits) clusters through distributed shared memory
+// (one (F, K) result, no slabs): when every cluster of the launch can be resident at once (GPC sizes decide), else the k-split slabs
+// are written and summed by their consumer as before.
+bool w_cluster_reduce(gccnmf_handle* h, const Plan& p, int F, int K) {
+  if (!h->w_cluster_reduce || p.w.splits < 2 || p.w.splits > 8) return false;
+  int resident = 0;
+  if (plane_gemm_z_clusters<true, true, EpiStoreT>(h, p.w.bn, p.w.splits, &resident)) return false;
+  const int tiles = m_tiles_of(K, false) * ((F + p.w.bn - 1) / p.w.bn);
+  return resident >= tiles;
+}
+
 #define TMA_CARVE_OR_FAIL(w)                                                                                        \
   TmaWorkspace w = tma_carve(workspace, workspace_bytes, F, T2, K);                                                 \
   if (!w.ok) return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf (TMA tensor-core path) workspace too small: need %zu bytes", tma_workspace_bytes(F, T2, K))
@@ -582,8 +594,8 @@ int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, c
 }
 
 // :77 numerator: partial[z] = (V / (W H)) . H^T over the frame range of split z (row sums of H come from update_H).
-int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
-                               void* workspace, size_t workspace_bytes, bool have_rowsum, void* stream) {
+int gccnmf_klnmf_tma_partial_W_to(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
+                                  void* workspace, size_t workspace_bytes, bool have_rowsum, float* numer_out, void* stream) {
   TMA_CARVE_OR_FAIL(w);
   (void)V; (void)W; (void)H;
   if (!have_rowsum) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf (TMA path): partial_W needs the row sums left by update_H");
@@ -597,10 +609,19 @@ int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, 
   {  // G4: partial[z][f][atom] = sum_t H^T[t][atom] R^T[t][f]
     const Operand HTmn{w.HTp, (int64_t)K, w.plane_ht, true};
     const Operand RTmn{w.RTp, w.Fp, w.plane_rt, true};
-    EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F, true, h->gemm_streaming != 0};
-    if (int st = plane_gemm<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, false, e, nullptr, stream)) return st;
+    if (w_cluster_reduce(h, p, F, K)) {     // k-splits summed inside clusters: one (F, K) result, straight into numer_out when given
+      EpiStoreT e{numer_out ? numer_out : w.partial, (int64_t)K, (int64_t)F * K, K, F, true, false};
+      if (int st = plane_gemm_z_reduce<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, e, nullptr, stream)) return st;
+    } else {
+      EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F, true, h->gemm_streaming != 0};
+      if (int st = plane_gemm<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, false, e, nullptr, stream)) return st;
+    }
   }
   return 0;
+}
+int gccnmf_klnmf_tma_partial_W(gccnmf_handle* h, const float* V, int F, int T2, const float* W, const float* H, int K,
+                               void* workspace, size_t workspace_bytes, bool have_rowsum, void* stream) {
+  return gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, have_rowsum, nullptr, stream);
 }
 
 // :77 in the (U, G) gauge (the normalisation of :79-:81 is applied by finish).  Numerator and row sums come from `numer`
@@ -616,7 +637,8 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
     return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial, 1,
                      rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected);
   return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<false>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial,
-                   numer ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected);
+                   (numer || w_cluster_reduce(h, p, F, K)) ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part, w.colsum,
+                   arrival_counter, arrivals_expected);
 }
 
 int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const float* numer_multicast, float* reduced_multicast, int rank, int world,
@@ -680,8 +702,11 @@ int gccnmf_klnmf_tma_pack_numer_mc(gccnmf_handle* h, int F, int T2, int K, float
   TMA_CARVE_OR_FAIL(w);
   const Plan p = make_plan(h, F, T2, K);
   const int64_t n = (int64_t)F * K;
-  return launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)((n + K + 255) / 256)), dim3(256), 0, stream, h->nmf_pdl, dim3(1, 1, 1),
-                   (const float*)w.partial, p.w.splits, n, (const float*)w.rowsum_part, p.rowsum_slots, K, numer, w.done, mc_counter);
+  // (pairs with gccnmf_klnmf_tma_partial_W_to(..., numer): with cluster-reduced k-splits the numerator is already in `numer`)
+  const bool in_place = w_cluster_reduce(h, p, F, K);
+  return launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)(((in_place ? 0 : n) + K + 255) / 256)), dim3(256), 0, stream,
+                   h->nmf_pdl, dim3(1, 1, 1), in_place ? (const float*)nullptr : (const float*)w.partial, p.w.splits, n, (const float*)w.rowsum_part,
+                   p.rowsum_slots, K, numer, w.done, mc_counter);
 }
 int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream) {
   return gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer, nullptr, workspace, workspace_bytes, stream);

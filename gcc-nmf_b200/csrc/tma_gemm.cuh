@@ -105,6 +105,14 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// 16 bytes from the shared memory of CTA `rank` of my cluster, at the offset of my own `local` pointer
+__device__ __forceinline__ float4 ld_cluster_f32x4(const float* local, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(umma::smem_u32(local)), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -186,6 +194,8 @@ struct PlaneGemmArgs {
   int preload;             // 1: the by-column epilogue's global operands are fetched into registers while the main loop runs
   int m_fastest;           // 0: grid (n tiles, m tiles, splits); 1: grid (m tiles, n tiles, splits) -- the CTAs that share a B tile are
                            // launched together, so a large B operand is read from HBM once (cluster shapes with CN == 1 only)
+  int z_cluster;           // S > 1: the S k-splits of a tile form a (1, 1, S) cluster and are summed through distributed shared memory
+                           // (CTA z finishes the z-th slice of the tile's columns, rank order 0 .. S - 1); the functor sees z = 0
   // SIMT tail rows (both operands K-major only): element (r, k) of plane p at ptr[p * plane + r * ld + k]
   const __nv_bfloat16* A; int64_t a_plane, lda;
   const __nv_bfloat16* B; int64_t b_plane, ldb;
@@ -616,6 +626,8 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // independent loads per thread before the first dependent store.
   umma::tc_fence_before_sync();
   __syncthreads();
+  const int zc = (kCluster == 1 && !has_tile_epilogue<Epilogue>::value) ? args.z_cluster : 0;
+  if (zc > 1) cluster_sync();             // every k-split of this tile has staged its partial accumulator
   if constexpr (has_tile_epilogue<Epilogue>::value) {
     // whole-tile epilogue: the functor reads the staged accumulator tile[n][m] itself (reductions ACROSS columns, e.g. the argmax
     // over the TDOAs of a frame, which the by-column hand-out below cannot express)
@@ -626,11 +638,16 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int m_first = m0 + 4 * lane;
     typename Epilogue::State st;
     epi.init(st, m_first, rowvals + 4 * lane);
-    const int n_valid = min(BN, args.N - n0);
+    int n_valid = min(BN, args.N - n0);
     constexpr int U = kColumnsInFlight;
     int c_first = warp;
+    if (zc > 1) {                          // my slice of the tile's columns
+      const int per = (n_valid + zc - 1) / zc;
+      c_first = z * per + warp;
+      n_valid = min(n_valid, (z + 1) * per);
+    }
     if constexpr (kPre > 0) {
-      if (args.preload) {
+      if (args.preload && zc <= 1) {
 #pragma unroll
         for (int u = 0; u < kPre; ++u) {
           const int cc = warp + kWarps * u;
@@ -654,8 +671,18 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int u = 0; u < U; ++u) {
         const int cc = c + kWarps * u;
         if (cc < n_valid) {
-          const float4 acc = *reinterpret_cast<const float4*>(tile + (size_t)cc * kBM + 4 * lane);
-          epi.store(m_first, n0 + cc, acc, loaded[u], z, st);
+          const float* src = tile + (size_t)cc * kBM + 4 * lane;
+          float4 acc;
+          if (zc > 1) {                    // sum of the k-splits in split order (the order the W update used for the slabs)
+            acc = ld_cluster_f32x4(src, 0);
+            for (int r = 1; r < zc; ++r) {
+              const float4 t = ld_cluster_f32x4(src, (uint32_t)r);
+              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+          } else {
+            acc = *reinterpret_cast<const float4*>(src);
+          }
+          epi.store(m_first, n0 + cc, acc, loaded[u], zc > 1 ? 0 : z, st);
         }
       }
     }
@@ -674,7 +701,7 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
   // No CTA of a cluster may exit while a peer can still signal its barriers (my last releases have been delivered by now:
   // they precede accum_full, which the epilogue waited for).
-  if (kCluster > 1) cluster_sync();
+  if (kCluster > 1 || zc > 1) cluster_sync();          // (z-cluster: no CTA exits while a peer still reads its tile)
   else __syncthreads();
   if (args.timing && tid == 0) args.timing[cta_linear * 8 + 7] = globaltimer_ns();
   if (warp == 1) {

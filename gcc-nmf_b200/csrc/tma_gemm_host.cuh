@@ -193,6 +193,7 @@ struct Operand {
 struct GemmShape {
   int M, N, Kc, splits, m_tiles, n_tiles, tail_rows;
   bool m_fastest;       // grid (m tiles, n tiles, splits): see PlaneGemmArgs
+  int z_cluster;        // > 1: the k-splits of a tile form a (1, 1, splits) cluster and are summed through distributed shared memory
 };
 
 // One instantiation: kernel attributes + how many of its clusters can be resident at once (queried once).
@@ -228,6 +229,32 @@ struct PlaneGemmInstance {
     *out = cached;
     return 0;
   }
+  // How many (1, 1, S) clusters of this kernel (k-splits summed through distributed shared memory) can be resident at once.
+  static int max_z_clusters(gccnmf_handle* h, int S, int* out) {
+    static int cached_per_device[kGccnmfMaxDevices][9];
+    if (S < 2 || S > 8 || CN * CM != 1 || PAIR) { *out = 0; return 0; }
+    int& slot = cached_per_device[h->device % kGccnmfMaxDevices][S];
+    if (slot == 0) {
+      int unused;
+      if (int st = max_clusters(h, &unused)) return st;     // (sets the shared-memory attribute)
+      auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, PAIR, Epi>;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(16, 16, S);
+      cfg.blockDim = dim3(tgemm::kThreads);
+      cfg.dynamicSmemBytes = C::kTotal;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      const cudaError_t err = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+      if (err != cudaSuccess) { (void)cudaGetLastError(); n = 0; }     // cluster shape not launchable: the caller keeps the slabs
+      slot = n + 1;
+    }
+    *out = slot - 1;
+    return 0;
+  }
   static int launch(gccnmf_handle* h, const Operand& A, const Operand& B, const GemmShape& g, const Epi& epi, unsigned long long* timing, void* stream) {
     auto kernel = tgemm::plane_gemm_kernel<BN, kKB, A_MN, B_MN, CN, CM, PAIR, Epi>;
     int unused;
@@ -253,13 +280,14 @@ struct PlaneGemmInstance {
     // m-fastest (always for a cta_group::2 pair, whose two m tiles must sit next to each other along x): grid (m, n, splits)
     const bool mf = PAIR || g.m_fastest;
     args.m_fastest = mf ? 1 : 0;
+    args.z_cluster = (CN * CM == 1 && !PAIR && g.z_cluster > 1) ? g.z_cluster : 0;
     const dim3 grid = mf ? dim3(g.m_tiles, g.n_tiles, g.splits) : dim3(g.n_tiles, g.m_tiles, g.splits);
     if (!timing && h->debug_timing) {   // diagnostics: every plane GEMM of the KL-NMF loop appends its CTA stamps (8 per CTA)
       args.timing = h->debug_timing + h->debug_timing_cursor;
       h->debug_timing_cursor += (size_t)grid.x * grid.y * grid.z * 8;
     }
     return launch_ex(h, "plane_gemm_kernel", kernel, grid, dim3(tgemm::kThreads), (size_t)C::kTotal, stream, h->nmf_pdl,
-                     mf ? dim3(CM, 1, 1) : dim3(CN, CM, 1), map_a, map_b, args, epi);
+                     args.z_cluster > 1 ? dim3(1, 1, args.z_cluster) : (mf ? dim3(CM, 1, 1) : dim3(CN, CM, 1)), map_a, map_b, args, epi);
   }
 };
 
@@ -334,6 +362,35 @@ int plane_gemm(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int
     case 256: return launch_plane_gemm<256, A_MN, B_MN>(h, A, B, M, N, Kc, splits, simt_tail, epi, timing, stream, m_fastest, prefer_pair);
   }
   return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm: tile width %d (supported: 104, 112, 128, 176, 208, 256)", bn);
+}
+
+// k-splits reduced inside (1, 1, splits) clusters (no slabs): query how many such clusters are resident at once / launch.
+template <bool A_MN, bool B_MN, class Epi>
+int plane_gemm_z_clusters(gccnmf_handle* h, int bn, int splits, int* out) {
+  switch (bn) {
+    case 128: return PlaneGemmInstance<128, A_MN, B_MN, 1, 1, Epi>::max_z_clusters(h, splits, out);
+    case 176: return PlaneGemmInstance<176, A_MN, B_MN, 1, 1, Epi>::max_z_clusters(h, splits, out);
+    case 208: return PlaneGemmInstance<208, A_MN, B_MN, 1, 1, Epi>::max_z_clusters(h, splits, out);
+    case 256: return PlaneGemmInstance<256, A_MN, B_MN, 1, 1, Epi>::max_z_clusters(h, splits, out);
+  }
+  *out = 0;
+  return 0;
+}
+template <bool A_MN, bool B_MN, class Epi>
+int plane_gemm_z_reduce(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, const Epi& epi,
+                        unsigned long long* timing, void* stream) {
+  GemmShape g{};
+  g.M = M; g.N = N; g.Kc = Kc; g.splits = splits; g.m_fastest = false; g.z_cluster = splits;
+  g.m_tiles = (M + tgemm::kBM - 1) / tgemm::kBM;
+  g.tail_rows = 0;
+  g.n_tiles = (N + bn - 1) / bn;
+  switch (bn) {
+    case 128: return PlaneGemmInstance<128, A_MN, B_MN, 1, 1, Epi>::launch(h, A, B, g, epi, timing, stream);
+    case 176: return PlaneGemmInstance<176, A_MN, B_MN, 1, 1, Epi>::launch(h, A, B, g, epi, timing, stream);
+    case 208: return PlaneGemmInstance<208, A_MN, B_MN, 1, 1, Epi>::launch(h, A, B, g, epi, timing, stream);
+    case 256: return PlaneGemmInstance<256, A_MN, B_MN, 1, 1, Epi>::launch(h, A, B, g, epi, timing, stream);
+  }
+  return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "plane gemm (cluster-reduced k-splits): tile width %d", bn);
 }
 
 }  // namespace tgemm_host

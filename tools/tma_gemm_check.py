@@ -180,8 +180,8 @@ def timing():
 
 
 def variants():
-    """KL-NMF stage time at config 2 over runtime switches: tile width of the W.H contractions (0 = planned), persisting L2 window
-    over G^T, streaming hints for the k-split partials; plus the result's distance from the default build.  (Measured earlier in the
+    """KL-NMF stage time at config 2 over runtime switches: k-splits of the W-update numerator summed inside clusters (vs slabs),
+    persisting L2 window over G^T, streaming hints for the k-split slabs; plus the result's distance from the default build.  (Measured earlier in the
     round: operand preload and CTA pairs change nothing; 104-column dual-N tiles beat 112 and 128.)"""
     import torch
     from oracle import gccnmf_oracle as orc
@@ -192,11 +192,11 @@ def variants():
     W0, H0 = orc.initKLNMF(F, T2, K)
     W0d, H0d = h.to_device(W0), h.to_device(H0)
     ref = None
-    for wh in (0, 128):
+    for wred in (1, 0):
         for l2 in (0, 1, 2):
-            for stream in (0, 1):
+            for stream in ((0,) if wred else (0, 1)):
                 h.set_option('gemm_streaming', stream)
-                h.set_option('wh_tile', wh)
+                h.set_option('w_cluster_reduce', wred)
                 h.set_option('l2_persist', l2)
                 ms = []
                 for rep in range(3):
@@ -210,8 +210,9 @@ def variants():
                 Wn = W.cpu().numpy()
                 if ref is None:
                     ref = Wn
-                print('wh_tile %3d l2_persist %d streaming %d: %s ms per 100 iterations | rel W vs first variant %.2e finite %s' % (
-                    wh, l2, stream, ['%.2f' % m for m in ms], _rel(Wn, ref), bool(np.isfinite(Wn).all())), flush=True)
+                print('w_cluster_reduce %d l2_persist %d streaming %d: %s ms per 100 iterations | rel W vs first variant %.2e finite %s' % (
+                    wred, l2, stream, ['%.2f' % m for m in ms], _rel(Wn, ref), bool(np.isfinite(Wn).all())), flush=True)
+    h.set_option('w_cluster_reduce', 1)
     h.set_option('l2_persist', 0)
     h.set_option('wh_tile', 0)
     h.set_option('gemm_preload', 1)
