@@ -14,7 +14,6 @@ namespace {
 // ------------------------------------------------------------------ a3 + a4: coherence + angular spectrogram
 constexpr int kAngT = 16;     // frames per CTA
 constexpr int kAngWarps = 4;  // warps per CTA: each takes a quarter of the staged bins (partial sums added in warp order at the end)
-constexpr int kAngBF = 16;    // frequency bins staged per step
 constexpr int kAngMaxD = 128;
 
 // numpy's complex64 arithmetic for  X0 * conj(X1) / |X0| / |X1|  (runGCCNMF.py:44): float32 products,
@@ -34,14 +33,20 @@ __device__ __forceinline__ float2 phat_coherence(float2 a, float2 b) {
 // CTA = 16 frames x all TDOAs, 4 warps.  A lane owns the TDOAs lane, lane + 32, ... (DPL of them) for ALL 16 frames of the tile:
 // per staged bin it reads its DPL steering values once and then one broadcast coherence value per frame, i.e. 2 DPL float64 FMAs
 // per shared-memory wavefront -- the previous layout (lane = frame, one broadcast E value per FMA pair) spent 6 wavefronts per 4 FMA
-// instructions and ran at 2.6 % of the float64 pipe.  The four warps split the bins of every staged chunk; their partial sums are
-// added in warp order at the end (deterministic).  Every CTA also writes the coherence of its frames.
-template <int DPL>
+// instructions.  The four warps split the bins of every staged chunk; their partial sums are added in warp order at the end
+// (deterministic).  The global loads of chunk i + 1 (spectrogram pair, steering rows) are issued into registers before chunk i is
+// consumed: with one CTA of 4 warps per SM the un-overlapped load latency of 33-65 chunks was most of the kernel's time.
+// Every CTA also writes the coherence of its frames.
+template <int DPL, int BF>
 __global__ void __launch_bounds__(kAngWarps * 32)
 phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coherence, const double2* __restrict__ E, int D,
                     float2* __restrict__ coherence, double* __restrict__ angular, double* __restrict__ tile_sums) {
-  __shared__ double2 Cs[kAngBF][kAngT];
-  __shared__ double2 Es[kAngBF][kAngMaxD];          // reused as the reduction buffer red[kAngT][kAngMaxD] (doubles) at the end
+  constexpr int kThreads = kAngWarps * 32;
+  constexpr int kCPerThread = BF * kAngT / kThreads;           // coherence values a thread stages per chunk
+  constexpr int kEPerThread = BF * 32 * DPL / kThreads;         // steering values a thread stages per chunk (D <= 32 DPL)
+  static_assert(BF * kAngT % kThreads == 0 && BF % kAngWarps == 0, "chunk shape");
+  __shared__ double2 Cs[BF][kAngT];
+  __shared__ double2 Es[(BF > kAngT / 2 ? BF : kAngT / 2)][32 * DPL];   // reused as the reduction buffer red[kAngT][32 DPL] (doubles) at the end
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int t0 = blockIdx.x * kAngT;
   const bool accumulate = angular != nullptr || tile_sums != nullptr;
@@ -51,32 +56,60 @@ phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coheren
 #pragma unroll
     for (int j = 0; j < DPL; ++j) acc[tt][j] = 0.0;
 
-  for (int f0 = 0; f0 < F; f0 += kAngBF) {
-    for (int e = threadIdx.x; e < kAngBF * kAngT; e += blockDim.x) {
-      const int ff = e / kAngT, tt = e % kAngT;
-      const int f = f0 + ff;
+  float2 xa[kCPerThread], xb[kCPerThread];
+  double2 er[kEPerThread];
+  auto fetch = [&](int f0) {
+#pragma unroll
+    for (int q = 0; q < kCPerThread; ++q) {
+      const int e = threadIdx.x + q * kThreads, f = f0 + e / kAngT, t = t0 + e % kAngT;
+      xa[q] = xb[q] = float2{0.f, 0.f};
+      if (f < F && t < T) {
+        xa[q] = X[(int64_t)f * T + t];
+        if (!x_is_coherence) xb[q] = X[((int64_t)F + f) * T + t];
+      }
+    }
+    if (accumulate) {
+#pragma unroll
+      for (int q = 0; q < kEPerThread; ++q) {
+        const int e = threadIdx.x + q * kThreads, ff = e / (32 * DPL), d = e % (32 * DPL);
+        er[q] = (f0 + ff < F && d < D) ? E[(int64_t)(f0 + ff) * D + d] : double2{0.0, 0.0};
+      }
+    }
+  };
+  auto stash = [&](int f0) {
+#pragma unroll
+    for (int q = 0; q < kCPerThread; ++q) {
+      const int e = threadIdx.x + q * kThreads, ff = e / kAngT, tt = e % kAngT;
+      const int f = f0 + ff, t = t0 + tt;
       double2 c = double2{0.0, 0.0};
-      if (f < F && t0 + tt < T) {
-        const float2 coh = x_is_coherence ? X[(int64_t)f * T + t0 + tt]
-                                          : phat_coherence(X[(int64_t)f * T + t0 + tt], X[((int64_t)F + f) * T + t0 + tt]);
-        if (coherence) coherence[(int64_t)f * T + t0 + tt] = coh;
+      if (f < F && t < T) {
+        const float2 coh = x_is_coherence ? xa[q] : phat_coherence(xa[q], xb[q]);
+        if (coherence) coherence[(int64_t)f * T + t] = coh;
         c = double2{(double)coh.x, (double)coh.y};
       }
       Cs[ff][tt] = c;
     }
-    if (accumulate)
-      for (int e = threadIdx.x; e < kAngBF * D; e += blockDim.x) {
-        const int ff = e / D, d = e % D;
-        Es[ff][d] = (f0 + ff < F) ? E[(int64_t)(f0 + ff) * D + d] : double2{0.0, 0.0};
-      }
-    __syncthreads();
     if (accumulate) {
 #pragma unroll
-      for (int i = 0; i < kAngBF / kAngWarps; ++i) {
+      for (int q = 0; q < kEPerThread; ++q) {
+        const int e = threadIdx.x + q * kThreads;
+        Es[e / (32 * DPL)][e % (32 * DPL)] = er[q];
+      }
+    }
+  };
+
+  fetch(0);
+  for (int f0 = 0; f0 < F; f0 += BF) {
+    stash(f0);
+    __syncthreads();
+    if (f0 + BF < F) fetch(f0 + BF);
+    if (accumulate) {
+#pragma unroll
+      for (int i = 0; i < BF / kAngWarps; ++i) {
         const int ff = w + kAngWarps * i;
         double2 e[DPL];
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) e[j] = (lane + 32 * j < D) ? Es[ff][lane + 32 * j] : double2{0.0, 0.0};
+        for (int j = 0; j < DPL; ++j) e[j] = Es[ff][lane + 32 * j];
 #pragma unroll
         for (int tt = 0; tt < kAngT; ++tt) {
           const double2 c = Cs[ff][tt];
@@ -88,7 +121,7 @@ phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coheren
     __syncthreads();
   }
   if (!accumulate) return;
-  double (*red)[kAngMaxD] = reinterpret_cast<double (*)[kAngMaxD]>(&Es[0][0]);
+  double (*red)[32 * DPL] = reinterpret_cast<double (*)[32 * DPL]>(&Es[0][0]);
   for (int r = 0; r < kAngWarps; ++r) {
     if (w == r) {
 #pragma unroll
@@ -96,7 +129,7 @@ phat_angspec_kernel(const float2* __restrict__ X, int F, int T, int x_is_coheren
 #pragma unroll
         for (int j = 0; j < DPL; ++j) {
           const int d = lane + 32 * j;
-          if (d < D) red[tt][d] = r == 0 ? acc[tt][j] : red[tt][d] + acc[tt][j];
+          red[tt][d] = r == 0 ? acc[tt][j] : red[tt][d] + acc[tt][j];
         }
     }
     __syncthreads();
@@ -449,9 +482,9 @@ int gccnmf_phat_angspec(gccnmf_handle* h, const float* X, int F, int T, int x_is
   const float2* Xc = reinterpret_cast<const float2*>(X);
   const double2* Ec = reinterpret_cast<const double2*>(expJOmegaTau);
   float2* Cc = reinterpret_cast<float2*>(coherence);
-  if (Dk <= 32) GCCNMF_LAUNCH(h, phat_angspec_kernel<1>, tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
-  else if (Dk <= 64) GCCNMF_LAUNCH(h, phat_angspec_kernel<2>, tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
-  else GCCNMF_LAUNCH(h, phat_angspec_kernel<4>, tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
+  if (Dk <= 32) GCCNMF_LAUNCH(h, (phat_angspec_kernel<1, 32>), tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
+  else if (Dk <= 64) GCCNMF_LAUNCH(h, (phat_angspec_kernel<2, 16>), tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
+  else GCCNMF_LAUNCH(h, (phat_angspec_kernel<4, 8>), tiles, kAngWarps * 32, 0, stream, Xc, F, T, x_is_coherence, Ec, Dk, Cc, angular, tile_sums);
   if (mean_angular) GCCNMF_LAUNCH(h, mean_tiles_kernel, (D + 63) / 64, 64, 0, stream, tile_sums, tiles, D, T, mean_angular);
   return GCCNMF_OK;
 }

@@ -193,6 +193,27 @@ class GCCNMFPipeline(object):
             raise ValueError('did not find enough peaks in the angular spectrum')          # gccNMFFunctions.py:102-104
         if st & 2:
             raise ValueError('All-NaN slice encountered')                                  # numpy.nanargmax, :138
+        if st & 4:
+            raise RuntimeError('all-TDOA argmax: more near-tie decisions than the refinement list holds; use enhance(), which falls '
+                               'back to the exact float64 kernel')
+
+    def run_fused_host(self, samples_host, numTargets=0, out_host=None, check=True):
+        """Pinned (or pageable) host samples in -> host float32 (S, 2, n_out) signal estimates out, through ONE library call
+        (gccnmf_separate): H2D copy, the whole flow enqueued without host synchronisation, D2H copy, one stream synchronise."""
+        torch = self.torch
+        s = samples_host if isinstance(samples_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(samples_host, dtype=np.float32))
+        r = self.run_fused(s.to(self.h.device, non_blocking=True), numTargets)
+        y = r['targetSignalEstimates']
+        if out_host is None:
+            out_host = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
+        if getattr(self, '_status_host', None) is None:
+            self._status_host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        out_host.copy_(y, non_blocking=True)
+        self._status_host.copy_(r['status'], non_blocking=True)
+        torch.cuda.current_stream(self.h.device).synchronize()
+        if check:
+            self.raise_on_status(self._status_host)
+        return out_host
 
     # ------------------------------------------------------------------ host-buffer entry (what e2e times)
     def enhance_host(self, samples_host, out_host=None):
