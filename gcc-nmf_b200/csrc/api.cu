@@ -45,6 +45,8 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   h->force_simt_nmf = path && strcmp(path, "simt") == 0;
   const char* pdl = getenv("GCCNMF_NMF_PDL");
   h->nmf_pdl = !(pdl && strcmp(pdl, "0") == 0);
+  const char* light = getenv("GCCNMF_MC_LIGHT_SIGNAL");
+  if (light) h->mc_light_signal = atoi(light);
   const char* pers = getenv("GCCNMF_ARGMAX_PERSISTENT");
   if (pers) h->argmax_persistent = strcmp(pers, "0") != 0;
   *out = h;
@@ -88,6 +90,7 @@ int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
   if (strcmp(name, "gemm_streaming") == 0) { h->gemm_streaming = value; return GCCNMF_OK; }
   if (strcmp(name, "argmax_persistent") == 0) { h->argmax_persistent = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "w_cluster_reduce") == 0) { h->w_cluster_reduce = value != 0; return GCCNMF_OK; }
+  if (strcmp(name, "mc_light_signal") == 0) { h->mc_light_signal = value; return GCCNMF_OK; }
   if (strcmp(name, "l2_persist") == 0) { h->l2_persist = value; return GCCNMF_OK; }
   if (strcmp(name, "gemm_preload") == 0) { h->gemm_preload = value; return GCCNMF_OK; }
   if (strcmp(name, "gemm_cluster") == 0) { h->gemm_cluster = value; return GCCNMF_OK; }

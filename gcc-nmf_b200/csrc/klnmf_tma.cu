@@ -233,11 +233,13 @@ template <bool MULTIMEM>
 __global__ void __launch_bounds__(256)
 tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, const float* __restrict__ partial, int splits,
                    const float* __restrict__ rowsum, int rowsum_slots, int F, int K, float* __restrict__ sumsq_part, float* __restrict__ colsum_part,
-                   const unsigned* arrival_counter, unsigned arrivals_expected) {
+                   const unsigned* arrival_counter, unsigned arrivals_expected, unsigned long long* stamp) {
   __shared__ float4 part[2][8][32];
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
   const int c = threadIdx.x, g = threadIdx.y;          // c: lane (4 atoms), g: row group 0..7
+  const bool stamping = stamp != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && g == 0;   // diagnostics (gccnmf_debug_timing)
+  if (stamping) stamp[0] = tgemm::globaltimer_ns();
   if (arrival_counter) {
     // every rank's contribution is in place once my copy of the counter has received all arrivals
     if (c == 0 && g == 0) {
@@ -250,6 +252,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
     }
     __syncthreads();
   }
+  if (stamping) stamp[1] = tgemm::globaltimer_ns();
   const int k = blockIdx.x * kApplyAtoms + 4 * c;       // K % 8 == 0 on this path: a thread's 4 atoms are all inside or all outside
   const int64_t slab = (int64_t)F * K;
   const bool active = k < K;
@@ -303,6 +306,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
     }
   }
   __syncthreads();                                       // part[] is reused below
+  if (stamping) stamp[2] = tgemm::globaltimer_ns();      // (the numerator and row sums of this CTA have arrived)
   float4 sumsq = make_float4(0.f, 0.f, 0.f, 0.f), csum = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
 #pragma unroll
@@ -327,6 +331,7 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
     for (int j = 0; j < 8; ++j) { const float4 v = part[g][j][c]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
     *reinterpret_cast<float4*>((g == 0 ? sumsq_part : colsum_part) + (int64_t)blockIdx.y * K + k) = s;
   }
+  if (stamping) stamp[7] = tgemm::globaltimer_ns();
 }
 
 // finish: the reference's normalisation (:79-:81), applied once.  c[k] = sqrt(sum of the row-block partial sums of squares).
@@ -369,9 +374,10 @@ __global__ void tma_finish_h_kernel(const float* __restrict__ HT, int T2, int K,
 // complete" -- so no host-launched barrier sits between the numerator and the W update (tma_apply_w_kernel<true> waits on its own
 // copy of the counter).
 __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t n, const float* rowsum, int rowsum_slots, int K, float* numer,
-                                      unsigned* done_counter, unsigned* mc_counter) {
+                                      unsigned* done_counter, unsigned* mc_counter, int light_signal, unsigned long long* stamp) {
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
+  if (stamp && blockIdx.x == 0 && threadIdx.x == 0) stamp[0] = tgemm::globaltimer_ns();
   // partial == NULL: the numerator itself is already in place (k-splits summed inside clusters by the contraction): row sums only
   const int64_t i = (partial ? 0 : n) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -393,10 +399,19 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
       if (prev == gridDim.x - 1) {
         __threadfence();                        // acquire side of the CTA count
         *done_counter = 0;                      // ready for the next iteration (this kernel is never concurrent with itself)
-        __threadfence_system();
-        asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
+        if (light_signal) {
+          // The data this signal publishes lies in THIS GPU's memory and peers fetch it over NVLink through this GPU's L2: a
+          // device-scope fence has already put it there, so the arrival is sent relaxed (no MEMBAR.SYS, which costs microseconds).
+          asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
+        } else {
+          __threadfence_system();
+          asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
+        }
+        if (stamp) stamp[7] = tgemm::globaltimer_ns();
       }
     }
+  } else if (stamp && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    stamp[7] = tgemm::globaltimer_ns();
   }
 }
 
@@ -406,9 +421,11 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
 // counter.  Per GPU and iteration the links carry one numerator out and one in, whatever the world size (the one-shot form, every rank
 // pulling the whole sum, makes each GPU serve `world` numerators: 16.8 MB per iteration at 8 ranks).
 __global__ void tma_reduce_bcast_kernel(const float* numer_mc, float* reduced_mc, int64_t n4, int rank, int world, const unsigned* arrivals_in,
-                                        unsigned arrivals_expected, unsigned* done_counter, unsigned* arrivals_out_mc) {
+                                        unsigned arrivals_expected, unsigned* done_counter, unsigned* arrivals_out_mc, unsigned long long* stamp) {
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
+  const bool stamping = stamp != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamping) stamp[0] = tgemm::globaltimer_ns();
   if (threadIdx.x == 0) {
     unsigned seen;
     unsigned long long spins = 0;
@@ -418,6 +435,7 @@ __global__ void tma_reduce_bcast_kernel(const float* numer_mc, float* reduced_mc
     } while ((int)(seen - arrivals_expected) < 0);
   }
   __syncthreads();
+  if (stamping) stamp[1] = tgemm::globaltimer_ns();
   const int64_t chunk = (n4 + world - 1) / world, begin = rank * chunk, end = begin + chunk < n4 ? begin + chunk : n4;
   for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = multimem_sum_f32x4(numer_mc + 4 * i);
@@ -428,12 +446,15 @@ __global__ void tma_reduce_bcast_kernel(const float* numer_mc, float* reduced_mc
   // the CTA's stores) before the CTA is counted; the last CTA signals every rank
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (stamping) stamp[2] = tgemm::globaltimer_ns();
     __threadfence_system();
+    if (stamping) stamp[3] = tgemm::globaltimer_ns();
     const unsigned prev = atomicAdd(done_counter, 1u);
     if (prev == gridDim.x - 1) {
       __threadfence();
       *done_counter = 0;
       asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(arrivals_out_mc), "r"(1u) : "memory");
+      if (stamp) stamp[7] = tgemm::globaltimer_ns();
     }
   }
 }
@@ -487,6 +508,15 @@ Plan make_plan(const gccnmf_handle* h, int F, int T2, int K) {
   p.bn_h = plan_tiles(h->sm_count, m_tiles_of(K, false), T2, F, false, kWidthsAll, 4).bn;
   p.w = plan_tiles(h->sm_count, m_tiles_of(K, false), F, T2, true, kWidthsAll, 4);
   p.rowsum_slots = (T2 + p.bn_h - 1) / p.bn_h;
+  return p;
+}
+
+// Diagnostics (gccnmf_debug_timing): one 8-slot record per launch of the W update / numerator pack / slice reduction, in launch
+// order with the plane GEMMs' per-CTA records.
+unsigned long long* next_stamp(gccnmf_handle* h) {
+  if (!h->debug_timing) return nullptr;
+  unsigned long long* p = h->debug_timing + h->debug_timing_cursor;
+  h->debug_timing_cursor += 8;
   return p;
 }
 
@@ -635,10 +665,10 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
   const dim3 grid((K + kApplyAtoms - 1) / kApplyAtoms, w.row_blocks), block(32, 8);
   if (numer_is_multicast)
     return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial, 1,
-                     rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected);
+                     rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected, next_stamp(h));
   return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<false>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial,
                    (numer || w_cluster_reduce(h, p, F, K)) ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part, w.colsum,
-                   arrival_counter, arrivals_expected);
+                   arrival_counter, arrivals_expected, next_stamp(h));
 }
 
 int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const float* numer_multicast, float* reduced_multicast, int rank, int world,
@@ -649,7 +679,7 @@ int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const 
   const int64_t chunk = (n4 + world - 1) / world;
   const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (chunk + 255) / 256));
   return launch_ex(h, "tma_reduce_bcast_kernel", tma_reduce_bcast_kernel, dim3(ctas), dim3(256), 0, stream, h->nmf_pdl, dim3(1, 1, 1), numer_multicast,
-                   reduced_multicast, n4, rank, world, arrivals_in, arrivals_expected, w.done + 1, arrivals_out_mc);
+                   reduced_multicast, n4, rank, world, arrivals_in, arrivals_expected, w.done + 1, arrivals_out_mc, next_stamp(h));
 }
 
 int gccnmf_klnmf_tma_apply_W(gccnmf_handle* h, int F, int T2, float* W, int K, const float* numer, bool numer_is_multicast,
@@ -706,7 +736,7 @@ int gccnmf_klnmf_tma_pack_numer_mc(gccnmf_handle* h, int F, int T2, int K, float
   const bool in_place = w_cluster_reduce(h, p, F, K);
   return launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)(((in_place ? 0 : n) + K + 255) / 256)), dim3(256), 0, stream,
                    h->nmf_pdl, dim3(1, 1, 1), in_place ? (const float*)nullptr : (const float*)w.partial, p.w.splits, n, (const float*)w.rowsum_part,
-                   p.rowsum_slots, K, numer, w.done, mc_counter);
+                   p.rowsum_slots, K, numer, w.done, mc_counter, h->mc_light_signal, next_stamp(h));
 }
 int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream) {
   return gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer, nullptr, workspace, workspace_bytes, stream);

@@ -36,8 +36,11 @@ def main():
     W0d, H0d = h.to_device(W0), h.to_device(H0)
     numer = h.empty((F * K + K,), torch.float32)
     nt = (T2 + 103) // 104
-    grids = [('G1', nt * 4), ('G2', 18 * 8), ('G3', nt * 4), ('G4', 3 * 8 * 6)]
-    per_iter = sum(c for _, c in grids)
+    gemms = [('G1', nt * 4), ('G2', 18 * 8), ('G3', nt * 4), ('G4', 3 * 8 * 6)]
+    # one 8-slot record per launch of the exchange kernels: PACK (row sums [+ numerator] -> symmetric buffer, arrival signal),
+    # RB (two-shot: slice reduction + multicast), AP (W update)
+    extra = {'fused': ['AP'], 'stepwise-no-exchange': ['PACK', 'AP'], 'two-shot': ['PACK', 'RB', 'AP'], 'one-shot': ['PACK', 'AP'],
+             'nccl': ['PACK', 'AP']}
     modes = ['fused', 'stepwise-no-exchange']
     if world > 1:
         modes += ['two-shot', 'one-shot', 'nccl']
@@ -89,7 +92,9 @@ def main():
         torch.cuda.synchronize()
         used = h.lib.gccnmf_debug_timing(h.h, None, 1)
         s = buf.cpu().numpy()[:used].reshape(-1, 8)
-        starts, ends = {}, {}
+        starts, ends, recs = {}, {}, {}
+        grids = gemms + [(n, 1) for n in extra[mode]]
+        per_iter = sum(c for _, c in grids)
         ok = len(s) >= per_iter * iters
         if ok:
             off = 0
@@ -97,6 +102,9 @@ def main():
                 for name, ctas in grids:
                     k = s[off:off + ctas]
                     off += ctas
+                    if ctas == 1 and name in ('PACK', 'RB', 'AP'):
+                        recs[it, name] = k[0].astype(np.int64)
+                        continue
                     k = k[(k[:, 0] > 0) & (k[:, 2] > 0)]
                     # under programmatic dependent launch a CTA is resident long before it may touch memory: its work starts when
                     # its first pipeline stage is full = CTA start + (clock64 at first full stage - clock64 at start) / SM clock
@@ -105,10 +113,27 @@ def main():
             its = range(4, iters - 1)
             period = np.median([starts[i + 1, 'G1'] - starts[i, 'G1'] for i in its]) / 1e3
             gap = np.median([starts[i + 1, 'G1'] - ends[i, 'G4'] for i in its]) / 1e3
-            spans = {n: np.median([ends[i, n] - starts[i, n] for i in its]) / 1e3 for n, _ in grids}
+            spans = {n: np.median([ends[i, n] - starts[i, n] for i in its]) / 1e3 for n, _ in gemms}
             inner = {a + '>' + b: np.median([starts[i, b] - ends[i, a] for i in its]) / 1e3 for a, b in (('G1', 'G2'), ('G2', 'G3'), ('G3', 'G4'))}
             msg = 'period %.1f us | G4 end -> next G1 first loads landed %.1f us | spans %s | gaps %s' % (
                 period, gap, {k: round(float(v), 1) for k, v in spans.items()}, {k: round(float(v), 1) for k, v in inner.items()})
+            # the exchange, relative to the end of the numerator contraction (medians, us)
+            med = lambda f: round(float(np.median([f(i) for i in its])) / 1e3, 1)   # noqa: E731
+            tl = {}
+            if 'PACK' in extra[mode]:
+                tl['pack start'] = med(lambda i: recs[i, 'PACK'][0] - ends[i, 'G4'])
+                tl['pack signalled'] = med(lambda i: recs[i, 'PACK'][7] - ends[i, 'G4'])
+            if 'RB' in extra[mode]:
+                tl['rb start'] = med(lambda i: recs[i, 'RB'][0] - ends[i, 'G4'])
+                tl['rb arrivals seen'] = med(lambda i: recs[i, 'RB'][1] - ends[i, 'G4'])
+                tl['rb cta0 stored'] = med(lambda i: recs[i, 'RB'][2] - ends[i, 'G4'])
+                tl['rb cta0 fenced'] = med(lambda i: recs[i, 'RB'][3] - ends[i, 'G4'])
+                tl['rb signalled'] = med(lambda i: recs[i, 'RB'][7] - ends[i, 'G4'])
+            tl['apply start'] = med(lambda i: recs[i, 'AP'][0] - ends[i, 'G4'])
+            tl['apply arrivals seen'] = med(lambda i: recs[i, 'AP'][1] - ends[i, 'G4'])
+            tl['apply operands in'] = med(lambda i: recs[i, 'AP'][2] - ends[i, 'G4'])
+            tl['apply cta0 end'] = med(lambda i: recs[i, 'AP'][7] - ends[i, 'G4'])
+            msg += ' | after G4 end: %s' % tl
         else:
             msg = 'stamps: %d records, expected %d' % (len(s), per_iter * iters)
         print('rank %d %-22s: %.2f ms per 100 iterations | %s' % (rank, mode, ms100, msg), flush=True)

@@ -247,12 +247,17 @@ def stamps():
         used = h.lib.gccnmf_debug_timing(h.h, None, 1)
         s = buf.cpu().numpy()[:used].reshape(-1, 8)
         nt = (T2 + WH - 1) // WH
-        grids = [('G1', nt * 4, 120), ('G2', 18 * 8, 144), ('G3', nt * 4, 120), ('G4', 3 * 8 * 6, 144)] * 3
+        grids = [('G1', nt * 4, 120), ('G2', 18 * 8, 144), ('G3', nt * 4, 120), ('G4', 3 * 8 * 6, 144), ('W update', 1, 0)] * 3
         off, prev_end = 0, None
         print('pdl=%d: %d CTA records' % (pdl, len(s)))
         for name, ctas, tc in grids:
             k = s[off:off + ctas]
             off += ctas
+            if name == 'W update':          # one record: [0] start (after the dependency wait), [2] operands loaded, [7] end of CTA 0
+                print('W update: CTA 0 %.1f us (loads %.1f us) | gap after previous GEMM %.1f us' % (
+                    (k[0, 7] - k[0, 0]) / 1e3, (k[0, 2] - k[0, 0]) / 1e3, (k[0, 0] - prev_end) / 1e3), flush=True)
+                prev_end = k[0, 7]
+                continue
             k = k[k[:, 0] > 0]
             t0 = k[:, 0].min()
             st, en = k[:, 0] - t0, k[:, 7] - t0
