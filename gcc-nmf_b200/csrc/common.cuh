@@ -22,6 +22,13 @@ struct gccnmf_handle {
   int gemm_preload = 1;          // plane GEMM epilogues that fetch their global operands during the main loop: bit 0 ratio (W.H), bit 1 H update
   int gemm_pair = -1;            // plane GEMM on cta_group::2 CTA pairs (256-row MMAs): -1 where the call site prefers it, 0 never, 1 wherever possible
   bool w_cluster_reduce = true;  // W-update numerator: k-splits summed inside (1, 1, splits) clusters through distributed shared memory (0: k-split slabs)
+  // set by gccnmf_klnmf_tma_step_pull around the contractions of a sharded iteration (pull exchange): where the row sums of G and the
+  // W-update numerator go (this rank's symmetric buffer) and whom the numerator contraction signals when its last CTA is done
+  float* xchg_rowsum = nullptr;
+  float* xchg_numer = nullptr;
+  unsigned* xchg_done = nullptr;
+  unsigned* xchg_counters[8] = {nullptr};
+  int xchg_world = 0;
   int mc_light_signal = 0;       // sharded runs: arrival signal of the numerator pack as device-scope fence + relaxed multimem.red (diagnostics)
   int l2_persist = 0;            // KL-NMF loop: launch-attribute L2 access-policy window (persisting) over G^T: 1 = float32 master, 2 = master + planes
   const void* l2_window_base = nullptr;   // set by the KL-NMF loop while it runs

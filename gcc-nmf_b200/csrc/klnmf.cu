@@ -260,6 +260,12 @@ int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const 
 
 int gccnmf_klnmf_tma_l2_window(gccnmf_handle* h, int F, int T2, int K, bool enable, void* workspace, size_t workspace_bytes);
 
+int64_t gccnmf_klnmf_tma_pull_floats(int F, int layout_T2, int K);
+bool gccnmf_klnmf_tma_pull_supported(gccnmf_handle* h, int F, int T2, int K);
+int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float alpha, float eps, int iteration,
+                               int64_t epoch, int rank, int world, float* const* bases, int layout_T2, int two_shot, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tma_supported(F, T2, K); }
 
 extern "C" {
@@ -379,6 +385,39 @@ int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int F, int T2,
   if (int st = gccnmf_klnmf_tma_reduce_bcast(h, F, T2, K, numer_multicast, reduced_multicast, rank, world, counters_local, arrivals_expected,
                                              counters_multicast + 1, workspace, workspace_bytes, stream)) return st;
   return gccnmf_klnmf_tma_apply_W_mc(h, F, T2, W, K, reduced_local, false, counters_local + 1, arrivals_expected, workspace, workspace_bytes, stream);
+}
+
+// PULL exchange: nothing is pushed over the links and nothing is reduced in the switch.  The numerator contraction writes this rank's
+// (F, K) partial straight into its symmetric buffer and its last CTA adds 1 to every rank's arrival counter; then either every rank's
+// W update reads all ranks' partials with plain peer loads and adds them in rank order (two_shot = 0: (world - 1) numerators inbound
+// per GPU), or each rank first sums its 1 / world slice the same way into its own buffer and the W updates fetch each word from its
+// owner (two_shot = 1: one numerator each way for any world size).  Row sums of G are read from every rank's slots directly.  No pack
+// pass, no system-scope fence, no multimem instruction; works on any peer-mapped symmetric buffer.
+// bases: HOST array of `world` device pointers -- every rank's buffer as mapped in this process (gccnmf_klnmf_pull_buffer_floats
+// floats each, zero before the first iteration); layout_T2: the largest 2T over the ranks (same value on every rank); epoch: how
+// many iterations earlier runs have executed on this buffer (its arrival counters keep counting, its halves alternate by parity).
+int64_t gccnmf_klnmf_pull_buffer_floats(int F, int layout_T2, int K) {
+  if (F <= 0 || layout_T2 <= 0 || K <= 0) return 0;
+  return gccnmf_klnmf_tma_pull_floats(F, layout_T2, K);
+}
+
+int gccnmf_klnmf_pull_supported(gccnmf_handle* h, int F, int T2, int K) {
+  GCCNMF_ENTER(h);
+  return (F > 0 && T2 > 0 && K > 0 && use_tc(h, F, T2, K) && gccnmf_klnmf_tma_pull_supported(h, F, T2, K)) ? 1 : 0;
+}
+
+int gccnmf_klnmf_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float sparsity_alpha, float epsilon,
+                           int iteration, int64_t epoch, int rank, int world, void* const* bases, int layout_T2, int two_shot, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  GCCNMF_ENTER(h);
+  if (int st = check_dims(h, F, T2, K)) return st;
+  GCCNMF_REQUIRE(h, bases && iteration >= 0 && epoch >= 0 && world >= 1 && world <= 8 && rank >= 0 && rank < world, "klnmf_step_pull: bad arguments");
+  for (int r = 0; r < world; ++r) GCCNMF_REQUIRE(h, bases[r] != nullptr, "klnmf_step_pull: NULL buffer of rank %d", r);
+  if (!use_tc(h, F, T2, K)) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_pull: shape not covered by the tensor-core path");
+  if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
+    return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
+  return gccnmf_klnmf_tma_step_pull(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, iteration, epoch, rank, world, reinterpret_cast<float* const*>(bases),
+                                    layout_T2, two_shot, workspace, workspace_bytes, stream);
 }
 
 int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,

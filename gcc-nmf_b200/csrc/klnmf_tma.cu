@@ -229,11 +229,32 @@ __device__ __forceinline__ float4 multimem_sum_f32x4(const float* p) {
 //   U <- U * (sum_z partial[z]) / rowsum(G)  (:77 in the (U, G) gauge); planes of U; per-tile column sums and column sums of
 //   squares -> colsum_part / sumsq_part[row block][atom] (summed by their consumers: colsum(U) and c = ||U[:, k]||)
 constexpr int kApplyAtoms = 128;      // atoms per CTA (32 lanes x 4)
-template <bool MULTIMEM>
+// Where the numerator and the row sums of G come from:
+//   kApplyLocal     this GPU's k-split partials / row-sum slots (single-GPU loop, or an all-reduced numerator given by the caller)
+//   kApplyMultimem  one-shot in the switch: every word is the multimem.ld_reduce sum over the ranks' symmetric buffers
+//   kApplyPull      one-shot pull: every rank's numerator and row-sum slots are read from its own memory over NVLink (peer-mapped
+//                   addresses) and added in rank order -- plain loads pipeline where multimem.ld_reduce took ~8 us for 2 MB
+//   kApplyPullOwner two-shot pull: the numerator word comes from the rank that owns (and has already summed) its slice
+enum { kApplyLocal = 0, kApplyMultimem = 1, kApplyPull = 2, kApplyPullOwner = 3 };
+struct PeerSet {
+  const float* numer[8];     // each rank's numerator buffer (F*K floats)
+  const float* rowsum[8];    // each rank's row-sum slots (rowsum_slots x K)
+  const float* reduced[8];   // each rank's slice-owner buffer (two-shot pull)
+  int world;
+  int64_t chunk4;            // float4 words per owned slice (two-shot pull)
+};
+__device__ __forceinline__ float4 ld_sys_f32x4(const float* p) {      // strong system-scope load: never served from a stale non-coherent line
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+template <int MODE>
 __global__ void __launch_bounds__(256)
 tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, const float* __restrict__ partial, int splits,
                    const float* __restrict__ rowsum, int rowsum_slots, int F, int K, float* __restrict__ sumsq_part, float* __restrict__ colsum_part,
-                   const unsigned* arrival_counter, unsigned arrivals_expected, unsigned long long* stamp) {
+                   const unsigned* arrival_counter, unsigned arrivals_expected, unsigned long long* stamp, PeerSet peers) {
+  constexpr bool MULTIMEM = MODE == kApplyMultimem;
+  constexpr bool PULL = MODE == kApplyPull || MODE == kApplyPullOwner;
   __shared__ float4 part[2][8][32];
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
@@ -262,11 +283,18 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
   float4 numer[kApplyTile / 8], u[kApplyTile / 8];
   float4 p[kApplyTile / 8][kMaxSplits];
   if (active) {
-    if (!MULTIMEM)
+    if (PULL) {
+      for (int rank = 0; rank < peers.world; ++rank)
+        for (int s = g; s < rowsum_slots; s += 8) {
+          const float4 v = ld_sys_f32x4(peers.rowsum[rank] + (int64_t)s * K + k);
+          rs_part.x += v.x; rs_part.y += v.y; rs_part.z += v.z; rs_part.w += v.w;
+        }
+    } else if (!MULTIMEM) {
       for (int s = g; s < rowsum_slots; s += 8) {
         const float4 v = arrival_counter ? __ldcg(reinterpret_cast<const float4*>(rowsum + (int64_t)s * K + k)) : __ldg(reinterpret_cast<const float4*>(rowsum + (int64_t)s * K + k));
         rs_part.x += v.x; rs_part.y += v.y; rs_part.z += v.z; rs_part.w += v.w;
       }
+    }
 #pragma unroll
     for (int r = 0; r < kApplyTile / 8; ++r) {
       const int f = blockIdx.y * kApplyTile + g + 8 * r;
@@ -276,6 +304,15 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
         u[r] = *reinterpret_cast<const float4*>(U + i);
         if (MULTIMEM) {
           numer[r] = multimem_sum_f32x4(partial + i);      // sum over ranks, reduced inside the NVSwitch
+        } else if (MODE == kApplyPull) {
+#pragma unroll
+          for (int z = 0; z < kMaxSplits; ++z)              // (z = rank: the ranks' numerators take the place of the k-split slabs)
+            p[r][z] = z < splits ? ld_sys_f32x4(peers.numer[z] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (MODE == kApplyPullOwner) {
+          const int owner = (int)((i >> 2) / peers.chunk4);
+#pragma unroll
+          for (int z = 1; z < kMaxSplits; ++z) p[r][z] = make_float4(0.f, 0.f, 0.f, 0.f);
+          p[r][0] = ld_sys_f32x4(peers.reduced[owner] + i);
         } else {
 #pragma unroll
           for (int z = 0; z < kMaxSplits; ++z)
@@ -459,6 +496,51 @@ __global__ void tma_reduce_bcast_kernel(const float* numer_mc, float* reduced_mc
   }
 }
 
+// Two-shot PULL exchange, first shot: rank r sums its slice of the numerator over the ranks with plain loads from their memories
+// (rank order: every rank would obtain the same bits) into its OWN `reduced` buffer and signals; the W update of every rank then
+// fetches each word from its owner (tma_apply_w_kernel<kApplyPullOwner>).  Per GPU and iteration the links carry one numerator in
+// each direction for any world size, nothing is pushed (no system-scope fence), and the loads pipeline.
+__global__ void tma_reduce_pull_kernel(PeerSet peers, float* reduced_local, int64_t n4, int rank, const unsigned* arrivals_in,
+                                       unsigned arrivals_expected, unsigned* done_counter, tgemm::PeerSignal signal, unsigned long long* stamp) {
+  tgemm::pdl_launch_dependents();
+  tgemm::pdl_wait_prior_grids();
+  const bool stamping = stamp != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamping) stamp[0] = tgemm::globaltimer_ns();
+  if (threadIdx.x == 0) {
+    unsigned seen;
+    unsigned long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrivals_in) : "memory");
+      if (++spins > (1ull << 25)) __trap();     // a lost peer must not hang the box
+    } while ((int)(seen - arrivals_expected) < 0);
+  }
+  __syncthreads();
+  if (stamping) stamp[1] = tgemm::globaltimer_ns();
+  const int64_t begin = rank * peers.chunk4, end = begin + peers.chunk4 < n4 ? begin + peers.chunk4 : n4;
+  for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = r < peers.world ? ld_sys_f32x4(peers.numer[r] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+      if (r < peers.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+    *reinterpret_cast<float4*>(reduced_local + 4 * i) = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (stamping) stamp[2] = tgemm::globaltimer_ns();
+    __threadfence();
+    const unsigned prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *done_counter = 0;
+      __threadfence();
+      tgemm::signal_peers(signal);
+      if (stamp) stamp[7] = tgemm::globaltimer_ns();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ tile plan
 // Cycles per 16-deep k-step of one CTA, from the CTA stamps (profiles/r02_cta_phase_stamps.md): a tcgen05.mma with M = 128 costs
 // ~128 cycles up to N = 208 (131 / 126 / 129 at N = 128 / 176 / 208) and ~168 at N = 224 / 256 (the rate cuBLAS reaches: 0.745 of
@@ -616,7 +698,8 @@ int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, c
   {  // G2: HT32, HTp = G * (U^T . R) / denom
     const Operand Wmn{w.Wp, (int64_t)K, w.plane_w, true};
     const Operand RTk{w.RTp, w.Fp, w.plane_rt, false};
-    EpiUpdateH e{w.HT, w.HTp, w.colsum, colsum_state == 2 ? w.sumsq_part : nullptr, w.rowsum_part, alpha, eps, (int64_t)K, w.plane_ht, K, T2,
+    EpiUpdateH e{w.HT, w.HTp, w.colsum, colsum_state == 2 ? w.sumsq_part : nullptr, h->xchg_rowsum ? h->xchg_rowsum : w.rowsum_part, alpha, eps,
+                 (int64_t)K, w.plane_ht, K, T2,
                  colsum_state == 2 ? w.row_blocks : 1, true};
     if (int st = plane_gemm<true, false>(h, p.bn_h, Wmn, RTk, K, T2, F, 1, false, e, nullptr, stream)) return st;
   }
@@ -641,7 +724,10 @@ int gccnmf_klnmf_tma_partial_W_to(gccnmf_handle* h, const float* V, int F, int T
     const Operand RTmn{w.RTp, w.Fp, w.plane_rt, true};
     if (w_cluster_reduce(h, p, F, K)) {     // k-splits summed inside clusters: one (F, K) result, straight into numer_out when given
       EpiStoreT e{numer_out ? numer_out : w.partial, (int64_t)K, (int64_t)F * K, K, F, true, false};
-      if (int st = plane_gemm_z_reduce<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, e, nullptr, stream)) return st;
+      tgemm::PeerSignal sig{};
+      sig.world = h->xchg_world;
+      for (int r = 0; r < sig.world; ++r) sig.counters[r] = h->xchg_counters[r];
+      if (int st = plane_gemm_z_reduce<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, e, nullptr, stream, h->xchg_done, &sig)) return st;
     } else {
       EpiStoreT e{w.partial, (int64_t)K, (int64_t)F * K, K, F, true, h->gemm_streaming != 0};
       if (int st = plane_gemm<true, true>(h, p.w.bn, HTmn, RTmn, K, F, T2, p.w.splits, false, e, nullptr, stream)) return st;
@@ -663,12 +749,95 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
   const float* partial = numer ? numer : w.partial;
   const float* rowsum = numer ? numer + (int64_t)F * K : w.rowsum_part;
   const dim3 grid((K + kApplyAtoms - 1) / kApplyAtoms, w.row_blocks), block(32, 8);
+  const PeerSet none{};
   if (numer_is_multicast)
-    return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<true>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial, 1,
-                     rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected, next_stamp(h));
-  return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<false>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial,
+    return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<kApplyMultimem>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w,
+                     partial, 1, rowsum, 1, F, K, w.sumsq_part, w.colsum, arrival_counter, arrivals_expected, next_stamp(h), none);
+  return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<kApplyLocal>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w, partial,
                    (numer || w_cluster_reduce(h, p, F, K)) ? 1 : p.w.splits, rowsum, numer ? 1 : p.rowsum_slots, F, K, w.sumsq_part, w.colsum,
-                   arrival_counter, arrivals_expected, next_stamp(h));
+                   arrival_counter, arrivals_expected, next_stamp(h), none);
+}
+
+// ---- pull exchange (gccnmf_klnmf_step_pull).  Layout of every rank's symmetric buffer, in floats:
+//   [numerator F*K] x 2 (iteration parity) | [row-sum slots max_slots*K] x 2 | reduced F*K | 64 floats: arrival counters (u32) 0, 1
+struct PullLayout { int64_t numer[2], rowsum[2], reduced, counters, total; };
+PullLayout pull_layout(int F, int T2, int K) {
+  PullLayout l;
+  const int64_t fk = (int64_t)F * K, rs = (int64_t)max_rowsum_slots(T2) * K;
+  l.numer[0] = 0; l.numer[1] = fk;
+  l.rowsum[0] = 2 * fk; l.rowsum[1] = 2 * fk + rs;
+  l.reduced = 2 * fk + 2 * rs;
+  l.counters = l.reduced + fk;
+  l.total = l.counters + 64;
+  return l;
+}
+PeerSet pull_peers(const float* const* bases, int world, const PullLayout& l, int parity, int F, int K) {
+  PeerSet ps{};
+  ps.world = world;
+  for (int r = 0; r < world; ++r) {
+    ps.numer[r] = bases[r] + l.numer[parity];
+    ps.rowsum[r] = bases[r] + l.rowsum[parity];
+    ps.reduced[r] = bases[r] + l.reduced;
+  }
+  const int64_t n4 = (int64_t)F * K / 4;
+  ps.chunk4 = (n4 + world - 1) / world;
+  return ps;
+}
+tgemm::PeerSignal pull_signal(float* const* bases, int world, const PullLayout& l, int which) {
+  tgemm::PeerSignal sg{};
+  sg.world = world;
+  for (int r = 0; r < world; ++r) sg.counters[r] = reinterpret_cast<unsigned*>(bases[r] + l.counters) + which;
+  return sg;
+}
+
+int64_t gccnmf_klnmf_tma_pull_floats(int F, int layout_T2, int K) { return pull_layout(F, layout_T2, K).total; }
+bool gccnmf_klnmf_tma_pull_supported(gccnmf_handle* h, int F, int T2, int K) { return w_cluster_reduce(h, make_plan(h, F, T2, K), F, K); }
+
+// One sharded iteration with the pull exchange; `bases`: host array of `world` device pointers, each rank's symmetric buffer as mapped
+// in THIS process (bases[rank] is the local one).
+int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float alpha, float eps, int iteration,
+                               int64_t epoch, int rank, int world, float* const* bases, int layout_T2, int two_shot, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  TMA_CARVE_OR_FAIL(w);
+  const Plan p = make_plan(h, F, T2, K);
+  if (!w_cluster_reduce(h, p, F, K) || world > 8)
+    return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_pull: needs the cluster-reduced numerator contraction and <= 8 ranks");
+  // (the layout is the same on every rank: built from the largest shard; a rank with fewer row-sum slots leaves the others zero)
+  const PullLayout l = pull_layout(F, layout_T2, K);
+  const int all_slots = max_rowsum_slots(layout_T2);
+  if (layout_T2 < T2) return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "klnmf_step_pull: layout_T2 %d < T2 %d", layout_T2, T2);
+  // epoch: iterations of earlier runs on this buffer (the arrival counters keep counting; buffers alternate by global parity)
+  const int parity = (int)((epoch + iteration) & 1);
+  const unsigned expected = (unsigned)((uint64_t)world * (uint64_t)(epoch + iteration + 1));
+  float* local = bases[rank];
+  const unsigned* counters_local = reinterpret_cast<const unsigned*>(local + l.counters);
+  // G1, G2 (row sums of G straight into the symmetric buffer), G3, G4 (numerator straight into the symmetric buffer; its last CTA
+  // signals every rank)
+  h->xchg_rowsum = local + l.rowsum[parity];
+  h->xchg_numer = local + l.numer[parity];
+  const tgemm::PeerSignal sig0 = pull_signal(bases, world, l, 0);
+  h->xchg_world = world;
+  for (int r = 0; r < world; ++r) h->xchg_counters[r] = sig0.counters[r];
+  h->xchg_done = w.done + 2;
+  int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, alpha, eps, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0, stream);
+  if (!st) st = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, h->xchg_numer, stream);
+  h->xchg_rowsum = nullptr; h->xchg_numer = nullptr; h->xchg_world = 0; h->xchg_done = nullptr;
+  if (st) return st;
+  const PeerSet peers = pull_peers(bases, world, l, parity, F, K);
+  const int64_t n4 = (int64_t)F * K / 4;
+  if (two_shot) {
+    const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (peers.chunk4 + 255) / 256));
+    if (int e = launch_ex(h, "tma_reduce_pull_kernel", tma_reduce_pull_kernel, dim3(ctas), dim3(256), 0, stream, h->nmf_pdl, dim3(1, 1, 1), peers,
+                          local + l.reduced, n4, rank, counters_local, expected, w.done + 1, pull_signal(bases, world, l, 1), next_stamp(h))) return e;
+  }
+  const dim3 grid((K + kApplyAtoms - 1) / kApplyAtoms, w.row_blocks), block(32, 8);
+  if (two_shot)
+    return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<kApplyPullOwner>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w,
+                     (const float*)nullptr, 1, (const float*)nullptr, all_slots, F, K, w.sumsq_part, w.colsum, counters_local + 1, expected,
+                     next_stamp(h), peers);
+  return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<kApplyPull>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w,
+                   (const float*)nullptr, world, (const float*)nullptr, all_slots, F, K, w.sumsq_part, w.colsum, counters_local, expected,
+                   next_stamp(h), peers);
 }
 
 int gccnmf_klnmf_tma_reduce_bcast(gccnmf_handle* h, int F, int T2, int K, const float* numer_multicast, float* reduced_multicast, int rank, int world,

@@ -185,6 +185,17 @@ __device__ __forceinline__ void load_planes8(const __nv_bfloat16* hi, const __nv
   }
 }
 
+// Completion signal of a whole launch to the ranks of a sharded run: the last CTA to finish adds 1 to the arrival counter of every
+// rank (peer-mapped addresses).  The data the signal publishes lies in THIS GPU's memory -- peers fetch it over NVLink through this
+// GPU's L2 -- so a device-scope fence per CTA is enough and the adds are relaxed (no MEMBAR.SYS: that costs ~5 us).
+struct PeerSignal {
+  unsigned* counters[8];
+  int world;              // 0: no signal
+};
+__device__ __forceinline__ void signal_peers(const PeerSignal& sig) {
+  for (int r = 0; r < sig.world; ++r) asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(sig.counters[r]), "r"(1u) : "memory");
+}
+
 struct PlaneGemmArgs {
   int M, N, Kc;
   int m_tiles;             // 128-row tiles on the tensor cores (= gridDim.y)
@@ -199,6 +210,8 @@ struct PlaneGemmArgs {
   // SIMT tail rows (both operands K-major only): element (r, k) of plane p at ptr[p * plane + r * ld + k]
   const __nv_bfloat16* A; int64_t a_plane, lda;
   const __nv_bfloat16* B; int64_t b_plane, ldb;
+  unsigned* done_counter;       // with `signal`: CTA completion count of this launch (zero before and after)
+  PeerSignal signal;
   unsigned long long* timing;   // optional diagnostics, 8 slots per CTA: [0] / [7] globaltimer (ns) at CTA start / end (tail CTAs too),
                                 // [1..6] clock64: start, first stage full, last MMA issued, producer done, accumulator complete, epilogue end
 };
@@ -703,6 +716,15 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   // they precede accum_full, which the epilogue waited for).
   if (kCluster > 1 || zc > 1) cluster_sync();          // (z-cluster: no CTA exits while a peer still reads its tile)
   else __syncthreads();
+  if (args.signal.world > 0 && tid == 0) {             // every store of this CTA precedes the barrier above
+    __threadfence();
+    const unsigned prev = atomicAdd(args.done_counter, 1u);
+    if (prev == gridDim.x * gridDim.y * gridDim.z - 1) {
+      *args.done_counter = 0;
+      __threadfence();
+      signal_peers(args.signal);
+    }
+  }
   if (args.timing && tid == 0) args.timing[cta_linear * 8 + 7] = globaltimer_ns();
   if (warp == 1) {
     umma::tc_fence_after_sync();

@@ -194,6 +194,8 @@ struct GemmShape {
   int M, N, Kc, splits, m_tiles, n_tiles, tail_rows;
   bool m_fastest;       // grid (m tiles, n tiles, splits): see PlaneGemmArgs
   int z_cluster;        // > 1: the k-splits of a tile form a (1, 1, splits) cluster and are summed through distributed shared memory
+  unsigned* done_counter;          // completion signal of the launch to the ranks of a sharded run (see tgemm::PeerSignal)
+  tgemm::PeerSignal signal;
 };
 
 // One instantiation: kernel attributes + how many of its clusters can be resident at once (queried once).
@@ -281,6 +283,8 @@ struct PlaneGemmInstance {
     const bool mf = PAIR || g.m_fastest;
     args.m_fastest = mf ? 1 : 0;
     args.z_cluster = (CN * CM == 1 && !PAIR && g.z_cluster > 1) ? g.z_cluster : 0;
+    args.done_counter = g.done_counter;
+    args.signal = g.signal;
     const dim3 grid = mf ? dim3(g.m_tiles, g.n_tiles, g.splits) : dim3(g.n_tiles, g.m_tiles, g.splits);
     if (!timing && h->debug_timing) {   // diagnostics: every plane GEMM of the KL-NMF loop appends its CTA stamps (8 per CTA)
       args.timing = h->debug_timing + h->debug_timing_cursor;
@@ -378,9 +382,10 @@ int plane_gemm_z_clusters(gccnmf_handle* h, int bn, int splits, int* out) {
 }
 template <bool A_MN, bool B_MN, class Epi>
 int plane_gemm_z_reduce(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, const Epi& epi,
-                        unsigned long long* timing, void* stream) {
+                        unsigned long long* timing, void* stream, unsigned* done_counter = nullptr, const tgemm::PeerSignal* signal = nullptr) {
   GemmShape g{};
   g.M = M; g.N = N; g.Kc = Kc; g.splits = splits; g.m_fastest = false; g.z_cluster = splits;
+  if (signal && signal->world > 0) { g.done_counter = done_counter; g.signal = *signal; }
   g.m_tiles = (M + tgemm::kBM - 1) / tgemm::kBM;
   g.tail_rows = 0;
   g.n_tiles = (N + bn - 1) / bn;

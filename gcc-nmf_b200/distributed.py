@@ -178,6 +178,60 @@ class MultimemTwoShot(object):
         return (self.rank, self.world, local, mc, local + red, mc + red, local + cnt, mc + cnt, self.world * self.iterations)
 
 
+class PullExchange(object):
+    """Symmetric buffer (torch symmetric memory: every rank's allocation mapped into every process) for gccnmf_klnmf_step_pull: the
+    numerator contraction writes this rank's partial into it and signals every rank; the W updates read the partials (or, two-shot,
+    the owners' slice sums) with plain peer loads.  No multicast object, no NCCL call, nothing on the host inside the loop.
+    two_shot: one numerator in each direction per GPU for any world size (default from 4 ranks up); one-shot: world - 1 inbound."""
+
+    def __init__(self, buffer, handle, bases, rank, world, layout_T2, two_shot):
+        self.buffer, self.handle, self.bases, self.rank, self.world = buffer, handle, bases, rank, world
+        self.layout_T2, self.two_shot = layout_T2, two_shot
+        self.epoch = 0                  # iterations executed on this buffer so far (identical on every rank)
+
+    @classmethod
+    def create(cls, lib, F, layout_T2, K, device, group, two_shot=None):
+        try:
+            import ctypes
+            import torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group if group is not None else dist.group.WORLD
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            if world > 8:
+                return None
+            numel = int(lib.gccnmf_klnmf_pull_buffer_floats(F, layout_T2, K))
+            t = symm_mem.empty(numel, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(t, group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != world or not all(ptrs):
+                return None
+            t.zero_()
+            torch.cuda.synchronize(device)
+            hdl.barrier(channel=0, timeout_ms=20000)           # every rank's buffer is zero before anyone signals
+            bases = (ctypes.c_void_p * world)(*ptrs)
+            if two_shot is None:
+                two_shot = world >= 4
+            return cls(t, hdl, bases, rank, world, layout_T2, bool(two_shot))
+        except Exception:
+            return None
+
+
+def klnmf_sharded_pull(ops, px, V_s, W, H_s, numIterations, sparsityAlpha, epsilon):
+    """klnmf_sharded with the pull exchange (gccnmf_klnmf_step_pull): one C call per iteration, five or six kernels, no host step."""
+    ops.klnmf_begin(V_s, W, H_s)
+    for it in range(numIterations):
+        ops.klnmf_step_pull(V_s, W, H_s, it, px.epoch, px.rank, px.world, px.bases, px.layout_T2, px.two_shot, sparsity_alpha=sparsityAlpha,
+                            epsilon=epsilon)
+    px.epoch += numIterations
+    ops.klnmf_end(W, H_s, numIterations)
+    return W, H_s
+
+
 def klnmf_sharded_multimem(ops, mm, V_s, W, H_s, numIterations, sparsityAlpha, epsilon):
     """klnmf_sharded with the exchange fused into the kernels: one C call per iteration, nothing on the host between the numerator
     and the W update (gccnmf_klnmf_step_multimem: one-shot; gccnmf_klnmf_step_multimem2: two-shot)."""
@@ -237,6 +291,7 @@ class ShardedGCCNMFPipeline(object):
         self.W0, self.H0s = self.h.to_device(W0), self.h.to_device(H0s)
         self.numer = self.h.empty((self.F * self.K + self.K,), torch.float32)
         self.multimem = None            # decided on the first call (needs the agreed NMF path)
+        self.pull = None
         self.collective = 'nccl-all-reduce'
         self.stage_events = None
 
@@ -258,6 +313,18 @@ class ShardedGCCNMFPipeline(object):
         ev = self.stage_events
         return {ev[i + 1][0]: ev[i][1].elapsed_time(ev[i + 1][1]) for i in range(len(ev) - 1)}
 
+    def _all_min(self, value):
+        t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.h.device)
+        if self.comm.world > 1:
+            self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+        return int(t.item())
+
+    def _all_max(self, value):
+        t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.h.device)
+        if self.comm.world > 1:
+            self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.MAX, group=self.comm.group)
+        return int(t.item())
+
     def _agree_on_nmf_path(self, T2):
         """All ranks must run the W update with the same kernels (bit-identical W): if any rank's shard
         shape falls back to the SIMT contractions, every rank does.  Decided once."""
@@ -269,20 +336,36 @@ class ShardedGCCNMFPipeline(object):
             self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
         if int(flag.item()) == 0:
             self.h.set_option('force_simt_nmf', 1)
-        elif self.comm.world > 1 and os.environ.get('GCCNMF_COLLECTIVE', 'multimem').startswith('multimem'):
-            # exchange fused into the kernels over the NVSwitch multicast (all ranks must agree that it is available);
-            # GCCNMF_COLLECTIVE=multimem1 selects the one-shot form (every rank pulls the whole sum)
-            one_shot = os.environ.get('GCCNMF_COLLECTIVE', 'multimem') == 'multimem1'
-            mm = (MultimemNumerator if one_shot else MultimemTwoShot).create(self.F * self.K + self.K, self.h.device, self.comm.group)
-            ok = self.torch.tensor([1 if mm is not None else 0], dtype=self.torch.int32, device=self.h.device)
-            self.comm.dist.all_reduce(ok, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
-            if int(ok.item()) == 1:
-                self.multimem = mm
-                self.collective = ('one-shot: multimem.red arrival signal in the numerator pack + multimem.ld_reduce of the whole sum in the '
-                                   'W-update kernel (no host-launched barrier)') if one_shot else (
-                                   'two-shot inside the NVSwitch: multimem.red arrival signal in the numerator pack, each rank '
-                                   'multimem.ld_reduce-s its 1/world slice and multimem.st-s it to every rank, second arrival counter, '
-                                   'W update from local memory (no host-launched barrier, no NCCL call in the loop)')
+        elif self.comm.world > 1 and os.environ.get('GCCNMF_COLLECTIVE', 'pull') != 'nccl':
+            # exchange fused into the kernels (all ranks must agree that it is available).  GCCNMF_COLLECTIVE: pull (default; pull1 /
+            # pull2 force the one- / two-shot form), multimem (two-shot inside the switch), multimem1 (one-shot inside the switch), nccl
+            mode = os.environ.get('GCCNMF_COLLECTIVE', 'pull')
+            agree = lambda ok: int(self._all_min(1 if ok else 0)) == 1       # noqa: E731
+            if mode.startswith('pull'):
+                layout_T2 = int(self._all_max(T2))
+                px = PullExchange.create(self.h.lib, self.F, layout_T2, self.K, self.h.device, self.comm.group,
+                                         two_shot={'pull1': False, 'pull2': True}.get(mode))
+                probe_ok = px is not None
+                if probe_ok:                                                  # the library refuses shapes without the cluster-reduced contraction
+                    probe_ok = self.h.lib.gccnmf_klnmf_pull_supported(self.h.h, self.F, T2, self.K) == 1
+                if agree(probe_ok):
+                    self.pull = px
+                    self.collective = ('pull exchange, %s: the numerator contraction writes its partial into the symmetric buffer and signals '
+                                       'every rank from its last CTA; %s; no pack pass, no system-scope fence, no NCCL call in the loop' % (
+                                           'two-shot' if px.two_shot else 'one-shot',
+                                           'each rank sums its 1/world slice with plain peer loads, the W updates fetch every word from its owner'
+                                           if px.two_shot else 'the W update reads every rank\'s partial with plain peer loads, added in rank order'))
+                else:
+                    mode = 'multimem'
+            if self.pull is None and mode.startswith('multimem'):
+                one_shot = mode == 'multimem1'
+                mm = (MultimemNumerator if one_shot else MultimemTwoShot).create(self.F * self.K + self.K, self.h.device, self.comm.group)
+                if agree(mm is not None):
+                    self.multimem = mm
+                    self.collective = ('one-shot in the switch: multimem.red arrival signal + multimem.ld_reduce of the whole sum in the W-update '
+                                       'kernel') if one_shot else (
+                                       'two-shot in the switch: each rank multimem.ld_reduce-s its 1/world slice and multimem.st-s it to every '
+                                       'rank, W update from local memory')
         self._path_agreed = True
 
     def enhance(self, samples, collect_stage_times=False):
@@ -303,7 +386,9 @@ class ShardedGCCNMFPipeline(object):
         W.copy_(self.W0)
         H.copy_(self.H0s)
         self._agree_on_nmf_path(V.shape[1])
-        if self.multimem is not None:
+        if self.pull is not None:
+            klnmf_sharded_pull(h, self.pull, V, W, H, self.I, self.alpha, self.eps)
+        elif self.multimem is not None:
             klnmf_sharded_multimem(h, self.multimem, V, W, H, self.I, self.alpha, self.eps)
         else:
             klnmf_sharded(h, comm, V, W, H, self.I, self.alpha, self.eps, self.numer)

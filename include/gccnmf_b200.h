@@ -170,6 +170,22 @@ GCCNMF_API int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int
                                 const float* numer_multicast, const float* reduced_local, float* reduced_multicast,
                                 const uint32_t* counters_local, uint32_t* counters_multicast, uint32_t arrivals_expected,
                                 void* workspace, size_t workspace_bytes, void* stream);
+/* PULL exchange (the default of the sharded pipeline): nothing is pushed over the links and nothing is reduced in the switch.  The
+ * numerator contraction writes this rank's (F, K) partial straight into its symmetric buffer and its last CTA adds 1 to every rank's
+ * arrival counter (device-scope fence + relaxed red: the published data is local, peers fetch it through this GPU's L2); then
+ *   two_shot = 0: every rank's W update reads all ranks' partials with plain peer loads, added in rank order;
+ *   two_shot = 1: each rank first sums its 1 / world slice that way into its own buffer, signals, and the W updates fetch each word
+ *                 from its owner -- one numerator in each direction per GPU for any world size.
+ * Row sums of G are read from every rank's slots.  bases: HOST array of `world` device pointers, every rank's buffer as mapped in
+ * this process (gccnmf_klnmf_pull_buffer_floats(F, layout_T2, K) floats each, zero before the first iteration; layout_T2 = the
+ * largest 2T over the ranks; epoch = iterations earlier runs executed on this buffer: the arrival counters keep counting).  Needs the
+ * cluster-reduced numerator contraction (GCCNMF_ERR_UNSUPPORTED otherwise). */
+GCCNMF_API int64_t gccnmf_klnmf_pull_buffer_floats(int F, int layout_T2, int K);
+/* 1 when gccnmf_klnmf_step_pull covers this shard shape on this device, else 0 (every rank must agree before using it). */
+GCCNMF_API int gccnmf_klnmf_pull_supported(gccnmf_handle* h, int F, int T2, int K);
+GCCNMF_API int gccnmf_klnmf_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K,
+                           float sparsity_alpha, float epsilon, int iteration, int64_t epoch, int rank, int world,
+                           void* const* bases, int layout_T2, int two_shot, void* workspace, size_t workspace_bytes, void* stream);
 GCCNMF_API int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done,
                      void* workspace, size_t workspace_bytes, void* stream);
 

@@ -40,14 +40,20 @@ def main():
     # one 8-slot record per launch of the exchange kernels: PACK (row sums [+ numerator] -> symmetric buffer, arrival signal),
     # RB (two-shot: slice reduction + multicast), AP (W update)
     extra = {'fused': ['AP'], 'stepwise-no-exchange': ['PACK', 'AP'], 'two-shot': ['PACK', 'RB', 'AP'], 'one-shot': ['PACK', 'AP'],
-             'nccl': ['PACK', 'AP']}
+             'nccl': ['PACK', 'AP'], 'pull-one-shot': ['AP'], 'pull-two-shot': ['RB', 'AP']}
     modes = ['fused', 'stepwise-no-exchange']
     if world > 1:
-        modes += ['two-shot', 'one-shot', 'nccl']
+        modes += ['pull-one-shot', 'pull-two-shot', 'two-shot', 'one-shot', 'nccl']
     iters = 24
     ghz = 1.75        # SM clock under this load (cycles per ns), from clock64 / globaltimer of whole CTAs
     for mode in modes:
-        mm = None
+        mm = px = None
+        if mode.startswith('pull'):
+            px = gd.PullExchange.create(h.lib, F, T2, K, h.device, None, two_shot=(mode == 'pull-two-shot'))
+            if px is None or h.lib.gccnmf_klnmf_pull_supported(h.h, F, T2, K) != 1:
+                if rank == 0:
+                    print(mode, ': not available on this box')
+                continue
         if mode == 'two-shot':
             mm = gd.MultimemTwoShot.create(F * K + K, h.device, None)
         elif mode == 'one-shot':
@@ -69,6 +75,8 @@ def main():
                 h.klnmf_end(W, H, n)
             elif mode == 'nccl':
                 gd.klnmf_sharded(h, comm, V, W, H, n, 0.0, 1e-16, numer)
+            elif px is not None:
+                gd.klnmf_sharded_pull(h, px, V, W, H, n, 0.0, 1e-16)
             else:
                 gd.klnmf_sharded_multimem(h, mm, V, W, H, n, 0.0, 1e-16)
             return W
@@ -123,7 +131,12 @@ def main():
             if 'PACK' in extra[mode]:
                 tl['pack start'] = med(lambda i: recs[i, 'PACK'][0] - ends[i, 'G4'])
                 tl['pack signalled'] = med(lambda i: recs[i, 'PACK'][7] - ends[i, 'G4'])
-            if 'RB' in extra[mode]:
+            if 'RB' in extra[mode] and mode == 'pull-two-shot':
+                tl['rb start'] = med(lambda i: recs[i, 'RB'][0] - ends[i, 'G4'])
+                tl['rb arrivals seen'] = med(lambda i: recs[i, 'RB'][1] - ends[i, 'G4'])
+                tl['rb cta0 summed'] = med(lambda i: recs[i, 'RB'][2] - ends[i, 'G4'])
+                tl['rb signalled'] = med(lambda i: recs[i, 'RB'][7] - ends[i, 'G4'])
+            elif 'RB' in extra[mode]:
                 tl['rb start'] = med(lambda i: recs[i, 'RB'][0] - ends[i, 'G4'])
                 tl['rb arrivals seen'] = med(lambda i: recs[i, 'RB'][1] - ends[i, 'G4'])
                 tl['rb cta0 stored'] = med(lambda i: recs[i, 'RB'][2] - ends[i, 'G4'])
