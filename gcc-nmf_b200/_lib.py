@@ -56,7 +56,7 @@ SIGNATURES = {
     'gccnmf_klnmf_pull_buffer_floats': (c_int64, [c_int, c_int, c_int]),
     'gccnmf_klnmf_pull_supported': (c_int, [_H, c_int, c_int, c_int]),
     'gccnmf_klnmf_step_pull': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, c_int, c_int64, c_int, c_int, ctypes.POINTER(ctypes.c_void_p), c_int, c_int,
-                                       _P, c_size_t, _S]),
+                                       c_int, _P, c_size_t, _S]),
     'gccnmf_klnmf_step_multimem2': (c_int, [_H, _P, c_int, c_int, _P, _P, c_int, c_float, c_float, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                             ctypes.c_uint32, _P, c_size_t, _S]),
     'gccnmf_klnmf_end': (c_int, [_H, c_int, c_int, _P, _P, c_int, c_int, _P, c_size_t, _S]),
@@ -330,13 +330,14 @@ class Handle(object):
                                                         int(counters_multicast_ptr), int(arrivals_expected) & 0xFFFFFFFF, _ptr(ws), ws.numel(),
                                                         self.stream))
 
-    def klnmf_step_pull(self, V, W, H, iteration, epoch, rank, world, bases, layout_T2, two_shot, sparsity_alpha=0.0, epsilon=1e-16):
+    def klnmf_step_pull(self, V, W, H, iteration, epoch, rank, world, bases, layout_T2, two_shot, direct, sparsity_alpha=0.0, epsilon=1e-16):
         """One sharded iteration with the pull exchange (see gccnmf_klnmf_step_pull); bases: ctypes array of world void pointers."""
         F, T2 = V.shape
         K = W.shape[1]
         ws = self._klnmf_ws(F, T2, K)
         self.check(self.lib.gccnmf_klnmf_step_pull(self.h, _ptr(V), F, T2, _ptr(W), _ptr(H), K, float(sparsity_alpha), float(epsilon), int(iteration),
-                                                   int(epoch), int(rank), int(world), bases, int(layout_T2), int(two_shot), _ptr(ws), ws.numel(), self.stream))
+                                                   int(epoch), int(rank), int(world), bases, int(layout_T2), int(two_shot), int(direct), _ptr(ws), ws.numel(),
+                                                   self.stream))
 
     def klnmf_end(self, W, H, iterations_done):
         F, K = W.shape

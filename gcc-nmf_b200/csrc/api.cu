@@ -90,6 +90,7 @@ int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
   if (strcmp(name, "gemm_streaming") == 0) { h->gemm_streaming = value; return GCCNMF_OK; }
   if (strcmp(name, "argmax_persistent") == 0) { h->argmax_persistent = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "w_cluster_reduce") == 0) { h->w_cluster_reduce = value != 0; return GCCNMF_OK; }
+  if (strcmp(name, "pull_force_pack") == 0) { h->pull_force_pack = value; return GCCNMF_OK; }
   if (strcmp(name, "mc_light_signal") == 0) { h->mc_light_signal = value; return GCCNMF_OK; }
   if (strcmp(name, "l2_persist") == 0) { h->l2_persist = value; return GCCNMF_OK; }
   if (strcmp(name, "gemm_preload") == 0) { h->gemm_preload = value; return GCCNMF_OK; }

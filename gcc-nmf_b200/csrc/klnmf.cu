@@ -263,8 +263,9 @@ int gccnmf_klnmf_tma_l2_window(gccnmf_handle* h, int F, int T2, int K, bool enab
 int64_t gccnmf_klnmf_tma_pull_floats(int F, int layout_T2, int K);
 bool gccnmf_klnmf_tma_pull_supported(gccnmf_handle* h, int F, int T2, int K);
 int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float alpha, float eps, int iteration,
-                               int64_t epoch, int rank, int world, float* const* bases, int layout_T2, int two_shot, void* workspace,
-                               size_t workspace_bytes, void* stream);
+                               int64_t epoch, int rank, int world, float* const* bases, int layout_T2, int two_shot, int want_direct,
+                               void* workspace, size_t workspace_bytes, void* stream);
+bool gccnmf_klnmf_tma_pull_direct(gccnmf_handle* h, int F, int T2, int K);
 
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tma_supported(F, T2, K); }
 
@@ -403,12 +404,13 @@ int64_t gccnmf_klnmf_pull_buffer_floats(int F, int layout_T2, int K) {
 
 int gccnmf_klnmf_pull_supported(gccnmf_handle* h, int F, int T2, int K) {
   GCCNMF_ENTER(h);
-  return (F > 0 && T2 > 0 && K > 0 && use_tc(h, F, T2, K) && gccnmf_klnmf_tma_pull_supported(h, F, T2, K)) ? 1 : 0;
+  if (!(F > 0 && T2 > 0 && K > 0 && use_tc(h, F, T2, K) && gccnmf_klnmf_tma_pull_supported(h, F, T2, K))) return 0;
+  return gccnmf_klnmf_tma_pull_direct(h, F, T2, K) ? 2 : 1;
 }
 
 int gccnmf_klnmf_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float sparsity_alpha, float epsilon,
-                           int iteration, int64_t epoch, int rank, int world, void* const* bases, int layout_T2, int two_shot, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+                           int iteration, int64_t epoch, int rank, int world, void* const* bases, int layout_T2, int two_shot, int direct,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   GCCNMF_ENTER(h);
   if (int st = check_dims(h, F, T2, K)) return st;
   GCCNMF_REQUIRE(h, bases && iteration >= 0 && epoch >= 0 && world >= 1 && world <= 8 && rank >= 0 && rank < world, "klnmf_step_pull: bad arguments");
@@ -417,7 +419,7 @@ int gccnmf_klnmf_step_pull(gccnmf_handle* h, const float* V, int F, int T2, floa
   if (!workspace || workspace_bytes < gccnmf_klnmf_workspace_bytes(F, T2, K))
     return gccnmf_fail(h, GCCNMF_ERR_WORKSPACE, "klnmf workspace too small: need %zu bytes", gccnmf_klnmf_workspace_bytes(F, T2, K));
   return gccnmf_klnmf_tma_step_pull(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, iteration, epoch, rank, world, reinterpret_cast<float* const*>(bases),
-                                    layout_T2, two_shot, workspace, workspace_bytes, stream);
+                                    layout_T2, two_shot, direct, workspace, workspace_bytes, stream);
 }
 
 int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done, void* workspace,

@@ -411,7 +411,8 @@ __global__ void tma_finish_h_kernel(const float* __restrict__ HT, int T2, int K,
 // complete" -- so no host-launched barrier sits between the numerator and the W update (tma_apply_w_kernel<true> waits on its own
 // copy of the counter).
 __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t n, const float* rowsum, int rowsum_slots, int K, float* numer,
-                                      unsigned* done_counter, unsigned* mc_counter, int light_signal, unsigned long long* stamp) {
+                                      unsigned* done_counter, unsigned* mc_counter, int light_signal, unsigned long long* stamp,
+                                      tgemm::PeerSignal peers_signal) {
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
   if (stamp && blockIdx.x == 0 && threadIdx.x == 0) stamp[0] = tgemm::globaltimer_ns();
@@ -426,7 +427,7 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
     for (int j = 0; j < rowsum_slots; ++j) s += rowsum[(int64_t)j * K + (i - n)];
     numer[i] = s;
   }
-  if (mc_counter) {
+  if (mc_counter || peers_signal.world > 0) {
     // One device-scope fence per CTA (cumulative over the CTA's stores through the barrier) and ONE system-scope release by the
     // last CTA: a __threadfence_system() per thread (MEMBAR.SC.SYS x 500 k) cost ~20 us per iteration at 2 ranks.
     __syncthreads();
@@ -436,7 +437,9 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
       if (prev == gridDim.x - 1) {
         __threadfence();                        // acquire side of the CTA count
         *done_counter = 0;                      // ready for the next iteration (this kernel is never concurrent with itself)
-        if (light_signal) {
+        if (peers_signal.world > 0) {
+          tgemm::signal_peers(peers_signal);     // pull exchange: relaxed adds to every rank's counter (see tgemm::PeerSignal)
+        } else if (light_signal) {
           // The data this signal publishes lies in THIS GPU's memory and peers fetch it over NVLink through this GPU's L2: a
           // device-scope fence has already put it there, so the arrival is sent relaxed (no MEMBAR.SYS, which costs microseconds).
           asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
@@ -759,24 +762,26 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
 }
 
 // ---- pull exchange (gccnmf_klnmf_step_pull).  Layout of every rank's symmetric buffer, in floats:
-//   [numerator F*K] x 2 (iteration parity) | [row-sum slots max_slots*K] x 2 | reduced F*K | 64 floats: arrival counters (u32) 0, 1
+//   [numerator F*K + K (packed row sums)] x 2 (iteration parity) | [row-sum slots max_slots*K] x 2 | reduced F*K | 64 floats: arrival
+//   counters (u32) 0, 1.  With the cluster-reduced numerator contraction the contraction writes the numerator and G2's epilogue the
+//   row-sum slots directly; otherwise the pack kernel sums the k-split slabs and the slots into [F*K + K].
 struct PullLayout { int64_t numer[2], rowsum[2], reduced, counters, total; };
 PullLayout pull_layout(int F, int T2, int K) {
   PullLayout l;
   const int64_t fk = (int64_t)F * K, rs = (int64_t)max_rowsum_slots(T2) * K;
-  l.numer[0] = 0; l.numer[1] = fk;
-  l.rowsum[0] = 2 * fk; l.rowsum[1] = 2 * fk + rs;
-  l.reduced = 2 * fk + 2 * rs;
+  l.numer[0] = 0; l.numer[1] = fk + K;
+  l.rowsum[0] = 2 * (fk + K); l.rowsum[1] = l.rowsum[0] + rs;
+  l.reduced = l.rowsum[1] + rs;
   l.counters = l.reduced + fk;
   l.total = l.counters + 64;
   return l;
 }
-PeerSet pull_peers(const float* const* bases, int world, const PullLayout& l, int parity, int F, int K) {
+PeerSet pull_peers(const float* const* bases, int world, const PullLayout& l, int parity, int F, int K, bool packed) {
   PeerSet ps{};
   ps.world = world;
   for (int r = 0; r < world; ++r) {
     ps.numer[r] = bases[r] + l.numer[parity];
-    ps.rowsum[r] = bases[r] + l.rowsum[parity];
+    ps.rowsum[r] = packed ? bases[r] + l.numer[parity] + (int64_t)F * K : bases[r] + l.rowsum[parity];
     ps.reduced[r] = bases[r] + l.reduced;
   }
   const int64_t n4 = (int64_t)F * K / 4;
@@ -791,39 +796,56 @@ tgemm::PeerSignal pull_signal(float* const* bases, int world, const PullLayout& 
 }
 
 int64_t gccnmf_klnmf_tma_pull_floats(int F, int layout_T2, int K) { return pull_layout(F, layout_T2, K).total; }
-bool gccnmf_klnmf_tma_pull_supported(gccnmf_handle* h, int F, int T2, int K) { return w_cluster_reduce(h, make_plan(h, F, T2, K), F, K); }
+bool gccnmf_klnmf_tma_pull_supported(gccnmf_handle* h, int F, int T2, int K) { (void)h; return gccnmf_klnmf_tma_supported(F, T2, K); }
+bool gccnmf_klnmf_tma_pull_direct(gccnmf_handle* h, int F, int T2, int K) { return w_cluster_reduce(h, make_plan(h, F, T2, K), F, K) && !h->pull_force_pack; }
 
 // One sharded iteration with the pull exchange; `bases`: host array of `world` device pointers, each rank's symmetric buffer as mapped
 // in THIS process (bases[rank] is the local one).
 int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float alpha, float eps, int iteration,
-                               int64_t epoch, int rank, int world, float* const* bases, int layout_T2, int two_shot, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               int64_t epoch, int rank, int world, float* const* bases, int layout_T2, int two_shot, int want_direct,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   TMA_CARVE_OR_FAIL(w);
   const Plan p = make_plan(h, F, T2, K);
-  if (!w_cluster_reduce(h, p, F, K) || world > 8)
-    return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_pull: needs the cluster-reduced numerator contraction and <= 8 ranks");
+  if (world > 8) return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_pull: at most 8 ranks");
   // (the layout is the same on every rank: built from the largest shard; a rank with fewer row-sum slots leaves the others zero)
   const PullLayout l = pull_layout(F, layout_T2, K);
-  const int all_slots = max_rowsum_slots(layout_T2);
   if (layout_T2 < T2) return gccnmf_fail(h, GCCNMF_ERR_INVALID_ARGUMENT, "klnmf_step_pull: layout_T2 %d < T2 %d", layout_T2, T2);
   // epoch: iterations of earlier runs on this buffer (the arrival counters keep counting; buffers alternate by global parity)
   const int parity = (int)((epoch + iteration) & 1);
   const unsigned expected = (unsigned)((uint64_t)world * (uint64_t)(epoch + iteration + 1));
   float* local = bases[rank];
   const unsigned* counters_local = reinterpret_cast<const unsigned*>(local + l.counters);
-  // G1, G2 (row sums of G straight into the symmetric buffer), G3, G4 (numerator straight into the symmetric buffer; its last CTA
-  // signals every rank)
-  h->xchg_rowsum = local + l.rowsum[parity];
-  h->xchg_numer = local + l.numer[parity];
   const tgemm::PeerSignal sig0 = pull_signal(bases, world, l, 0);
-  h->xchg_world = world;
-  for (int r = 0; r < world; ++r) h->xchg_counters[r] = sig0.counters[r];
-  h->xchg_done = w.done + 2;
-  int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, alpha, eps, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0, stream);
-  if (!st) st = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, h->xchg_numer, stream);
-  h->xchg_rowsum = nullptr; h->xchg_numer = nullptr; h->xchg_world = 0; h->xchg_done = nullptr;
-  if (st) return st;
-  const PeerSet peers = pull_peers(bases, world, l, parity, F, K);
+  // direct = the numerator contraction sums its k-splits inside clusters (when every cluster of the launch is resident at once): it
+  // writes the numerator, and G2's epilogue the row-sum slots, straight into the symmetric buffer, and its last CTA signals the ranks.
+  // Otherwise the pack kernel sums the k-split slabs and the row-sum slots into the buffer and signals.
+  // Every rank must take the same branch (the readers' addresses depend on it): the caller passes the agreed choice.
+  const bool direct = want_direct != 0;
+  if (direct && !(w_cluster_reduce(h, p, F, K) && !h->pull_force_pack))
+    return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_pull: direct form asked for, but the cluster-reduced contraction is unavailable here");
+  const int rs_slots = direct ? max_rowsum_slots(layout_T2) : 1;
+  int st = 0;
+  if (direct) {
+    h->xchg_rowsum = local + l.rowsum[parity];
+    h->xchg_numer = local + l.numer[parity];
+    h->xchg_world = world;
+    for (int r = 0; r < world; ++r) h->xchg_counters[r] = sig0.counters[r];
+    h->xchg_done = w.done + 2;
+    st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, alpha, eps, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0, stream);
+    if (!st) st = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, h->xchg_numer, stream);
+    h->xchg_rowsum = nullptr; h->xchg_numer = nullptr; h->xchg_world = 0; h->xchg_done = nullptr;
+    if (st) return st;
+  } else {
+    st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, alpha, eps, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0, stream);
+    if (!st) st = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, nullptr, stream);
+    if (st) return st;
+    const int64_t n = (int64_t)F * K;
+    const bool summed = w_cluster_reduce(h, p, F, K);       // (pull_force_pack: the contraction left one slab, not p.w.splits)
+    if (int e = launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)((n + K + 255) / 256)), dim3(256), 0, stream, h->nmf_pdl,
+                          dim3(1, 1, 1), (const float*)w.partial, summed ? 1 : p.w.splits, n, (const float*)w.rowsum_part, p.rowsum_slots, K,
+                          local + l.numer[parity], w.done, (unsigned*)nullptr, 0, next_stamp(h), sig0)) return e;
+  }
+  const PeerSet peers = pull_peers(bases, world, l, parity, F, K, !direct);
   const int64_t n4 = (int64_t)F * K / 4;
   if (two_shot) {
     const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (peers.chunk4 + 255) / 256));
@@ -833,10 +855,10 @@ int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, 
   const dim3 grid((K + kApplyAtoms - 1) / kApplyAtoms, w.row_blocks), block(32, 8);
   if (two_shot)
     return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<kApplyPullOwner>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w,
-                     (const float*)nullptr, 1, (const float*)nullptr, all_slots, F, K, w.sumsq_part, w.colsum, counters_local + 1, expected,
+                     (const float*)nullptr, 1, (const float*)nullptr, rs_slots, F, K, w.sumsq_part, w.colsum, counters_local + 1, expected,
                      next_stamp(h), peers);
   return launch_ex(h, "tma_apply_w_kernel", tma_apply_w_kernel<kApplyPull>, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w,
-                   (const float*)nullptr, world, (const float*)nullptr, all_slots, F, K, w.sumsq_part, w.colsum, counters_local, expected,
+                   (const float*)nullptr, world, (const float*)nullptr, rs_slots, F, K, w.sumsq_part, w.colsum, counters_local, expected,
                    next_stamp(h), peers);
 }
 
@@ -905,7 +927,7 @@ int gccnmf_klnmf_tma_pack_numer_mc(gccnmf_handle* h, int F, int T2, int K, float
   const bool in_place = w_cluster_reduce(h, p, F, K);
   return launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)(((in_place ? 0 : n) + K + 255) / 256)), dim3(256), 0, stream,
                    h->nmf_pdl, dim3(1, 1, 1), in_place ? (const float*)nullptr : (const float*)w.partial, p.w.splits, n, (const float*)w.rowsum_part,
-                   p.rowsum_slots, K, numer, w.done, mc_counter, h->mc_light_signal, next_stamp(h));
+                   p.rowsum_slots, K, numer, w.done, mc_counter, h->mc_light_signal, next_stamp(h), tgemm::PeerSignal{});
 }
 int gccnmf_klnmf_tma_pack_numer(gccnmf_handle* h, int F, int T2, int K, float* numer, void* workspace, size_t workspace_bytes, void* stream) {
   return gccnmf_klnmf_tma_pack_numer_mc(h, F, T2, K, numer, nullptr, workspace, workspace_bytes, stream);

@@ -188,6 +188,7 @@ class PullExchange(object):
         self.buffer, self.handle, self.bases, self.rank, self.world = buffer, handle, bases, rank, world
         self.layout_T2, self.two_shot = layout_T2, two_shot
         self.epoch = 0                  # iterations executed on this buffer so far (identical on every rank)
+        self.direct = False             # agreed by the caller: every rank supports the direct form (gccnmf_klnmf_pull_supported == 2)
 
     @classmethod
     def create(cls, lib, F, layout_T2, K, device, group, two_shot=None):
@@ -217,7 +218,11 @@ class PullExchange(object):
             if two_shot is None:
                 two_shot = world >= 4
             return cls(t, hdl, bases, rank, world, layout_T2, bool(two_shot))
-        except Exception:
+        except Exception as e:                                     # noqa: BLE001  (no symmetric memory / no peer mapping: the caller falls back)
+            if os.environ.get('GCCNMF_DEBUG_EXCHANGE'):
+                import traceback
+                traceback.print_exc()
+                print('PullExchange.create failed:', repr(e), flush=True)
             return None
 
 
@@ -225,7 +230,7 @@ def klnmf_sharded_pull(ops, px, V_s, W, H_s, numIterations, sparsityAlpha, epsil
     """klnmf_sharded with the pull exchange (gccnmf_klnmf_step_pull): one C call per iteration, five or six kernels, no host step."""
     ops.klnmf_begin(V_s, W, H_s)
     for it in range(numIterations):
-        ops.klnmf_step_pull(V_s, W, H_s, it, px.epoch, px.rank, px.world, px.bases, px.layout_T2, px.two_shot, sparsity_alpha=sparsityAlpha,
+        ops.klnmf_step_pull(V_s, W, H_s, it, px.epoch, px.rank, px.world, px.bases, px.layout_T2, px.two_shot, px.direct, sparsity_alpha=sparsityAlpha,
                             epsilon=epsilon)
     px.epoch += numIterations
     ops.klnmf_end(W, H_s, numIterations)
@@ -345,14 +350,16 @@ class ShardedGCCNMFPipeline(object):
                 layout_T2 = int(self._all_max(T2))
                 px = PullExchange.create(self.h.lib, self.F, layout_T2, self.K, self.h.device, self.comm.group,
                                          two_shot={'pull1': False, 'pull2': True}.get(mode))
-                probe_ok = px is not None
-                if probe_ok:                                                  # the library refuses shapes without the cluster-reduced contraction
-                    probe_ok = self.h.lib.gccnmf_klnmf_pull_supported(self.h.h, self.F, T2, self.K) == 1
-                if agree(probe_ok):
+                level = self.h.lib.gccnmf_klnmf_pull_supported(self.h.h, self.F, T2, self.K) if px is not None else 0
+                level = self._all_min(level)                                  # 0 unsupported somewhere, 1 through the pack kernel, 2 direct
+                if level >= 1:
+                    px.direct = level >= 2
                     self.pull = px
-                    self.collective = ('pull exchange, %s: the numerator contraction writes its partial into the symmetric buffer and signals '
-                                       'every rank from its last CTA; %s; no pack pass, no system-scope fence, no NCCL call in the loop' % (
+                    self.collective = ('pull exchange, %s: %s; %s; no system-scope fence, no multimem, no NCCL call in the loop' % (
                                            'two-shot' if px.two_shot else 'one-shot',
+                                           'the numerator contraction writes its partial into the symmetric buffer and signals every rank from its '
+                                           'last CTA' if px.direct else 'the pack kernel sums the k-split slabs into the symmetric buffer and signals '
+                                           'every rank',
                                            'each rank sums its 1/world slice with plain peer loads, the W updates fetch every word from its owner'
                                            if px.two_shot else 'the W update reads every rank\'s partial with plain peer loads, added in rank order'))
                 else:

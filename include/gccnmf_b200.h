@@ -179,13 +179,17 @@ GCCNMF_API int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int
  * Row sums of G are read from every rank's slots.  bases: HOST array of `world` device pointers, every rank's buffer as mapped in
  * this process (gccnmf_klnmf_pull_buffer_floats(F, layout_T2, K) floats each, zero before the first iteration; layout_T2 = the
  * largest 2T over the ranks; epoch = iterations earlier runs executed on this buffer: the arrival counters keep counting).  Needs the
- * cluster-reduced numerator contraction (GCCNMF_ERR_UNSUPPORTED otherwise). */
+ * cluster-reduced numerator contraction for direct = 1 (see gccnmf_klnmf_pull_supported). */
 GCCNMF_API int64_t gccnmf_klnmf_pull_buffer_floats(int F, int layout_T2, int K);
-/* 1 when gccnmf_klnmf_step_pull covers this shard shape on this device, else 0 (every rank must agree before using it). */
+/* 0: gccnmf_klnmf_step_pull does not cover this shard shape on this device; 1: it does, through the pack kernel (k-split slabs
+ * and row-sum slots summed into the symmetric buffer, then the signal); 2: also in the direct form (the numerator contraction sums
+ * its k-splits inside clusters, writes the buffer itself and signals from its last CTA).  `direct` of step_pull must be the same
+ * on every rank: 1 only if every rank answers 2. */
 GCCNMF_API int gccnmf_klnmf_pull_supported(gccnmf_handle* h, int F, int T2, int K);
 GCCNMF_API int gccnmf_klnmf_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K,
                            float sparsity_alpha, float epsilon, int iteration, int64_t epoch, int rank, int world,
-                           void* const* bases, int layout_T2, int two_shot, void* workspace, size_t workspace_bytes, void* stream);
+                           void* const* bases, int layout_T2, int two_shot, int direct, void* workspace, size_t workspace_bytes,
+                           void* stream);
 GCCNMF_API int gccnmf_klnmf_end(gccnmf_handle* h, int F, int T2, float* W, float* H, int K, int iterations_done,
                      void* workspace, size_t workspace_bytes, void* stream);
 

@@ -44,15 +44,21 @@ def main():
     modes = ['fused', 'stepwise-no-exchange']
     if world > 1:
         modes += ['pull-one-shot', 'pull-two-shot', 'two-shot', 'one-shot', 'nccl']
+    if os.environ.get('STAMP_MODES'):
+        modes = [m for m in modes if m in os.environ['STAMP_MODES'].split(',')]
     iters = 24
     ghz = 1.75        # SM clock under this load (cycles per ns), from clock64 / globaltimer of whole CTAs
     for mode in modes:
         mm = px = None
         if mode.startswith('pull'):
             px = gd.PullExchange.create(h.lib, F, T2, K, h.device, None, two_shot=(mode == 'pull-two-shot'))
-            if px is None or h.lib.gccnmf_klnmf_pull_supported(h.h, F, T2, K) != 1:
+            sup = h.lib.gccnmf_klnmf_pull_supported(h.h, F, T2, K)
+            if px is not None:
+                px.direct = sup >= 2
+                extra[mode] = (['RB', 'AP'] if px.two_shot else ['AP']) if px.direct else (['PACK', 'RB', 'AP'] if px.two_shot else ['PACK', 'AP'])
+            if px is None or sup < 1:
                 if rank == 0:
-                    print(mode, ': not available on this box')
+                    print(mode, ': not available on this box (buffer %s, supported %s)' % (px is not None, sup))
                 continue
         if mode == 'two-shot':
             mm = gd.MultimemTwoShot.create(F * K + K, h.device, None)
