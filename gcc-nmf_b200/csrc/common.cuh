@@ -30,7 +30,7 @@ struct gccnmf_handle {
   unsigned* xchg_counters[8] = {nullptr};
   int xchg_world = 0;
   int pull_force_pack = 0;       // pull exchange: always go through the pack kernel (diagnostics)
-  int mc_light_signal = 0;       // sharded runs: arrival signal of the numerator pack as device-scope fence + relaxed multimem.red (diagnostics)
+  int mc_light_signal = 1;       // sharded runs: arrival signal of the numerator pack as device-scope fence + relaxed multimem.red (0: MEMBAR.SYS + release)
   int l2_persist = 0;            // KL-NMF loop: launch-attribute L2 access-policy window (persisting) over G^T: 1 = float32 master, 2 = master + planes
   const void* l2_window_base = nullptr;   // set by the KL-NMF loop while it runs
   size_t l2_window_bytes = 0;

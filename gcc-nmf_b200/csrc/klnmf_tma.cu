@@ -416,16 +416,29 @@ __global__ void tma_pack_numer_kernel(const float* partial, int splits, int64_t 
   tgemm::pdl_launch_dependents();
   tgemm::pdl_wait_prior_grids();
   if (stamp && blockIdx.x == 0 && threadIdx.x == 0) stamp[0] = tgemm::globaltimer_ns();
-  // partial == NULL: the numerator itself is already in place (k-splits summed inside clusters by the contraction): row sums only
-  const int64_t i = (partial ? 0 : n) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    float s = partial[i];
-    for (int z = 1; z < splits; ++z) s += partial[(int64_t)z * n + i];
-    numer[i] = s;
-  } else if (i < n + K) {
-    float s = 0.f;
-    for (int j = 0; j < rowsum_slots; ++j) s += rowsum[(int64_t)j * K + (i - n)];
-    numer[i] = s;
+  // partial == NULL: the numerator itself is already in place (k-splits summed inside clusters by the contraction): row sums only.
+  // 16 bytes per thread and matrix, every slab's load of an item in flight before the first add, a few hundred CTAs (grid-stride):
+  // the scalar one-item-per-thread form (2 053 CTAs) took 3.6 us and its completion count 4 more.
+  const int64_t n4 = n >> 2, k4 = K >> 2;
+  const int64_t first = partial ? 0 : n4, total = n4 + k4;
+  for (int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      float4 v[kMaxSplits];
+#pragma unroll
+      for (int z = 0; z < kMaxSplits; ++z)
+        v[z] = z < splits ? __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)z * n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc = v[0];
+#pragma unroll
+      for (int z = 1; z < kMaxSplits; ++z)
+        if (z < splits) { acc.x += v[z].x; acc.y += v[z].y; acc.z += v[z].z; acc.w += v[z].w; }
+    } else {
+      for (int j = 0; j < rowsum_slots; ++j) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(rowsum + (int64_t)j * K) + (i - n4));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    reinterpret_cast<float4*>(numer)[i] = acc;
   }
   if (mc_counter || peers_signal.world > 0) {
     // One device-scope fence per CTA (cumulative over the CTA's stores through the barrier) and ONE system-scope release by the
@@ -841,7 +854,7 @@ int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, 
     if (st) return st;
     const int64_t n = (int64_t)F * K;
     const bool summed = w_cluster_reduce(h, p, F, K);       // (pull_force_pack: the contraction left one slab, not p.w.splits)
-    if (int e = launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)((n + K + 255) / 256)), dim3(256), 0, stream, h->nmf_pdl,
+    if (int e = launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)std::min<int64_t>(((n + K) / 4 + 255) / 256, 2 * h->sm_count)), dim3(256), 0, stream, h->nmf_pdl,
                           dim3(1, 1, 1), (const float*)w.partial, summed ? 1 : p.w.splits, n, (const float*)w.rowsum_part, p.rowsum_slots, K,
                           local + l.numer[parity], w.done, (unsigned*)nullptr, 0, next_stamp(h), sig0)) return e;
   }
@@ -925,7 +938,8 @@ int gccnmf_klnmf_tma_pack_numer_mc(gccnmf_handle* h, int F, int T2, int K, float
   const int64_t n = (int64_t)F * K;
   // (pairs with gccnmf_klnmf_tma_partial_W_to(..., numer): with cluster-reduced k-splits the numerator is already in `numer`)
   const bool in_place = w_cluster_reduce(h, p, F, K);
-  return launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)(((in_place ? 0 : n) + K + 255) / 256)), dim3(256), 0, stream,
+  const int64_t items = ((in_place ? 0 : n) + K) / 4;
+  return launch_ex(h, "tma_pack_numer_kernel", tma_pack_numer_kernel, dim3((unsigned)std::min<int64_t>((items + 255) / 256, 2 * h->sm_count)), dim3(256), 0, stream,
                    h->nmf_pdl, dim3(1, 1, 1), in_place ? (const float*)nullptr : (const float*)w.partial, p.w.splits, n, (const float*)w.rowsum_part,
                    p.rowsum_slots, K, numer, w.done, mc_counter, h->mc_light_signal, next_stamp(h), tgemm::PeerSignal{});
 }

@@ -341,15 +341,18 @@ class ShardedGCCNMFPipeline(object):
             self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
         if int(flag.item()) == 0:
             self.h.set_option('force_simt_nmf', 1)
-        elif self.comm.world > 1 and os.environ.get('GCCNMF_COLLECTIVE', 'pull') != 'nccl':
-            # exchange fused into the kernels (all ranks must agree that it is available).  GCCNMF_COLLECTIVE: pull (default; pull1 /
-            # pull2 force the one- / two-shot form), multimem (two-shot inside the switch), multimem1 (one-shot inside the switch), nccl
-            mode = os.environ.get('GCCNMF_COLLECTIVE', 'pull')
+        elif self.comm.world > 1 and os.environ.get('GCCNMF_COLLECTIVE', 'auto') != 'nccl':
+            # exchange fused into the kernels (all ranks must agree that it is available).  GCCNMF_COLLECTIVE: auto (default: measured at
+            # 2 ranks, DESIGN.md section 5 -- one-shot pull for 2 ranks, whose traffic grows with the world size, two-shot inside the
+            # switch from 3 ranks up), pull1 / pull2 (one- / two-shot pull), multimem / multimem1 (two- / one-shot inside the switch), nccl
+            mode = os.environ.get('GCCNMF_COLLECTIVE', 'auto')
+            if mode == 'auto':
+                mode = 'pull1' if self.comm.world == 2 else 'multimem' 
             agree = lambda ok: int(self._all_min(1 if ok else 0)) == 1       # noqa: E731
             if mode.startswith('pull'):
                 layout_T2 = int(self._all_max(T2))
                 px = PullExchange.create(self.h.lib, self.F, layout_T2, self.K, self.h.device, self.comm.group,
-                                         two_shot={'pull1': False, 'pull2': True}.get(mode))
+                                         two_shot={'pull1': False, 'pull2': True}.get(mode))     # ('pull': by world size)
                 level = self.h.lib.gccnmf_klnmf_pull_supported(self.h.h, self.F, T2, self.K) if px is not None else 0
                 level = self._all_min(level)                                  # 0 unsupported somewhere, 1 through the pack kernel, 2 direct
                 if level >= 1:

@@ -26,10 +26,6 @@ except Exception as e:
     print('bench parse failed', e)
 PY
 if [ "$N" = "2" ]; then
-  GCCNMF_COLLECTIVE=multimem1 timeout 900 $TR --master-port 29523 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2m${N}_bench_oneshot.json 2> gpurun_out/r2m${N}_bench_oneshot.err
-  python -c "
-import json
-d=json.loads(open('gpurun_out/r2m2_bench_oneshot.json').read().strip().splitlines()[-1]); print('bench one-shot value', d['value'], d['stage_ms']['nmf'], d.get('collective'))" >> $S 2>&1
   GCCNMF_COLLECTIVE=nccl timeout 900 $TR --master-port 29522 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2m${N}_bench_nccl.json 2> gpurun_out/r2m${N}_bench_nccl.err
   echo "bench nccl rc=$?" >> $S
   python -c "
