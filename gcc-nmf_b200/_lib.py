@@ -467,8 +467,16 @@ class Handle(object):
 _default_handles = {}
 
 
-def default_handle(device=0):
-    """Process-wide handle per device (created lazily; raises without a GPU)."""
+def default_handle(device=None):
+    """Process-wide handle per device (created lazily; raises without a GPU).  device None: the reference's functions take no device
+    argument -- $GCCNMF_DEVICE if set, else torch's current device (what a torchrun rank selected with torch.cuda.set_device)."""
+    if device is None:
+        env = os.environ.get('GCCNMF_DEVICE')
+        if env is not None:
+            device = int(env)
+        else:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     h = _default_handles.get(device)
     if h is None:
         h = _default_handles[device] = Handle(device)

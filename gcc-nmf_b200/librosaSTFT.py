@@ -25,7 +25,7 @@ def _window_vector(window, n_fft, scale=1.0):
     return np.ascontiguousarray(w, dtype=np.float64)
 
 
-def stft(y, n_fft=2048, hop_length=None, win_length=None, window=None, center=True, dtype=np.complex64, device=0):
+def stft(y, n_fft=2048, hop_length=None, win_length=None, window=None, center=True, dtype=np.complex64, device=None):
     """gccNMF/librosaSTFT.py:20-181 -> (1 + n_fft/2, T) complex64, conjugated like :179."""
     if win_length is None:
         win_length = n_fft
@@ -50,7 +50,7 @@ def stft(y, n_fft=2048, hop_length=None, win_length=None, window=None, center=Tr
     return X[0].cpu().numpy().astype(dtype, copy=False)
 
 
-def istft(stft_matrix, hop_length=None, win_length=None, window=None, center=True, dtype=np.float32, device=0):
+def istft(stft_matrix, hop_length=None, win_length=None, window=None, center=True, dtype=np.float32, device=None):
     """gccNMF/librosaSTFT.py:183-286 -> float32 signal (centre-trimmed by default like :283-284)."""
     stft_matrix = np.asarray(stft_matrix)
     n_fft = 2 * (stft_matrix.shape[0] - 1)
