@@ -266,6 +266,7 @@ int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, 
                                int64_t epoch, int rank, int world, float* const* bases, int layout_T2, int two_shot, int want_direct,
                                void* workspace, size_t workspace_bytes, void* stream);
 bool gccnmf_klnmf_tma_pull_direct(gccnmf_handle* h, int F, int T2, int K);
+bool gccnmf_klnmf_tma_pull_fused_ok(gccnmf_handle* h, int F, int K);
 
 static bool use_tc(const gccnmf_handle* h, int F, int T2, int K) { return !h->force_simt_nmf && gccnmf_klnmf_tma_supported(F, T2, K); }
 
@@ -388,7 +389,10 @@ int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int F, int T2,
   return gccnmf_klnmf_tma_apply_W_mc(h, F, T2, W, K, reduced_local, false, counters_local + 1, arrivals_expected, workspace, workspace_bytes, stream);
 }
 
-// PULL exchange: nothing is pushed over the links and nothing is reduced in the switch.  The numerator contraction writes this rank's
+// PULL exchange (two_shot: 0 one-shot, 1 two-shot, 2 inside the W update): nothing is pushed over the links and nothing is reduced in
+// the switch.  Form 2: the W-update CTA that owns a tile sums this rank's k-split slabs for it, publishes the tile, flags it on every
+// rank, waits for the same tile of the other ranks and reads them -- no pack kernel, no kernel boundary inside the exchange.  Forms
+// 0 / 1:  The numerator contraction writes this rank's
 // (F, K) partial straight into its symmetric buffer and its last CTA adds 1 to every rank's arrival counter; then either every rank's
 // W update reads all ranks' partials with plain peer loads and adds them in rank order (two_shot = 0: (world - 1) numerators inbound
 // per GPU), or each rank first sums its 1 / world slice the same way into its own buffer and the W updates fetch each word from its
@@ -405,7 +409,7 @@ int64_t gccnmf_klnmf_pull_buffer_floats(int F, int layout_T2, int K) {
 int gccnmf_klnmf_pull_supported(gccnmf_handle* h, int F, int T2, int K) {
   GCCNMF_ENTER(h);
   if (!(F > 0 && T2 > 0 && K > 0 && use_tc(h, F, T2, K) && gccnmf_klnmf_tma_pull_supported(h, F, T2, K))) return 0;
-  return gccnmf_klnmf_tma_pull_direct(h, F, T2, K) ? 2 : 1;
+  return 1 | (gccnmf_klnmf_tma_pull_direct(h, F, T2, K) ? 2 : 0) | (gccnmf_klnmf_tma_pull_fused_ok(h, F, K) ? 4 : 0);
 }
 
 int gccnmf_klnmf_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K, float sparsity_alpha, float epsilon,

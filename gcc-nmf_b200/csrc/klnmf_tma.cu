@@ -371,6 +371,141 @@ tma_apply_w_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, 
   if (stamping) stamp[7] = tgemm::globaltimer_ns();
 }
 
+// W update with the cross-rank exchange INSIDE it, tile by tile (frame-sharded runs, gccnmf_klnmf_step_pull form 2): the CTA that
+// owns a 32 x 128 tile of U sums this rank's k-split slabs for that tile, writes the packed tile into this rank's symmetric buffer and
+// adds 1 to the tile's flag on every rank (device-scope fence + relaxed red: the published data is local, peers fetch it through this
+// GPU's L2); it then waits until its own flag shows one arrival per rank -- the same-tile CTAs of the other ranks, all resident: the
+// grid is one wave -- reads their packed tiles and every rank's row-sum slots with plain peer loads, adds in rank order and updates U.
+// No pack kernel, no slice-reduction kernel, no kernel boundary inside the exchange: five launches per iteration like the single-GPU
+// loop.  Every rank adds the same values in the same order: bit-identical U.
+__global__ void __launch_bounds__(256)
+tma_apply_w_exchange_kernel(float* __restrict__ U, bf16* __restrict__ Up, int64_t plane, const float* __restrict__ partial, int splits, int rowsum_slots,
+                            int F, int K, float* __restrict__ sumsq_part, float* __restrict__ colsum_part, PeerSet peers, int me, float* my_numer,
+                            tgemm::PeerSignal flags, unsigned arrivals_expected, unsigned long long* stamp) {
+  __shared__ float4 part[2][8][32];
+  tgemm::pdl_launch_dependents();
+  tgemm::pdl_wait_prior_grids();
+  const int c = threadIdx.x, g = threadIdx.y;
+  const bool first = c == 0 && g == 0;
+  const bool stamping = stamp != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && first;
+  if (stamping) stamp[0] = tgemm::globaltimer_ns();
+  const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+  const int k = blockIdx.x * kApplyAtoms + 4 * c;
+  const int64_t slab = (int64_t)F * K;
+  const bool active = k < K;
+  float4 numer[kApplyTile / 8], u[kApplyTile / 8];
+  float4 p[kApplyTile / 8][kMaxSplits];
+  // ---- phase A: this rank's tile = sum of its k-split slabs (split order), published in the symmetric buffer
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {
+      const int f = blockIdx.y * kApplyTile + g + 8 * r;
+      numer[r] = u[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < F) {
+        const int64_t i = (int64_t)f * K + k;
+        u[r] = *reinterpret_cast<const float4*>(U + i);
+#pragma unroll
+        for (int z = 0; z < kMaxSplits; ++z)
+          p[r][z] = z < splits ? __ldg(reinterpret_cast<const float4*>(partial + (int64_t)z * slab + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {
+      const int f = blockIdx.y * kApplyTile + g + 8 * r;
+      if (f < F) {
+        numer[r] = p[r][0];
+#pragma unroll
+        for (int z = 1; z < kMaxSplits; ++z)
+          if (z < splits) { numer[r].x += p[r][z].x; numer[r].y += p[r][z].y; numer[r].z += p[r][z].z; numer[r].w += p[r][z].w; }
+        *reinterpret_cast<float4*>(my_numer + (int64_t)f * K + k) = numer[r];
+      }
+    }
+  }
+  __syncthreads();
+  if (first) {
+    __threadfence();
+    for (int r = 0; r < flags.world; ++r)
+      asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(flags.counters[r] + tile_id), "r"(1u) : "memory");
+    if (stamping) stamp[1] = tgemm::globaltimer_ns();
+    // ---- phase B: the same tile of every rank has been published
+    unsigned seen;
+    unsigned long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags.counters[me] + tile_id) : "memory");
+      if (++spins > (1ull << 25)) __trap();     // a lost peer must not hang the box
+    } while ((int)(seen - arrivals_expected) < 0);
+  }
+  __syncthreads();
+  if (stamping) stamp[2] = tgemm::globaltimer_ns();
+  // ---- phase C: the other ranks' tiles and every rank's row sums of G, all loads in flight before the first add
+  float4 rs_part = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    for (int rank = 0; rank < peers.world; ++rank)
+      for (int s = g; s < rowsum_slots; s += 8) {
+        const float4 v = ld_sys_f32x4(peers.rowsum[rank] + (int64_t)s * K + k);
+        rs_part.x += v.x; rs_part.y += v.y; rs_part.z += v.z; rs_part.w += v.w;
+      }
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {
+      const int f = blockIdx.y * kApplyTile + g + 8 * r;
+      if (f < F) {
+        const int64_t i = (int64_t)f * K + k;
+#pragma unroll
+        for (int z = 0; z < kMaxSplits; ++z)
+          p[r][z] = (z < peers.world && z != me) ? ld_sys_f32x4(peers.numer[z] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  part[0][g][c] = rs_part;
+  __syncthreads();
+  float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (active) {
+    rs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 v = part[0][j][c]; rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w; }
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {          // ranks added in rank order (mine from registers)
+      const float4 mine = numer[r];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int z = 0; z < kMaxSplits; ++z)
+        if (z < peers.world) {
+          const float4 v = z == me ? mine : p[r][z];
+          if (z == 0) acc = v;
+          else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        }
+      numer[r] = acc;
+    }
+  }
+  __syncthreads();                                       // part[] is reused below
+  if (stamping) stamp[3] = tgemm::globaltimer_ns();
+  float4 sumsq = make_float4(0.f, 0.f, 0.f, 0.f), csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 8; ++r) {
+      const int f = blockIdx.y * kApplyTile + g + 8 * r;
+      if (f < F) {
+        const int64_t i = (int64_t)f * K + k;
+        const float4 w = make_float4(u[r].x * (numer[r].x / rs.x), u[r].y * (numer[r].y / rs.y), u[r].z * (numer[r].z / rs.z), u[r].w * (numer[r].w / rs.w));
+        *reinterpret_cast<float4*>(U + i) = w;
+        store_planes4(Up + i, plane, w, 4, true);
+        sumsq.x += w.x * w.x; sumsq.y += w.y * w.y; sumsq.z += w.z * w.z; sumsq.w += w.w * w.w;
+        csum.x += w.x; csum.y += w.y; csum.z += w.z; csum.w += w.w;
+      }
+    }
+  }
+  part[0][g][c] = sumsq;
+  part[1][g][c] = csum;
+  __syncthreads();
+  if (g < 2 && active) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 v = part[g][j][c]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    *reinterpret_cast<float4*>((g == 0 ? sumsq_part : colsum_part) + (int64_t)blockIdx.y * K + k) = s;
+  }
+  if (stamping) stamp[7] = tgemm::globaltimer_ns();
+}
+
 // finish: the reference's normalisation (:79-:81), applied once.  c[k] = sqrt(sum of the row-block partial sums of squares).
 __device__ __forceinline__ float column_norm(const float* __restrict__ sumsq_part, int row_blocks, int K, int k) {
   float q = 0.f;
@@ -776,9 +911,9 @@ int gccnmf_klnmf_tma_apply_W_mc(gccnmf_handle* h, int F, int T2, float* W, int K
 
 // ---- pull exchange (gccnmf_klnmf_step_pull).  Layout of every rank's symmetric buffer, in floats:
 //   [numerator F*K + K (packed row sums)] x 2 (iteration parity) | [row-sum slots max_slots*K] x 2 | reduced F*K | 64 floats: arrival
-//   counters (u32) 0, 1.  With the cluster-reduced numerator contraction the contraction writes the numerator and G2's epilogue the
+//   counters (u32) 0, 1 | one u32 flag per tile of U.  With the cluster-reduced numerator contraction the contraction writes the numerator and G2's epilogue the
 //   row-sum slots directly; otherwise the pack kernel sums the k-split slabs and the slots into [F*K + K].
-struct PullLayout { int64_t numer[2], rowsum[2], reduced, counters, total; };
+struct PullLayout { int64_t numer[2], rowsum[2], reduced, counters, flags, total; };
 PullLayout pull_layout(int F, int T2, int K) {
   PullLayout l;
   const int64_t fk = (int64_t)F * K, rs = (int64_t)max_rowsum_slots(T2) * K;
@@ -786,7 +921,9 @@ PullLayout pull_layout(int F, int T2, int K) {
   l.rowsum[0] = 2 * (fk + K); l.rowsum[1] = l.rowsum[0] + rs;
   l.reduced = l.rowsum[1] + rs;
   l.counters = l.reduced + fk;
-  l.total = l.counters + 64;
+  l.flags = l.counters + 64;                // one u32 per 32 x 128 tile of U (exchange inside the W update)
+  const int64_t tiles = (int64_t)((F + kApplyTile - 1) / kApplyTile) * ((K + kApplyAtoms - 1) / kApplyAtoms);
+  l.total = l.flags + ((tiles + 63) & ~(int64_t)63);
   return l;
 }
 PeerSet pull_peers(const float* const* bases, int world, const PullLayout& l, int parity, int F, int K, bool packed) {
@@ -810,6 +947,14 @@ tgemm::PeerSignal pull_signal(float* const* bases, int world, const PullLayout& 
 
 int64_t gccnmf_klnmf_tma_pull_floats(int F, int layout_T2, int K) { return pull_layout(F, layout_T2, K).total; }
 bool gccnmf_klnmf_tma_pull_supported(gccnmf_handle* h, int F, int T2, int K) { (void)h; return gccnmf_klnmf_tma_supported(F, T2, K); }
+// form 2 (exchange inside the W update) spins on flags set by the same-tile CTAs of the other ranks: every CTA of the grid must be
+// resident at once
+bool gccnmf_klnmf_tma_pull_fused_ok(gccnmf_handle* h, int F, int K) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tma_apply_w_exchange_kernel, 256, 0) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  const int64_t tiles = (int64_t)((F + kApplyTile - 1) / kApplyTile) * ((K + kApplyAtoms - 1) / kApplyAtoms);
+  return (int64_t)per_sm * h->sm_count >= tiles;
+}
 bool gccnmf_klnmf_tma_pull_direct(gccnmf_handle* h, int F, int T2, int K) { return w_cluster_reduce(h, make_plan(h, F, T2, K), F, K) && !h->pull_force_pack; }
 
 // One sharded iteration with the pull exchange; `bases`: host array of `world` device pointers, each rank's symmetric buffer as mapped
@@ -832,6 +977,29 @@ int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, 
   // direct = the numerator contraction sums its k-splits inside clusters (when every cluster of the launch is resident at once): it
   // writes the numerator, and G2's epilogue the row-sum slots, straight into the symmetric buffer, and its last CTA signals the ranks.
   // Otherwise the pack kernel sums the k-split slabs and the row-sum slots into the buffer and signals.
+  if (two_shot == 2) {
+    if (!gccnmf_klnmf_tma_pull_fused_ok(h, F, K))
+      return gccnmf_fail(h, GCCNMF_ERR_UNSUPPORTED, "klnmf_step_pull: form 2 needs every tile CTA of the W update resident at once");
+    // form 2: the exchange happens inside the W update, tile by tile (tma_apply_w_exchange_kernel): G2 writes its row-sum slots into
+    // the symmetric buffer, the numerator contraction its k-split slabs (or cluster-reduced single slab) as in the single-GPU loop
+    h->xchg_rowsum = local + l.rowsum[parity];
+    int e = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, alpha, eps, workspace, workspace_bytes, iteration > 0 ? 2 : 0, iteration > 0, stream);
+    h->xchg_rowsum = nullptr;
+    if (!e) e = gccnmf_klnmf_tma_partial_W_to(h, V, F, T2, W, H, K, workspace, workspace_bytes, true, nullptr, stream);
+    if (e) return e;
+    PeerSet ps{};
+    tgemm::PeerSignal flags{};
+    ps.world = flags.world = world;
+    for (int r = 0; r < world; ++r) {
+      ps.numer[r] = bases[r] + l.numer[parity];
+      ps.rowsum[r] = bases[r] + l.rowsum[parity];
+      flags.counters[r] = reinterpret_cast<unsigned*>(bases[r] + l.flags);
+    }
+    const dim3 grid((K + kApplyAtoms - 1) / kApplyAtoms, w.row_blocks), block(32, 8);
+    return launch_ex(h, "tma_apply_w_exchange_kernel", tma_apply_w_exchange_kernel, grid, block, 0, stream, h->nmf_pdl, dim3(1, 1, 1), W, w.Wp, w.plane_w,
+                     (const float*)w.partial, w_cluster_reduce(h, p, F, K) ? 1 : p.w.splits, max_rowsum_slots(layout_T2), F, K, w.sumsq_part, w.colsum,
+                     ps, rank, local + l.numer[parity], flags, expected, next_stamp(h));
+  }
   // Every rank must take the same branch (the readers' addresses depend on it): the caller passes the agreed choice.
   const bool direct = want_direct != 0;
   if (direct && !(w_cluster_reduce(h, p, F, K) && !h->pull_force_pack))
@@ -860,6 +1028,7 @@ int gccnmf_klnmf_tma_step_pull(gccnmf_handle* h, const float* V, int F, int T2, 
   }
   const PeerSet peers = pull_peers(bases, world, l, parity, F, K, !direct);
   const int64_t n4 = (int64_t)F * K / 4;
+  (void)n4;
   if (two_shot) {
     const unsigned ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (peers.chunk4 + 255) / 256));
     if (int e = launch_ex(h, "tma_reduce_pull_kernel", tma_reduce_pull_kernel, dim3(ctas), dim3(256), 0, stream, h->nmf_pdl, dim3(1, 1, 1), peers,

@@ -182,7 +182,8 @@ class PullExchange(object):
     """Symmetric buffer (torch symmetric memory: every rank's allocation mapped into every process) for gccnmf_klnmf_step_pull: the
     numerator contraction writes this rank's partial into it and signals every rank; the W updates read the partials (or, two-shot,
     the owners' slice sums) with plain peer loads.  No multicast object, no NCCL call, nothing on the host inside the loop.
-    two_shot: one numerator in each direction per GPU for any world size (default from 4 ranks up); one-shot: world - 1 inbound."""
+    form 0 one-shot (world - 1 numerators inbound per GPU), 1 two-shot (one numerator in each direction for any world size), 2 the
+    exchange inside the W update, tile by tile (no pack kernel, no kernel boundary inside the exchange; world - 1 inbound)."""
 
     def __init__(self, buffer, handle, bases, rank, world, layout_T2, two_shot):
         self.buffer, self.handle, self.bases, self.rank, self.world = buffer, handle, bases, rank, world
@@ -216,8 +217,8 @@ class PullExchange(object):
             hdl.barrier(channel=0, timeout_ms=20000)           # every rank's buffer is zero before anyone signals
             bases = (ctypes.c_void_p * world)(*ptrs)
             if two_shot is None:
-                two_shot = world >= 4
-            return cls(t, hdl, bases, rank, world, layout_T2, bool(two_shot))
+                two_shot = 1 if world >= 4 else 2
+            return cls(t, hdl, bases, rank, world, layout_T2, int(two_shot))
         except Exception as e:                                     # noqa: BLE001  (no symmetric memory / no peer mapping: the caller falls back)
             if os.environ.get('GCCNMF_DEBUG_EXCHANGE'):
                 import traceback
@@ -324,6 +325,12 @@ class ShardedGCCNMFPipeline(object):
             self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
         return int(t.item())
 
+    def _all_and(self, value):
+        t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.h.device)
+        if self.comm.world > 1:
+            self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.BAND, group=self.comm.group)
+        return int(t.item())
+
     def _all_max(self, value):
         t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.h.device)
         if self.comm.world > 1:
@@ -347,24 +354,29 @@ class ShardedGCCNMFPipeline(object):
             # switch from 3 ranks up), pull1 / pull2 (one- / two-shot pull), multimem / multimem1 (two- / one-shot inside the switch), nccl
             mode = os.environ.get('GCCNMF_COLLECTIVE', 'auto')
             if mode == 'auto':
-                mode = 'pull1' if self.comm.world == 2 else 'multimem' 
+                mode = 'pullw' if self.comm.world == 2 else 'multimem' 
             agree = lambda ok: int(self._all_min(1 if ok else 0)) == 1       # noqa: E731
             if mode.startswith('pull'):
                 layout_T2 = int(self._all_max(T2))
                 px = PullExchange.create(self.h.lib, self.F, layout_T2, self.K, self.h.device, self.comm.group,
-                                         two_shot={'pull1': False, 'pull2': True}.get(mode))     # ('pull': by world size)
+                                         two_shot={'pull1': 0, 'pull2': 1, 'pullw': 2}.get(mode))     # ('pull': by world size)
                 level = self.h.lib.gccnmf_klnmf_pull_supported(self.h.h, self.F, T2, self.K) if px is not None else 0
-                level = self._all_min(level)                                  # 0 unsupported somewhere, 1 through the pack kernel, 2 direct
-                if level >= 1:
-                    px.direct = level >= 2
+                level = self._all_and(level)                                  # bits: 1 pull available, 2 direct contraction, 4 form 2
+                if px is not None and px.two_shot == 2 and not level & 4:
+                    px.two_shot = 0
+                if level & 1:
+                    px.direct = bool(level & 2)
                     self.pull = px
                     self.collective = ('pull exchange, %s: %s; %s; no system-scope fence, no multimem, no NCCL call in the loop' % (
-                                           'two-shot' if px.two_shot else 'one-shot',
+                                           {0: 'one-shot', 1: 'two-shot', 2: 'inside the W update'}[px.two_shot],
+                                           'each W-update CTA sums this rank\'s k-split slabs for its tile, publishes it, flags every rank and reads '
+                                           'the same tile of the other ranks' if px.two_shot == 2 else
                                            'the numerator contraction writes its partial into the symmetric buffer and signals every rank from its '
                                            'last CTA' if px.direct else 'the pack kernel sums the k-split slabs into the symmetric buffer and signals '
                                            'every rank',
+                                           'five launches per iteration' if px.two_shot == 2 else
                                            'each rank sums its 1/world slice with plain peer loads, the W updates fetch every word from its owner'
-                                           if px.two_shot else 'the W update reads every rank\'s partial with plain peer loads, added in rank order'))
+                                           if px.two_shot == 1 else 'the W update reads every rank\'s partial with plain peer loads, added in rank order'))
                 else:
                     mode = 'multimem'
             if self.pull is None and mode.startswith('multimem'):

@@ -173,6 +173,9 @@ GCCNMF_API int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int
 /* PULL exchange (the default of the sharded pipeline): nothing is pushed over the links and nothing is reduced in the switch.  The
  * numerator contraction writes this rank's (F, K) partial straight into its symmetric buffer and its last CTA adds 1 to every rank's
  * arrival counter (device-scope fence + relaxed red: the published data is local, peers fetch it through this GPU's L2); then
+ *   two_shot = 2: the exchange happens INSIDE the W update, tile by tile: the CTA that owns a 32 x 128 tile of U sums this rank's
+ *                 k-split slabs for it, publishes the tile in the symmetric buffer, flags it on every rank, waits for the same tile
+ *                 of the other ranks and reads them with plain peer loads -- five launches per iteration, like the single-GPU loop;
  *   two_shot = 0: every rank's W update reads all ranks' partials with plain peer loads, added in rank order;
  *   two_shot = 1: each rank first sums its 1 / world slice that way into its own buffer, signals, and the W updates fetch each word
  *                 from its owner -- one numerator in each direction per GPU for any world size.
@@ -181,10 +184,11 @@ GCCNMF_API int gccnmf_klnmf_step_multimem2(gccnmf_handle* h, const float* V, int
  * largest 2T over the ranks; epoch = iterations earlier runs executed on this buffer: the arrival counters keep counting).  Needs the
  * cluster-reduced numerator contraction for direct = 1 (see gccnmf_klnmf_pull_supported). */
 GCCNMF_API int64_t gccnmf_klnmf_pull_buffer_floats(int F, int layout_T2, int K);
-/* 0: gccnmf_klnmf_step_pull does not cover this shard shape on this device; 1: it does, through the pack kernel (k-split slabs
- * and row-sum slots summed into the symmetric buffer, then the signal); 2: also in the direct form (the numerator contraction sums
- * its k-splits inside clusters, writes the buffer itself and signals from its last CTA).  `direct` of step_pull must be the same
- * on every rank: 1 only if every rank answers 2. */
+/* Bit mask.  0: gccnmf_klnmf_step_pull does not cover this shard shape on this device.  Bit 0: it does, through the pack kernel
+ * (k-split slabs and row-sum slots summed into the symmetric buffer, then the signal).  Bit 1: also in the direct form (the numerator
+ * contraction sums its k-splits inside clusters, writes the buffer itself and signals from its last CTA): `direct` of step_pull must be
+ * the same on every rank, 1 only if every rank has this bit.  Bit 2: form 2 (exchange inside the W update) is available: every tile
+ * CTA of the W update is resident at once. */
 GCCNMF_API int gccnmf_klnmf_pull_supported(gccnmf_handle* h, int F, int T2, int K);
 GCCNMF_API int gccnmf_klnmf_step_pull(gccnmf_handle* h, const float* V, int F, int T2, float* W, float* H, int K,
                            float sparsity_alpha, float epsilon, int iteration, int64_t epoch, int rank, int world,

@@ -40,10 +40,10 @@ def main():
     # one 8-slot record per launch of the exchange kernels: PACK (row sums [+ numerator] -> symmetric buffer, arrival signal),
     # RB (two-shot: slice reduction + multicast), AP (W update)
     extra = {'fused': ['AP'], 'stepwise-no-exchange': ['PACK', 'AP'], 'two-shot': ['PACK', 'RB', 'AP'], 'one-shot': ['PACK', 'AP'],
-             'nccl': ['PACK', 'AP'], 'pull-one-shot': ['AP'], 'pull-two-shot': ['RB', 'AP']}
+             'nccl': ['PACK', 'AP'], 'pull-one-shot': ['AP'], 'pull-two-shot': ['RB', 'AP'], 'pull-in-w-update': ['XW']}
     modes = ['fused', 'stepwise-no-exchange']
     if world > 1:
-        modes += ['pull-one-shot', 'pull-two-shot', 'two-shot', 'one-shot', 'nccl']
+        modes += ['pull-in-w-update', 'pull-one-shot', 'pull-two-shot', 'two-shot', 'one-shot', 'nccl']
     if os.environ.get('STAMP_MODES'):
         modes = [m for m in modes if m in os.environ['STAMP_MODES'].split(',')]
     iters = 24
@@ -51,11 +51,11 @@ def main():
     for mode in modes:
         mm = px = None
         if mode.startswith('pull'):
-            px = gd.PullExchange.create(h.lib, F, T2, K, h.device, None, two_shot=(mode == 'pull-two-shot'))
+            px = gd.PullExchange.create(h.lib, F, T2, K, h.device, None, two_shot={'pull-one-shot': 0, 'pull-two-shot': 1, 'pull-in-w-update': 2}[mode])
             sup = h.lib.gccnmf_klnmf_pull_supported(h.h, F, T2, K)
             if px is not None:
-                px.direct = sup >= 2
-                extra[mode] = (['RB', 'AP'] if px.two_shot else ['AP']) if px.direct else (['PACK', 'RB', 'AP'] if px.two_shot else ['PACK', 'AP'])
+                px.direct = bool(sup & 2)
+                extra[mode] = ['XW'] if px.two_shot == 2 else ((['RB', 'AP'] if px.two_shot else ['AP']) if px.direct else (['PACK', 'RB', 'AP'] if px.two_shot else ['PACK', 'AP']))
             if px is None or sup < 1:
                 if rank == 0:
                     print(mode, ': not available on this box (buffer %s, supported %s)' % (px is not None, sup))
@@ -116,7 +116,7 @@ def main():
                 for name, ctas in grids:
                     k = s[off:off + ctas]
                     off += ctas
-                    if ctas == 1 and name in ('PACK', 'RB', 'AP'):
+                    if ctas == 1 and name in ('PACK', 'RB', 'AP', 'XW'):
                         recs[it, name] = k[0].astype(np.int64)
                         continue
                     k = k[(k[:, 0] > 0) & (k[:, 2] > 0)]
@@ -148,6 +148,15 @@ def main():
                 tl['rb cta0 stored'] = med(lambda i: recs[i, 'RB'][2] - ends[i, 'G4'])
                 tl['rb cta0 fenced'] = med(lambda i: recs[i, 'RB'][3] - ends[i, 'G4'])
                 tl['rb signalled'] = med(lambda i: recs[i, 'RB'][7] - ends[i, 'G4'])
+            if 'XW' in extra[mode]:
+                tl['w update start'] = med(lambda i: recs[i, 'XW'][0] - ends[i, 'G4'])
+                tl['tile published + flagged'] = med(lambda i: recs[i, 'XW'][1] - ends[i, 'G4'])
+                tl['peers tile flagged'] = med(lambda i: recs[i, 'XW'][2] - ends[i, 'G4'])
+                tl['operands in'] = med(lambda i: recs[i, 'XW'][3] - ends[i, 'G4'])
+                tl['cta0 end'] = med(lambda i: recs[i, 'XW'][7] - ends[i, 'G4'])
+                msg += ' | after G4 end: %s' % tl
+                print('rank %d %-22s: %.2f ms per 100 iterations | %s' % (rank, mode, ms100, msg), flush=True)
+                continue
             tl['apply start'] = med(lambda i: recs[i, 'AP'][0] - ends[i, 'G4'])
             tl['apply arrivals seen'] = med(lambda i: recs[i, 'AP'][1] - ends[i, 'G4'])
             tl['apply operands in'] = med(lambda i: recs[i, 'AP'][2] - ends[i, 'G4'])
