@@ -217,7 +217,7 @@ class PullExchange(object):
             hdl.barrier(channel=0, timeout_ms=20000)           # every rank's buffer is zero before anyone signals
             bases = (ctypes.c_void_p * world)(*ptrs)
             if two_shot is None:
-                two_shot = 1 if world >= 4 else 2
+                two_shot = 1 if world >= 4 else 0
             return cls(t, hdl, bases, rank, world, layout_T2, int(two_shot))
         except Exception as e:                                     # noqa: BLE001  (no symmetric memory / no peer mapping: the caller falls back)
             if os.environ.get('GCCNMF_DEBUG_EXCHANGE'):
@@ -325,11 +325,12 @@ class ShardedGCCNMFPipeline(object):
             self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
         return int(t.item())
 
-    def _all_and(self, value):
-        t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.h.device)
+    def _all_and(self, value, bits=8):
+        """Bitwise AND over the ranks (NCCL has no BAND: MIN over the separated bits)."""
+        t = self.torch.tensor([(int(value) >> b) & 1 for b in range(bits)], dtype=self.torch.int32, device=self.h.device)
         if self.comm.world > 1:
-            self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.BAND, group=self.comm.group)
-        return int(t.item())
+            self.comm.dist.all_reduce(t, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+        return sum(int(v) << b for b, v in enumerate(t.tolist()))
 
     def _all_max(self, value):
         t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.h.device)
@@ -354,7 +355,7 @@ class ShardedGCCNMFPipeline(object):
             # switch from 3 ranks up), pull1 / pull2 (one- / two-shot pull), multimem / multimem1 (two- / one-shot inside the switch), nccl
             mode = os.environ.get('GCCNMF_COLLECTIVE', 'auto')
             if mode == 'auto':
-                mode = 'pullw' if self.comm.world == 2 else 'multimem' 
+                mode = 'pull1' if self.comm.world == 2 else 'multimem' 
             agree = lambda ok: int(self._all_min(1 if ok else 0)) == 1       # noqa: E731
             if mode.startswith('pull'):
                 layout_T2 = int(self._all_max(T2))
