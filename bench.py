@@ -30,9 +30,9 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(sampleRate=16000, windowSize=1024, hopSize=256, dictionarySize=1024, numTDOAs=64,
            numIterations=100, microphoneSeparationInMetres=0.1, duration_s=30.0)
-# dram__bytes_read.sum + dram__bytes_write.sum of the six kernels of one KL-NMF iteration (profiles/r01e_ncu_full_nmf_kernels.csv,
-# ncu --set full --cache-control none inside the running loop: 36.0 MB of it is the H update re-reading / writing back H^T)
-NMF_ITERATION_DRAM_BYTES = 36.4e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the five kernels of one KL-NMF iteration (profiles/r02k_ncu_full_nmf_kernels.csv,
+# ncu --set full --cache-control none inside the running loop: 39.4 MB of it is the H update re-reading / writing back G^T)
+NMF_ITERATION_DRAM_BYTES = 39.7e6
 # tensor-core products executed per algorithmic product, averaged over the four contractions of an iteration: (4 + 3 + 4 + 3) / 4
 EXECUTED_PRODUCTS = 3.5
 METRIC = 'STFT frames/sec (1024-FFT, K=1024) full GCC-NMF pipeline'

@@ -45,6 +45,8 @@ int gccnmf_create(gccnmf_handle** out, int device) {
   h->force_simt_nmf = path && strcmp(path, "simt") == 0;
   const char* pdl = getenv("GCCNMF_NMF_PDL");
   h->nmf_pdl = !(pdl && strcmp(pdl, "0") == 0);
+  const char* split2 = getenv("GCCNMF_WH_SPLIT2");
+  if (split2) h->wh_split2 = atoi(split2);
   const char* light = getenv("GCCNMF_MC_LIGHT_SIGNAL");
   if (light) h->mc_light_signal = atoi(light);
   const char* pers = getenv("GCCNMF_ARGMAX_PERSISTENT");
@@ -89,6 +91,7 @@ int gccnmf_set_option(gccnmf_handle* h, const char* name, int value) {
   if (strcmp(name, "gemm_pair") == 0) { h->gemm_pair = value; return GCCNMF_OK; }
   if (strcmp(name, "gemm_streaming") == 0) { h->gemm_streaming = value; return GCCNMF_OK; }
   if (strcmp(name, "argmax_persistent") == 0) { h->argmax_persistent = value != 0; return GCCNMF_OK; }
+  if (strcmp(name, "wh_split2") == 0) { h->wh_split2 = value; return GCCNMF_OK; }
   if (strcmp(name, "w_cluster_reduce") == 0) { h->w_cluster_reduce = value != 0; return GCCNMF_OK; }
   if (strcmp(name, "pull_force_pack") == 0) { h->pull_force_pack = value; return GCCNMF_OK; }
   if (strcmp(name, "mc_light_signal") == 0) { h->mc_light_signal = value; return GCCNMF_OK; }

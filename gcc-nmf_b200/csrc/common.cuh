@@ -21,6 +21,7 @@ struct gccnmf_handle {
   bool argmax_persistent = true; // all-TDOA argmax GEMM as one persistent CTA per SM with double-buffered TMEM accumulators (0: one CTA per tile)
   int gemm_preload = 1;          // plane GEMM epilogues that fetch their global operands during the main loop: bit 0 ratio (W.H), bit 1 H update
   int gemm_pair = -1;            // plane GEMM on cta_group::2 CTA pairs (256-row MMAs): -1 where the call site prefers it, 0 never, 1 wherever possible
+  int wh_split2 = 0;             // W.H contractions as plain 128 x 208 tiles split in two k-halves summed inside (1, 1, 2) clusters (0: dual-N 104-column tiles)
   bool w_cluster_reduce = true;  // W-update numerator: k-splits summed inside (1, 1, splits) clusters through distributed shared memory (0: k-split slabs)
   // set by gccnmf_klnmf_tma_step_pull around the contractions of a sharded iteration (pull exchange): where the row sums of G and the
   // W-update numerator go (this rank's symmetric buffer) and whom the numerator contraction signals when its last CTA is done

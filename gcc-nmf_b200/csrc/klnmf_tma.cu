@@ -791,6 +791,24 @@ TmaWorkspace tma_carve(void* ws, size_t bytes, int F, int T2, int K) {
 
 size_t tma_workspace_bytes(int F, int T2, int K) { return tma_carve(nullptr, 0, F, T2, K).bytes; }
 
+// The W.H contractions (G1, G3) in their second form (option wh_split2): plain 128 x 208 tiles -- three MMAs of N = 208 at ~129 cycles
+// each, 1.86 cycles per column and k-step, where the dual-N loop pays 2 x 171 for 104 columns (3.3) -- with the contraction split in
+// two halves that a (1, 1, 2) cluster sums through distributed shared memory before the (non-linear) ratio epilogue; each CTA of the
+// pair finishes half of the tile's columns.  72 tiles x 2 = 144 CTAs at the headline shape.
+constexpr int kWhSplitTile = 208;
+bool wh_split2(gccnmf_handle* h, int F, int T2, int K) {
+  if (!h->wh_split2 || K < 128) return false;
+  int resident = 0;
+  if (plane_gemm_z_clusters<false, false, EpiRatioPlanes>(h, kWhSplitTile, 2, &resident)) return false;
+  const int tiles = m_tiles_of(F, true) * ((T2 + kWhSplitTile - 1) / kWhSplitTile);
+  return resident >= tiles && 2 * tiles <= h->sm_count;
+}
+int launch_wh(gccnmf_handle* h, const Plan& p, const Operand& Wk, const Operand& HTk, int F, int T2, int K, const EpiRatioPlanes& e, void* stream) {
+  if (wh_split2(h, F, T2, K))
+    return plane_gemm_z_reduce<false, false>(h, kWhSplitTile, Wk, HTk, F, T2, K, 2, e, nullptr, stream, nullptr, nullptr, true);
+  return plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream, false, true);
+}
+
 // Whether the W-update numerator contraction sums its k-splits inside (1, 1, splits) clusters through distributed shared memory
 // (one (F, K) result, no slabs): when every cluster of the launch can be resident at once (GPC sizes decide), else the k-split slabs
 // are written and summed by their consumer as before.
@@ -843,7 +861,7 @@ int gccnmf_klnmf_tma_update_H(gccnmf_handle* h, const float* V, int F, int T2, c
   const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
   {  // G1: RT = split(VT / (U . G^T))
     EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2, true};
-    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream, false, true)) return st;
+    if (int st = launch_wh(h, p, Wk, HTk, F, T2, K, e, stream)) return st;
   }
   if (colsum_state == 0) GCCNMF_LAUNCH(h, tma_colsum_kernel, (K + 127) / 128, 128, 0, stream, W, F, K, w.colsum);
   {  // G2: HT32, HTp = G * (U^T . R) / denom
@@ -868,7 +886,7 @@ int gccnmf_klnmf_tma_partial_W_to(gccnmf_handle* h, const float* V, int F, int T
     const Operand Wk{w.Wp, (int64_t)K, w.plane_w, false};
     const Operand HTk{w.HTp, (int64_t)K, w.plane_ht, false};
     EpiRatioPlanes e{w.VT, w.RTp, w.Fp, w.plane_rt, F, T2, true};
-    if (int st = plane_gemm<false, false>(h, p.bn_wh, Wk, HTk, F, T2, K, 1, true, e, nullptr, stream, false, true)) return st;
+    if (int st = launch_wh(h, p, Wk, HTk, F, T2, K, e, stream)) return st;
   }
   {  // G4: partial[z][f][atom] = sum_t H^T[t][atom] R^T[t][f]
     const Operand HTmn{w.HTp, (int64_t)K, w.plane_ht, true};

@@ -278,7 +278,7 @@ struct PlaneGemmInstance {
     args.A = A.planes; args.a_plane = A.plane; args.lda = A.pitch;
     args.B = B.planes; args.b_plane = B.plane; args.ldb = B.pitch;
     args.timing = timing;
-    args.preload = h->gemm_preload & 1;     // (only epilogues that opt in with kPreloadOperands have the code)
+    args.preload = (g.z_cluster > 1) ? 0 : (h->gemm_preload & 1);     // (only epilogues that opt in with kPreloadOperands have the code)
     // m-fastest (always for a cta_group::2 pair, whose two m tiles must sit next to each other along x): grid (m, n, splits)
     const bool mf = PAIR || g.m_fastest;
     args.m_fastest = mf ? 1 : 0;
@@ -382,12 +382,15 @@ int plane_gemm_z_clusters(gccnmf_handle* h, int bn, int splits, int* out) {
 }
 template <bool A_MN, bool B_MN, class Epi>
 int plane_gemm_z_reduce(gccnmf_handle* h, int bn, const Operand& A, const Operand& B, int M, int N, int Kc, int splits, const Epi& epi,
-                        unsigned long long* timing, void* stream, unsigned* done_counter = nullptr, const tgemm::PeerSignal* signal = nullptr) {
+                        unsigned long long* timing, void* stream, unsigned* done_counter = nullptr, const tgemm::PeerSignal* signal = nullptr,
+                        bool simt_tail = false) {
   GemmShape g{};
   g.M = M; g.N = N; g.Kc = Kc; g.splits = splits; g.m_fastest = false; g.z_cluster = splits;
   if (signal && signal->world > 0) { g.done_counter = done_counter; g.signal = *signal; }
-  g.m_tiles = (M + tgemm::kBM - 1) / tgemm::kBM;
-  g.tail_rows = 0;
+  const int tail = M % tgemm::kBM;
+  const bool use_tail = simt_tail && !A_MN && !B_MN && tail != 0 && tail <= kTailRowsMax && M > tgemm::kBM && (M / tgemm::kBM) * 128 >= bn;
+  g.m_tiles = use_tail ? M / tgemm::kBM : (M + tgemm::kBM - 1) / tgemm::kBM;
+  g.tail_rows = use_tail ? tail : 0;
   g.n_tiles = (N + bn - 1) / bn;
   switch (bn) {
     case 128: return PlaneGemmInstance<128, A_MN, B_MN, 1, 1, Epi>::launch(h, A, B, g, epi, timing, stream);

@@ -85,3 +85,17 @@ def test_klnmf_tile_plan_fills_the_chip(lib):
     # fewer SMs -> the planner may not use more CTAs than a wave when a single-wave choice exists
     assert lib.gccnmf_klnmf_tile_plan(132, 513, 3744, 1024, out) == 0
     assert out[7] <= 132
+
+
+def test_pull_exchange_buffer_layout(lib):
+    """Size of the symmetric buffer of the pull exchange (gccnmf_klnmf_step_pull): 2 x (numerator + packed row sums), 2 x row-sum slots,
+    the slice-owner buffer, the arrival counters and one flag per 32 x 128 tile of U; identical on every rank when built from the largest
+    shard (host logic only)."""
+    F, T2, K = 513, 3744, 1024
+    n = lib.gccnmf_klnmf_pull_buffer_floats(F, T2, K)
+    slots = (T2 + 127) // 128
+    tiles = ((F + 31) // 32) * ((K + 127) // 128)
+    assert n == 2 * (F * K + K) + 2 * slots * K + F * K + 64 + (tiles + 63) // 64 * 64
+    assert lib.gccnmf_klnmf_pull_buffer_floats(F, T2 + 2, K) >= n           # uneven shards: every rank uses the largest 2T
+    assert lib.gccnmf_klnmf_pull_buffer_floats(1025, 4688, 4096) > 3 * 1025 * 4096
+    assert lib.gccnmf_klnmf_pull_buffer_floats(0, T2, K) == 0

@@ -192,28 +192,25 @@ def variants():
     W0, H0 = orc.initKLNMF(F, T2, K)
     W0d, H0d = h.to_device(W0), h.to_device(H0)
     ref = None
-    for wred in (1, 0):
-        for l2 in (0, 1, 2):
-            for stream in ((0,) if wred else (0, 1)):
-                h.set_option('gemm_streaming', stream)
-                h.set_option('w_cluster_reduce', wred)
-                h.set_option('l2_persist', l2)
-                ms = []
-                for rep in range(3):
-                    W, H = W0d.clone(), H0d.clone()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    h.klnmf(V, W, H, iters)
-                    e1.record()
-                    e1.synchronize()
-                    ms.append(e0.elapsed_time(e1))
-                Wn = W.cpu().numpy()
-                if ref is None:
-                    ref = Wn
-                print('w_cluster_reduce %d l2_persist %d streaming %d: %s ms per 100 iterations | rel W vs first variant %.2e finite %s' % (
-                    wred, l2, stream, ['%.2f' % m for m in ms], _rel(Wn, ref), bool(np.isfinite(Wn).all())), flush=True)
+    for split2 in (0, 1, 0, 1):
+        h.set_option('wh_split2', split2)
+        ms = []
+        for rep in range(3):
+            W, H = W0d.clone(), H0d.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            h.klnmf(V, W, H, iters)
+            e1.record()
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        Wn = W.cpu().numpy()
+        if ref is None:
+            ref = Wn
+            Wo, Ho = orc.performKLNMF(V.cpu().numpy(), K, iters, 0, W0=W0, H0=H0)
+        print('wh_split2 %d: %s ms per 100 iterations | rel W vs first variant %.2e, vs oracle %.2e finite %s' % (
+            split2, ['%.2f' % m for m in ms], _rel(Wn, ref), _rel(Wn, Wo), bool(np.isfinite(Wn).all())), flush=True)
+    h.set_option('wh_split2', 0)
     h.set_option('w_cluster_reduce', 1)
-    h.set_option('l2_persist', 0)
     h.set_option('wh_tile', 0)
     h.set_option('gemm_preload', 1)
     h.set_option('gemm_streaming', 0)
@@ -234,6 +231,8 @@ def stamps():
     h.set_option('force_simt_nmf', 0)
     WH = int(os.environ.get('WH_TILE', '128'))
     h.set_option('wh_tile', WH)
+    split2 = int(os.environ.get('WH_SPLIT2', '0'))
+    h.set_option('wh_split2', split2)
     h.set_option('gemm_cluster', int(os.environ.get('GEMM_CLUSTER', '-1')))
     for pdl in (0, 1):
         h.set_option('nmf_pdl', pdl)
@@ -246,7 +245,7 @@ def stamps():
         torch.cuda.synchronize()
         used = h.lib.gccnmf_debug_timing(h.h, None, 1)
         s = buf.cpu().numpy()[:used].reshape(-1, 8)
-        nt = (T2 + WH - 1) // WH
+        nt = 2 * ((T2 + 207) // 208) if split2 else (T2 + WH - 1) // WH
         grids = [('G1', nt * 4, 120), ('G2', 18 * 8, 144), ('G3', nt * 4, 120), ('G4', 3 * 8 * 6, 144), ('W update', 1, 0)] * 3
         off, prev_end = 0, None
         print('pdl=%d: %d CTA records' % (pdl, len(s)))
