@@ -683,22 +683,41 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int cc = c + kWarps * u;
         if (cc < n_valid) loaded[u] = epi.load(m_first, n0 + cc);
       }
+      if (zc > 1) {
+        // sum of the k-splits in split order (the order the W update used for the slabs): the distributed-shared-memory loads of ALL
+        // U columns of a split are issued before the first add (one at a time they cost a remote-SM round trip per column: the
+        // epilogue took 15 k cycles instead of 6 k)
+        float4 sum[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int cc = c + kWarps * u;
-        if (cc < n_valid) {
-          const float* src = tile + (size_t)cc * kBM + 4 * lane;
-          float4 acc;
-          if (zc > 1) {                    // sum of the k-splits in split order (the order the W update used for the slabs)
-            acc = ld_cluster_f32x4(src, 0);
-            for (int r = 1; r < zc; ++r) {
-              const float4 t = ld_cluster_f32x4(src, (uint32_t)r);
-              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            }
-          } else {
-            acc = *reinterpret_cast<const float4*>(src);
+        for (int u = 0; u < U; ++u) {
+          const int cc = c + kWarps * u;
+          const float* src = tile + (size_t)(cc < n_valid ? cc : 0) * kBM + 4 * lane;
+          sum[u] = z == 0 ? *reinterpret_cast<const float4*>(src) : ld_cluster_f32x4(src, 0);
+        }
+        for (int r = 1; r < zc; ++r) {
+          float4 t[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int cc = c + kWarps * u;
+            const float* src = tile + (size_t)(cc < n_valid ? cc : 0) * kBM + 4 * lane;
+            t[u] = r == z ? *reinterpret_cast<const float4*>(src) : ld_cluster_f32x4(src, (uint32_t)r);
           }
-          epi.store(m_first, n0 + cc, acc, loaded[u], zc > 1 ? 0 : z, st);
+#pragma unroll
+          for (int u = 0; u < U; ++u) { sum[u].x += t[u].x; sum[u].y += t[u].y; sum[u].z += t[u].z; sum[u].w += t[u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cc = c + kWarps * u;
+          if (cc < n_valid) epi.store(m_first, n0 + cc, sum[u], loaded[u], 0, st);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cc = c + kWarps * u;
+          if (cc < n_valid) {
+            const float4 acc = *reinterpret_cast<const float4*>(tile + (size_t)cc * kBM + 4 * lane);
+            epi.store(m_first, n0 + cc, acc, loaded[u], z, st);
+          }
         }
       }
     }
