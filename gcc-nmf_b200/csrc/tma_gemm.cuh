@@ -535,12 +535,14 @@ plane_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // this n tile share its columns (tail_cols <= 256 each), each warp takes two columns per step, each lane 8 consecutive k per
       // 16-byte load (hi and lo plane), four k-chunks in flight.  The result of step i stays in lanes 2i / 2i + 1 and the
       // functor runs with one column per lane, so its global loads overlap.
-      // (k-splits summed inside a cluster, z_cluster > 1: the functor is not linear in the accumulator, so split 0 computes the tail
-      // rows over the WHOLE contraction and the other splits skip them)
+      // (k-splits summed inside a cluster, z_cluster > 1: the functor is not linear in the accumulator, so the tail rows are computed
+      // over the WHOLE contraction, each split taking its share of the tile's tail columns)
       const bool z_red = kCluster == 1 && args.z_cluster > 1;
       const int k_begin = z_red ? 0 : kb_begin * KB, k_end = z_red ? args.Kc : min(args.Kc, kb_end * KB);
-      const int c_begin = n0 + tile_m * args.tail_cols, c_end = min(min(args.N, n0 + BN), c_begin + args.tail_cols);
-      for (int m = args.m_tiles * kBM; m < (z_red && z > 0 ? 0 : args.M); ++m) {
+      const int tcols = z_red ? (((args.tail_cols + args.z_cluster - 1) / args.z_cluster) + 1) & ~1 : args.tail_cols;
+      const int c_begin = n0 + (z_red ? tile_m * args.z_cluster + z : tile_m) * tcols;
+      const int c_end = min(min(args.N, n0 + BN), c_begin + tcols);
+      for (int m = args.m_tiles * kBM; m < args.M; ++m) {
         const __nv_bfloat16* a_hi = args.A + (int64_t)m * args.lda;
         const __nv_bfloat16* a_lo = a_hi + args.a_plane;
         float keep = 0.f;
