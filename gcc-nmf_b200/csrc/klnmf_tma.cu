@@ -693,9 +693,10 @@ __global__ void tma_reduce_pull_kernel(PeerSet peers, float* reduced_local, int6
 }
 
 // ------------------------------------------------------------------------------------------------ tile plan
-// Cycles per 16-deep k-step of one CTA, from the CTA stamps (profiles/r02_cta_phase_stamps.md): a tcgen05.mma with M = 128 costs
-// ~128 cycles up to N = 208 (131 / 126 / 129 at N = 128 / 176 / 208) and ~168 at N = 224 / 256 (the rate cuBLAS reaches: 0.745 of
-// nominal); the dual-N loop issues 2 MMAs of N = 2 bn per k-step, the plain loop 3 of N = bn.
+// Cycles per 16-deep k-step of one CTA, from the CTA stamps (profiles/r02_cta_phase_stamps.md): a plain tcgen05.mma with M = 128
+// costs ~128 cycles up to N = 208 (131 / 127 / 129 at N = 128 / 176 / 208) and ~168 at N = 224 / 256; the dual-N loop issues 2 MMAs
+// of N = 2 bn per k-step at ~170 cycles each for bn = 104 and 128 alike (the model below under-estimates bn = 104; the planner's
+// choice is the measured-fastest one either way), the plain loop 3 of N = bn.
 double mma_cycles(int n) { return n <= 208 ? 128.0 : 168.0; }
 double kstep_cycles(int bn, bool dual) { return (dual && 2 * bn <= 256) ? 2.0 * mma_cycles(2 * bn) : 3.0 * mma_cycles(bn); }
 double epilogue_cycles(int bn) { return 1500.0 + 20.0 * bn; }
