@@ -75,7 +75,12 @@ def _worker(rank, world, port, out):
         for i in range(t0, t1):
             y_local[0, (i - t0) * hop:(i - t0) * hop + N] += torch.from_numpy(frames[0, i])
         y_owned = d.overlap_add_seams(comm, y_local, hop * (t1 - t0), N - hop)
-        out[rank] = dict(W=W.numpy().copy(), H=H.numpy().copy(), t=(t0, t1), y=y_owned.numpy().copy())
+        # cross-rank agreement helpers of the sharded pipeline (exchange form, buffer layout): AND over bits via MIN, MAX, MIN
+        import types
+        fake = types.SimpleNamespace(torch=torch, comm=comm, h=types.SimpleNamespace(device='cpu'))
+        agree = (d.ShardedGCCNMFPipeline._all_and(fake, 7 if rank == 0 else 5), d.ShardedGCCNMFPipeline._all_max(fake, 10 + rank),
+                 d.ShardedGCCNMFPipeline._all_min(fake, 3 - rank))
+        out[rank] = dict(W=W.numpy().copy(), H=H.numpy().copy(), t=(t0, t1), y=y_owned.numpy().copy(), agree=agree)
     finally:
         dist.destroy_process_group()
 
@@ -105,6 +110,7 @@ def test_sharded_nmf_and_seams_world2():
         Hs_ref = np.concatenate([Href[:, t0:t1], Href[:, T + t0:T + t1]], axis=1)
         np.testing.assert_allclose(out[r]['H'], Hs_ref, rtol=2e-5, atol=1e-7)
     assert np.array_equal(out[0]['W'], out[1]['W'])
+    assert out[0]['agree'] == out[1]['agree'] == (5, 11, 2)
     N, hop = 16, 4
     frames = np.random.default_rng(1).standard_normal((1, T, N)).astype(np.float32)
     y = np.zeros((1, N + hop * (T - 1)), np.float32)
