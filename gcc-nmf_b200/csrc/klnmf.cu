@@ -453,7 +453,7 @@ int gccnmf_klnmf(gccnmf_handle* h, const float* V, int F, int T2, float* W, floa
     struct WindowGuard { gccnmf_handle* h; ~WindowGuard() { h->l2_window_base = nullptr; h->l2_window_bytes = 0; } } guard{h};
     for (int it = 0; it < iterations; ++it) {
       // colsum(W) comes out of the previous W update; with a fixed dictionary it is computed once
-      // and the H *= norms of :81 stays pending: the next iteration's G1 loader and G2 epilogue apply it
+      // (in the (U, G) gauge nothing is rescaled inside the loop: see klnmf_tma.cu)
       if (int st = gccnmf_klnmf_tma_update_H(h, V, F, T2, W, H, K, sparsity_alpha, epsilon, workspace, workspace_bytes,
                                             it == 0 ? 0 : (update_W ? 2 : 1), update_W && it > 0, stream)) return st;
       if (!update_W) continue;

@@ -827,7 +827,7 @@ bool w_cluster_reduce(gccnmf_handle* h, const Plan& p, int F, int K) {
 
 }  // namespace
 
-// Whether the TMA path supports this problem (else the loader-based path in klnmf_tc.cu / the SIMT path is used).
+// Whether the TMA path supports this problem (else the float32 SIMT path of klnmf.cu is used).
 bool gccnmf_klnmf_tma_supported(int F, int T2, int K) { return K % 8 == 0 && F >= 128 && T2 >= 128 && K >= 32; }
 size_t gccnmf_klnmf_tma_workspace_bytes(int F, int T2, int K) { return tma_workspace_bytes(F, T2, K); }
 

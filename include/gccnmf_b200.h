@@ -103,8 +103,8 @@ GCCNMF_API int gccnmf_istft_ola(gccnmf_handle* h, const float* spec, int batch, 
 
 /* ---- a2: KL-NMF  (gccNMFFunctions.py:69-83) -------------------------------------------------- */
 GCCNMF_API size_t gccnmf_klnmf_workspace_bytes(int F, int T2, int K);
-/* 1 when the contractions of this shape run on tcgen05 (3xTF32, K % 4 == 0, T2 % 4 == 0, F, T2 >= 128),
- * 0 when they run on the float32 SIMT kernels (small or odd shapes, or GCCNMF_NMF_PATH=simt). */
+/* 1 when the contractions of this shape run on tcgen05 (TMA-fed plane GEMM over bf16 hi/lo operand planes: K % 8 == 0, K >= 32,
+ * F, T2 >= 128), 0 when they run on the float32 SIMT kernels (small or odd shapes, or GCCNMF_NMF_PATH=simt). */
 GCCNMF_API int gccnmf_klnmf_uses_tensor_cores(const gccnmf_handle* h, int F, int T2, int K);
 /*
  * V (F, T2) f32 non-negative; W (F, K) and H (K, T2) f32 hold the initial values on entry (the
@@ -224,8 +224,9 @@ GCCNMF_API int gccnmf_tdoa_gccnmf(gccnmf_handle* h, const float* coherence, int 
 
 /*
  * a10 / a11 fast path: argmax over ALL hypothesis TDOAs without materialising (K, D, T) float64.
- * For D in {32, 64} and K % 4 == 0 the contraction runs as a 3xTF32 tcgen05 GEMM whose epilogue keeps the
- * best / second-best value per (atom, frame); every decision whose margin is inside the GEMM's worst-case
+ * For D a power of two in [8, 128], K % 8 == 0, K >= 64 the contraction runs as a tcgen05 GEMM over bf16 hi/lo planes of
+ * Re(C E) (persistent kernel, two TMEM accumulators) whose epilogue keeps the best / second-best value per (atom, frame) and the
+ * candidates within the margin; every decision whose margin is inside the GEMM's worst-case
  * error is recomputed exactly in float64, so the result equals gccnmf_tdoa_gccnmf's argmax (the
  * reference's numpy.argmax on float64) on every input.  Other shapes run the float64 kernel directly.
  * *overflow_flag (device int32, may be NULL) receives the number of refined decisions; if it exceeds
