@@ -68,6 +68,12 @@ GCCNMF_API int64_t gccnmf_launch_count(const gccnmf_handle* h);
  *   "gemm_pair" [-1]            plane GEMM on cta_group::2 CTA pairs: -1 where a call site prefers it, 0 never, 1 wherever possible
  *                               (bit-identical results either way; measured no faster)
  *   "l2_persist" [0]            KL-NMF loop: persisting L2 access-policy window over G^T (1 = float32 master, 2 = master + planes)
+ *   "wh_split2" [0]             W.H contractions as plain 128 x 208 tiles with the contraction split in two halves that a
+ *                               (1, 1, 2) cluster sums through distributed shared memory (measured: parity with the default)
+ *   "w_cluster_reduce" [1]      W-update numerator: k-splits summed inside (1, 1, splits) clusters where every cluster of the
+ *                               launch is resident at once (else k-split slabs)
+ *   "mc_light_signal" [1]       sharded runs: arrival signal as device-scope fence + relaxed red (0: MEMBAR.SYS + release)
+ *   "pull_force_pack" [0]       pull exchange: always through the pack kernel (diagnostics)
  *   "gemm_preload" [1]          bit 0: the W.H ratio epilogue fetches V during the main loop
  *   "gemm_streaming" [0]        st.global.cs / ld.global.cs for the k-split partials of the W-update numerator */
 GCCNMF_API int gccnmf_set_option(gccnmf_handle* h, const char* name, int value);

@@ -99,3 +99,13 @@ def test_pull_exchange_buffer_layout(lib):
     assert lib.gccnmf_klnmf_pull_buffer_floats(F, T2 + 2, K) >= n           # uneven shards: every rank uses the largest 2T
     assert lib.gccnmf_klnmf_pull_buffer_floats(1025, 4688, 4096) > 3 * 1025 * 4096
     assert lib.gccnmf_klnmf_pull_buffer_floats(0, T2, K) == 0
+
+
+def test_documented_options_are_the_accepted_ones():
+    """Every option gccnmf_set_option accepts (csrc/api.cu) is listed in the header's option block, and vice versa."""
+    api = open(os.path.join(ROOT, 'gcc-nmf_b200', 'csrc', 'api.cu')).read()
+    accepted = set(re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', api))
+    hdr = open(os.path.join(ROOT, 'include', 'gccnmf_b200.h')).read()
+    block = hdr[hdr.index('Options (A/B switches'):hdr.index('GCCNMF_API int gccnmf_set_option')]
+    documented = set(re.findall(r'^ \*   "([a-z_0-9]+)"', block, re.M))
+    assert accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
